@@ -1,0 +1,139 @@
+/*
+ * libovk — C ABI of the B200-native (sm_100a) kernels behind OpenVision's ViT image tower and CLIP contrastive loss.
+ *
+ * The reference (zer0int/OpenVision) has no native code and no C-level plugin API: its hot path is the PyTorch module
+ * surface in src/convert_upload/open_clip/{transformer,model,loss}.py, and every FLOP is an ATen/cuBLAS/cuDNN call.
+ * Each entry point below therefore cites the reference call site (file:line, relative to the reference root) whose
+ * ATen dispatch it replaces.  The Python host layer (openvision_b200/) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers, explicit sizes / leading dimensions in ELEMENTS, `void* stream`
+ *     (a cudaStream_t; NULL = legacy default stream).  No torch / C++ types cross the boundary.
+ *   - the caller owns all memory (inputs, outputs, saved-for-backward tensors, workspaces); the library never
+ *     allocates device memory and keeps no pointer after a call returns.
+ *   - kernels are enqueued on `stream`; no call synchronises the device.
+ *   - return value: 0 on success, negative OVK_ERR_* otherwise; ovk_last_error() gives a thread-local message.
+ *   - bf16 = __nv_bfloat16 (IEEE bfloat16, 2 bytes); "f32" = float.
+ *   - requires compute capability 10.x (tcgen05 / TMEM / TMA); anything else returns OVK_ERR_ARCH.
+ */
+#ifndef OVK_H_
+#define OVK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVK_VERSION 100 /* 0.1.0 */
+
+enum {
+  OVK_OK = 0,
+  OVK_ERR_SHAPE = -1, /* unsupported / inconsistent sizes            */
+  OVK_ERR_ALIGN = -2, /* pointer or leading-dimension alignment       */
+  OVK_ERR_ARCH = -3,  /* device is not sm_100                         */
+  OVK_ERR_CUDA = -4,  /* CUDA runtime / driver error (launch, tmap)   */
+  OVK_ERR_NCCL = -5
+};
+
+/* epilogue flags of ovk_gemm_bf16 */
+enum {
+  OVK_EPI_NONE = 0,
+  OVK_EPI_GELU_ERF = 1,   /* nn.GELU()                 transformer.py:232-236 */
+  OVK_EPI_GELU_TANH = 2,  /* nn.GELU(approximate=tanh) text tower act_kwargs  */
+  OVK_EPI_GELU_QUICK = 3, /* QuickGELU                 transformer.py:33-36   */
+  OVK_EPI_ACT_MASK = 3,
+  OVK_EPI_BIAS = 4,
+  OVK_EPI_RESIDUAL = 8 /* C = act(A*B^T + bias) + residual (act is applied before the residual add) */
+};
+
+int ovk_version(void);
+const char* ovk_last_error(void);
+/* 0 when the current device can run the library (compute capability 10.x), OVK_ERR_ARCH otherwise. */
+int ovk_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense projections: C[M,N] = epi(A[M,K] · B[N,K]^T), bf16 operands, fp32 accumulation in TMEM, bf16 output.
+ * Replaces F.linear in nn.MultiheadAttention in_proj / out_proj (transformer.py:225,250-252), mlp.c_fc / c_proj
+ * (transformer.py:232-236,264) and `pooled @ proj` (transformer.py:645-646).  B is the nn.Linear weight layout
+ * [out_features, in_features].  lda/ldb/ldc/ldr in elements, multiples of 8; K, N multiples of 8.  `bias` is f32[N].
+ * `residual` (bf16 [M, ldr]) may alias C (in-place residual stream update).
+ */
+int ovk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                  int K, const float* bias, const void* residual, long long ldr, int flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dimension (biased variance, fp32 statistics), transformer.py:15-30 (LayerNorm /
+ * LayerNormFp32, eps = 1e-6 in this fork, transformer.py:458).  x, y: bf16 [rows, D] with row strides ldx / ldy
+ * (elements, multiples of 8); gamma, beta: f32[D].  mean / rstd: optional f32[rows] saved for the backward pass.
+ * D % 8 == 0, D <= 8192.
+ */
+int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
+                      float* mean, float* rstd, int rows, int D, float eps, void* stream);
+/* dx = LN'(x)·dy ; dgamma/dbeta (f32[D]) are ACCUMULATED atomically (zero them first).  dx may alias dy. */
+int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
+                      const float* mean, const float* rstd, void* dx, long long lddx, float* dgamma, float* dbeta,
+                      int rows, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Patch embedding, transformer.py:469,610-617: Conv2d(3->D, kernel = stride = P, no bias) as an im2col GEMM,
+ * then x = cat([class_embedding, patches]) + positional_embedding.
+ *   ovk_im2col_patches : images [B,3,H,W] (f32 when img_is_f32, else bf16, NCHW contiguous) -> cols bf16 [B*gh*gw, ldc]
+ *                        column order (c, ph, pw) = conv1.weight.reshape(D, 3*P*P); columns [3P², ldc) are zero-filled.
+ *   ovk_embed_assemble : tokens[b,0,:] = cls + pos[0];  tokens[b,1+n,:] = patch[b*N+n,:] + pos[1+n]   (bf16 out)
+ *                        patch: bf16 [B*N, D] (GEMM output); cls f32[D]; pos f32[L,D], L = N+1.
+ */
+int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long ldc, int B, int H, int W, int P,
+                       void* stream);
+int ovk_embed_assemble(const void* patch, const float* cls, const float* pos, void* tokens, int B, int N, int D,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-head self-attention core, nn.MultiheadAttention(need_weights=False, attn_mask=None) between in_proj and
+ * out_proj (transformer.py:225,239-252): O = softmax(Q K^T / sqrt(hd)) V per (batch, head), flash-style with online
+ * softmax (recurrence as in src/models/bpt.py:105-124).
+ *   qkv : bf16 [B, L, 3, H, hd] (= in_proj output [B*L, 3*D], rows q|k|v as in in_proj_weight)
+ *   out : bf16 [B, L, H*hd]
+ *   lse : optional f32 [B, H, L], natural-log sum-exp of the scaled scores (saved for backward)
+ * hd must be 64 in this build.
+ */
+int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pooling head, transformer.py:599-607,638-646.
+ *   ovk_pool_tokens: mode 0 ('avg', OpenVision): pooled[b] = mean(x[b,1:,:]);  mode 1 ('tok'): pooled[b] = x[b,0,:]
+ *                    x bf16 [B,L,D] -> pooled bf16 [B,D]
+ *   ovk_l2_normalize: F.normalize(x, dim=-1) (model.py:267,284), y = x / max(||x||2, eps); x bf16 [rows,E] -> y f32 or bf16
+ */
+int ovk_pool_tokens(const void* x, void* pooled, int B, int L, int D, int mode, void* stream);
+int ovk_l2_normalize(const void* x, void* y, int y_is_f32, float* norms, int rows, int E, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * CLIP contrastive loss, loss.py:102-131 (ClipLoss.get_logits + 2x F.cross_entropy), fused: the N x N logits are
+ * never written to memory.
+ *   z = scale * I_loc · T_all^T   (rows = local images, cols = all texts);  labels: row i <-> column (row_offset + i)
+ *   img_loc : bf16 [n_loc, E]    txt_all : bf16 [n_all, E]
+ *   forward outputs (all f32): row_lse[n_loc], diag[n_loc] (z_ii), and per-column partial statistics of THIS row block
+ *   col_max[n_all], col_sum[n_all] (sum_i exp(z_ij - col_max_j)) so that ranks can combine column LSEs.
+ *   workspace: f32, size from ovk_clip_loss_workspace_floats(n_loc, n_all).
+ */
+long long ovk_clip_loss_workspace_floats(int n_loc, int n_all);
+int ovk_clip_loss_fwd(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E, int row_offset,
+                      float scale, float* row_lse, float* diag, float* col_max, float* col_sum, float* workspace,
+                      void* stream);
+/* G[i,j] = w_row * exp(z_ij - row_lse_i) + w_col * exp(z_ij - col_lse_j) - (w_row + w_col) * [j == row_offset + i],
+ * written as bf16 [n_loc, n_all] (ldg elements).  Also d_scale_partial (f32[1], accumulated) = sum_ij G_ij * z_ij / scale.
+ * The embedding gradients are then two ovk_gemm_* calls: dI = scale * G · T_all, dT = scale * G^T · I_loc. */
+int ovk_clip_loss_grad_logits(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E, int row_offset,
+                              float scale, const float* row_lse, const float* col_lse, float w_row, float w_col,
+                              void* G, long long ldg, float* d_scale_partial, void* stream);
+/* C[M,N] = alpha * A[M,K] · B[K,N]   with B row-major [K,N] (i.e. "NN": dI = s·G·T).        bf16 in, bf16/f32 out */
+int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
+                     int M, int N, int K, float alpha, void* stream);
+/* C[M,N] = alpha * A[K,M]^T · B[K,N] with A, B row-major (i.e. "TN": dT = s·G^T·I, weight gradients dW = dY^T·X). */
+int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
+                     int M, int N, int K, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVK_H_ */

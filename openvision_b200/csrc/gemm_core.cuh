@@ -1,0 +1,181 @@
+// Persistent warp-specialised tcgen05 GEMM main loop shared by every GEMM-shaped kernel in libovk:
+//   D[M,N] (fp32, TMEM) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major)
+// One CTA per SM, 128 x BN output tile, BK = 64 (one 128-byte swizzle atom), 4-stage TMA->smem ring,
+// two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..+31, the hardware's lane-quadrant rule for tcgen05.ld).
+#pragma once
+#include "ptx.cuh"
+
+namespace ovk {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_THREADS = 128;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+
+// C_BYTES: output staging area (TMA store), EPI_BYTES: epilogue scratch (bias tile, column statistics, ...).
+template <int BN, int C_BYTES = 2 * GEMM_BM * 128, int EPI_BYTES = BN * 4>
+struct GemmSmemLayout {
+  static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_B = OFF_A + GEMM_STAGES * GEMM_A_STAGE_BYTES;
+  static constexpr int OFF_C = OFF_B + GEMM_STAGES * B_STAGE_BYTES;  // 2 x [128 rows x 128 B] staging
+  static constexpr int C_STAGE_BYTES = GEMM_BM * 128;
+  static constexpr int OFF_EPI = OFF_C + C_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2]  + tmem base slot
+  static constexpr int NUM_BARS = 2 * GEMM_STAGES + 4;
+  static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+  static constexpr int TMEM_COLS = 2 * BN;        // 256 or 512 (power of two)
+  static_assert(DYN_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
+};
+
+struct GemmTileInfo {
+  int m0, n0;
+};
+
+struct GemmSched {
+  int tiles_m, tiles_n, total;
+  __device__ __forceinline__ GemmSched(int M, int N, int BN) {
+    tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
+    tiles_n = (N + BN - 1) / BN;
+    total = tiles_m * tiles_n;
+  }
+  // n fastest: the CTAs resident at one moment share A row-blocks through L2, B (weights) stays L2-resident.
+  __device__ __forceinline__ GemmTileInfo tile(int t, int BN) const {
+    GemmTileInfo ti;
+    ti.n0 = (t % tiles_n) * BN;
+    ti.m0 = (t / tiles_n) * GEMM_BM;
+    return ti;
+  }
+};
+
+template <int BN, class L_ = GemmSmemLayout<BN>>
+struct GemmCtx {
+  uint8_t* smem;  // 1024-aligned base
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* tmem_full;
+  uint64_t* tmem_empty;
+  uint32_t* tmem_slot;
+  using L = L_;
+  __device__ __forceinline__ explicit GemmCtx(uint8_t* raw) {
+    uintptr_t p = reinterpret_cast<uintptr_t>(raw);
+    p = (p + 1023) & ~static_cast<uintptr_t>(1023);
+    smem = reinterpret_cast<uint8_t*>(p);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+    full = bars;
+    empty = bars + GEMM_STAGES;
+    tmem_full = bars + 2 * GEMM_STAGES;
+    tmem_empty = bars + 2 * GEMM_STAGES + 2;
+    tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_SLOT);
+  }
+  __device__ __forceinline__ uint8_t* a_stage(int s) const { return smem + L::OFF_A + s * GEMM_A_STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* b_stage(int s) const { return smem + L::OFF_B + s * L::B_STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* c_stage(int s) const { return smem + L::OFF_C + s * L::C_STAGE_BYTES; }
+  __device__ __forceinline__ uint8_t* epi_scratch() const { return smem + L::OFF_EPI; }
+};
+
+// Prologue executed by all threads: barrier init, TMEM alloc, descriptor prefetch. Returns TMEM base address.
+template <int BN, class L>
+__device__ __forceinline__ uint32_t gemm_prologue(const GemmCtx<BN, L>& cx, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                                  const CUtensorMap* tmC) {
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0 && lane_id() == 0) {
+    tma_prefetch_desc(tmA);
+    tma_prefetch_desc(tmB);
+    if (tmC) tma_prefetch_desc(tmC);
+  }
+  if (warp == 1 && lane_id() == 0) {
+    for (int i = 0; i < GEMM_STAGES; ++i) {
+      mbar_init(&cx.full[i], 1);
+      mbar_init(&cx.empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&cx.tmem_full[i], 1);
+      mbar_init(&cx.tmem_empty[i], GEMM_EPI_THREADS / 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<L::TMEM_COLS>(cx.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  return *cx.tmem_slot;
+}
+
+template <int BN, class L>
+__device__ __forceinline__ void gemm_teardown(const GemmCtx<BN, L>& cx, uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 2) {
+    tc_fence_after();
+    tmem_dealloc<L::TMEM_COLS>(tmem_base);
+  }
+}
+
+// Warp 0, one elected lane. Streams A/B k-blocks of every tile this CTA owns through the smem ring.
+template <int BN, class L>
+__device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CUtensorMap* tmA, const CUtensorMap* tmB,
+                                              int M, int N, int K) {
+  GemmSched sched(M, N, BN);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
+    GemmTileInfo ti = sched.tile(t, BN);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&cx.empty[stage], phase ^ 1, 1);
+      mbar_arrive_expect_tx(&cx.full[stage], L::STAGE_BYTES);
+      tma_load_2d(cx.a_stage(stage), tmA, &cx.full[stage], kb * GEMM_BK, ti.m0);
+      tma_load_2d(cx.b_stage(stage), tmB, &cx.full[stage], kb * GEMM_BK, ti.n0);
+      if (++stage == GEMM_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  }
+}
+
+// Warp 1, one elected lane. Issues BK/16 tcgen05.mma per k-block into the tile's TMEM accumulator buffer.
+template <int BN, class L>
+__device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32_t tmem_base, int M, int N, int K) {
+  GemmSched sched(M, N, BN);
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+  int stage = 0;
+  uint32_t phase = 0;
+  int it = 0;
+  for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    mbar_wait(&cx.tmem_empty[acc], acc_phase ^ 1, 2);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + acc * BN;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&cx.full[stage], phase, 3);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(cx.a_stage(stage));
+      const uint32_t b_addr = smem_u32(cx.b_stage(stage));
+#pragma unroll
+      for (int k = 0; k < GEMM_BK / 16; ++k) {
+        umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32), idesc,
+                     (kb | k) != 0);
+      }
+      umma_commit(&cx.empty[stage]);
+      if (++stage == GEMM_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    umma_commit(&cx.tmem_full[acc]);
+  }
+}
+
+}  // namespace ovk

@@ -1,0 +1,428 @@
+// Bandwidth-bound kernels of the image tower: LayerNorm (fwd/bwd), im2col for the patch-embedding GEMM,
+// cls/pos assembly, token pooling and L2 normalisation.  All use 128-bit vector loads/stores, one warp per row,
+// warp-shuffle reductions and fp32 statistics.
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace ovk {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// transformer.py:15-30: y = (x - mean) / sqrt(var + eps) * gamma + beta, biased variance, statistics in fp32.
+template <int MAXV>  // vectors (of 8 bf16) per lane; D <= MAXV * 256
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            __nv_bfloat16* __restrict__ y, long long ldy,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ mean_out,
+                                                            float* __restrict__ rstd_out, int rows, int D, float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+  uint4 raw[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    raw[i] = v < nvec ? xr[v] : make_uint4(0, 0, 0, 0);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    float f[8];
+    unpack8(raw[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[j];
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + i * 32 < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  const float rstd = rsqrtf(var + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float f[8];
+      unpack8(raw[i], f);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+      f[0] = fmaf((f[0] - mean) * rstd, g0.x, b0.x);
+      f[1] = fmaf((f[1] - mean) * rstd, g0.y, b0.y);
+      f[2] = fmaf((f[2] - mean) * rstd, g0.z, b0.z);
+      f[3] = fmaf((f[3] - mean) * rstd, g0.w, b0.w);
+      f[4] = fmaf((f[4] - mean) * rstd, g1.x, b1.x);
+      f[5] = fmaf((f[5] - mean) * rstd, g1.y, b1.y);
+      f[6] = fmaf((f[6] - mean) * rstd, g1.z, b1.z);
+      f[7] = fmaf((f[7] - mean) * rstd, g1.w, b1.w);
+      yr[v] = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// g = dy*gamma ; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) ; dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy.
+// Each block handles ROWS_PER_BLOCK consecutive rows; per-block dgamma/dbeta partials live in registers of the
+// owning lane (lane <-> column mapping is fixed), reduced across the block's warps in smem, then one atomicAdd per
+// column per block.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                            const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                            int rows, int D, int rows_per_block) {
+  extern __shared__ float red[];  // [2][D]
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float dg[MAXV][8], db[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+
+  const int row_begin = blockIdx.x * rows_per_block;
+  const int row_end = min(rows, row_begin + rows_per_block);
+  for (int row = row_begin + warp; row < row_end; row += nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
+    const float mu = mean[row], rs = rstd[row];
+    float xh[MAXV][8], g[MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float fx[8], fd[8];
+        unpack8(xr[v], fx);
+        unpack8(dyr[v], fd);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (fx[j] - mu) * rs;
+          g[i][j] = fd[j] * gm[j];
+          s1 += g[i][j];
+          s2 = fmaf(g[i][j], xh[i][j], s2);
+          dg[i][j] = fmaf(fd[j], xh[i][j], dg[i][j]);
+          db[i][j] += fd[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xh[i][j] = g[i][j] = 0.f;
+      }
+    }
+    const float m1 = warp_sum(s1) / static_cast<float>(D);
+    const float m2 = warp_sum(s2) / static_cast<float>(D);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
+        dxr[v] = pack8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[v * 8 + j], dg[i][j]);
+        atomicAdd(&red[D + v * 8 + j], db[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    atomicAdd(&dgamma[i], red[i]);
+    atomicAdd(&dbeta[i], red[D + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// Row r = (b, gy, gx) of `cols` holds conv1's receptive field in the order of conv1.weight.reshape(D, 3*P*P):
+// k = (c*P + ph)*P + pw  <->  images[b, c, gy*P + ph, gx*P + pw].   transformer.py:469,610-612.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ cols,
+                                                     long long ldc, int B, int H, int W, int P) {
+  const int gh = H / P, gw = W / P;
+  const int K = 3 * P * P;
+  const int vec_per_row = static_cast<int>(ldc >> 3);
+  const long long total = static_cast<long long>(B) * gh * gw * vec_per_row;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % vec_per_row);
+    const long long r = idx / vec_per_row;
+    const int gx = static_cast<int>(r % gw);
+    const int gy = static_cast<int>((r / gw) % gh);
+    const int b = static_cast<int>(r / (static_cast<long long>(gw) * gh));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = v * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int pw = k % P;
+        const int ph = (k / P) % P;
+        const int c = k / (P * P);
+        const long long src = ((static_cast<long long>(b) * 3 + c) * H + (gy * P + ph)) * W + (gx * P + pw);
+        val = static_cast<float>(img[src]);
+      }
+      f[j] = val;
+    }
+    *reinterpret_cast<uint4*>(cols + r * ldc + v * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cls / pos assembly
+// transformer.py:615-617: x = cat([class_embedding, patches]) + positional_embedding.
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const __nv_bfloat16* __restrict__ patch,
+                                                             const float* __restrict__ cls, const float* __restrict__ pos,
+                                                             __nv_bfloat16* __restrict__ tokens, int B, int N, int D) {
+  const int L = N + 1;
+  const int dv = D >> 3;
+  const long long total = static_cast<long long>(B) * L * dv;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(idx % dv);
+    const long long bl = idx / dv;
+    const int l = static_cast<int>(bl % L);
+    const long long b = bl / L;
+    float f[8];
+    if (l == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls) + 2 * v);
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls) + 2 * v + 1);
+      f[0] = c0.x; f[1] = c0.y; f[2] = c0.z; f[3] = c0.w; f[4] = c1.x; f[5] = c1.y; f[6] = c1.z; f[7] = c1.w;
+    } else {
+      unpack8(*reinterpret_cast<const uint4*>(patch + (b * N + (l - 1)) * D + v * 8), f);
+    }
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D) + 2 * v);
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D) + 2 * v + 1);
+    f[0] += p0.x; f[1] += p0.y; f[2] += p0.z; f[3] += p0.w; f[4] += p1.x; f[5] += p1.y; f[6] += p1.z; f[7] += p1.w;
+    *reinterpret_cast<uint4*>(tokens + bl * D + v * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ token pooling
+// transformer.py:599-607: 'avg' -> mean over tokens 1..L-1 (cls excluded); 'tok' -> token 0.
+// grid (B, ceil(D/8/32)); block (32, TY): lane <-> one 16-byte column vector, TY row groups reduced through smem.
+constexpr int POOL_TY = 8;
+__global__ void __launch_bounds__(32 * POOL_TY) pool_tokens_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                    __nv_bfloat16* __restrict__ pooled, int L, int D,
+                                                                    int mode) {
+  __shared__ float red[POOL_TY][32][8];
+  const int b = blockIdx.x;
+  const int v = blockIdx.y * 32 + threadIdx.x;
+  const int dv = D >> 3;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * L * D;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (v < dv) {
+    if (mode == 1) {
+      if (threadIdx.y == 0) unpack8(*reinterpret_cast<const uint4*>(xb + v * 8), acc);
+    } else {
+      for (int l = 1 + threadIdx.y; l < L; l += POOL_TY) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(xb + static_cast<long long>(l) * D + v * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (threadIdx.y == 0 && v < dv) {
+    float o[8];
+    const float inv = mode == 1 ? 1.f : 1.f / static_cast<float>(L - 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < POOL_TY; ++t) s += red[t][threadIdx.x][j];
+      o[j] = s * inv;
+    }
+    *reinterpret_cast<uint4*>(pooled + static_cast<long long>(b) * D + v * 8) = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// model.py:267,284: F.normalize(x, dim=-1) = x / max(||x||_2, eps).  One warp per row.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ y,
+                                                           float* __restrict__ norms, int rows, int E, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = E >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * E);
+  float s = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    unpack8(xr[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s = fmaf(f[j], f[j], s);
+  }
+  const float nrm = sqrtf(warp_sum(s));
+  if (lane == 0 && norms) norms[row] = nrm;
+  const float inv = 1.f / fmaxf(nrm, eps);
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    unpack8(xr[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    if (OUT_F32) {
+      float4* yr = reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + static_cast<long long>(row) * E);
+      yr[2 * v] = make_float4(f[0], f[1], f[2], f[3]);
+      yr[2 * v + 1] = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(y) + static_cast<long long>(row) * E)[v] = pack8(f);
+    }
+  }
+}
+
+static int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace ovk
+
+using namespace ovk;
+
+extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long long ldy, const float* gamma,
+                                 const float* beta, float* mean, float* rstd, int rows, int D, float eps, void* stream) {
+  if (rows <= 0 || D <= 0) return set_error(OVK_ERR_SHAPE, "layernorm: empty input");
+  if ((D % 8) || (ldx % 8) || (ldy % 8)) return set_error(OVK_ERR_ALIGN, "layernorm: D, ldx, ldy must be multiples of 8");
+  if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm: D=%d > 2048 not supported", D);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yp = reinterpret_cast<__nv_bfloat16*>(y);
+  if (D <= 256) layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  else if (D <= 512) layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  else if (D <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  else layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
+                                 const float* mean, const float* rstd, void* dx, long long lddx, float* dgamma,
+                                 float* dbeta, int rows, int D, void* stream) {
+  if (rows <= 0 || D <= 0) return set_error(OVK_ERR_SHAPE, "layernorm_bwd: empty input");
+  if ((D % 8) || (ldx % 8) || (lddy % 8) || (lddx % 8))
+    return set_error(OVK_ERR_ALIGN, "layernorm_bwd: D and leading dimensions must be multiples of 8");
+  if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm_bwd: D=%d > 2048 not supported", D);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // ~4 blocks per SM; each block reduces its rows' dgamma/dbeta before touching global atomics
+  int nblocks = num_sms() * 4;
+  int rpb = (rows + nblocks - 1) / nblocks;
+  if (rpb < 8) rpb = 8;
+  nblocks = (rows + rpb - 1) / rpb;
+  const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
+  auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
+  if (D <= 256) layernorm_bwd_kernel<1><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else if (D <= 512) layernorm_bwd_kernel<2><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else if (D <= 1024) layernorm_bwd_kernel<4><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else layernorm_bwd_kernel<8><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long ldc, int B, int H, int W,
+                                  int P, void* stream) {
+  if (B <= 0 || P <= 0 || H % P || W % P) return set_error(OVK_ERR_SHAPE, "im2col: H=%d W=%d not divisible by P=%d", H, W, P);
+  if (ldc % 8 || ldc < 3LL * P * P) return set_error(OVK_ERR_ALIGN, "im2col: ldc must be a multiple of 8 and >= 3*P*P");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * (ldc / 8);
+  const int grid = grid_for(total, 256);
+  if (img_is_f32)
+    im2col_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(images),
+                                              reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P);
+  else
+    im2col_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(images),
+                                                      reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P);
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int ovk_embed_assemble(const void* patch, const float* cls, const float* pos, void* tokens, int B, int N,
+                                  int D, void* stream) {
+  if (B <= 0 || N <= 0 || D <= 0 || D % 8) return set_error(OVK_ERR_SHAPE, "embed_assemble: bad shape B=%d N=%d D=%d", B, N, D);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(B) * (N + 1) * (D / 8);
+  embed_assemble_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(patch), cls, pos,
+                                                             reinterpret_cast<__nv_bfloat16*>(tokens), B, N, D);
+  return check_launch("embed_assemble_kernel");
+}
+
+extern "C" int ovk_pool_tokens(const void* x, void* pooled, int B, int L, int D, int mode, void* stream) {
+  if (B <= 0 || L <= 0 || D <= 0 || D % 8) return set_error(OVK_ERR_SHAPE, "pool_tokens: bad shape");
+  if (mode == 0 && L < 2) return set_error(OVK_ERR_SHAPE, "pool_tokens: avg pooling needs L >= 2");
+  if (mode != 0 && mode != 1) return set_error(OVK_ERR_SHAPE, "pool_tokens: mode must be 0 (avg) or 1 (tok)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(B, (D / 8 + 31) / 32), block(32, POOL_TY);
+  pool_tokens_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                            reinterpret_cast<__nv_bfloat16*>(pooled), L, D, mode);
+  return check_launch("pool_tokens_kernel");
+}
+
+extern "C" int ovk_l2_normalize(const void* x, void* y, int y_is_f32, float* norms, int rows, int E, float eps,
+                                void* stream) {
+  if (rows <= 0 || E <= 0 || E % 8) return set_error(OVK_ERR_SHAPE, "l2_normalize: bad shape");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (rows + 7) / 8;
+  if (y_is_f32)
+    l2_normalize_kernel<true><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, norms, rows, E, eps);
+  else
+    l2_normalize_kernel<false><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), y, norms, rows, E, eps);
+  return check_launch("l2_normalize_kernel");
+}

@@ -1,0 +1,190 @@
+"""Tensor-level wrappers over the libovk C ABI (torch is used for memory and streams only).
+
+Every function takes CUDA tensors, validates dtype / layout, and enqueues exactly the kernels named in its
+docstring on torch's current stream.  Nothing here computes on the CPU or falls back to ATen math.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_GELU_ERF, EPI_GELU_QUICK, EPI_GELU_TANH, EPI_NONE, EPI_RESIDUAL, OvkError
+
+_ACT = {None: EPI_NONE, "none": EPI_NONE, "gelu": EPI_GELU_ERF, "gelu_erf": EPI_GELU_ERF, "gelu_tanh": EPI_GELU_TANH,
+        "quick_gelu": EPI_GELU_QUICK}
+
+launch_count = 0  # number of libovk kernels enqueued since import (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
+    if not t.is_cuda:
+        raise OvkError(f"{name}: expected a CUDA tensor (libovk has no CPU path)")
+    if t.dtype != dtype:
+        raise OvkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise OvkError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
+    if t.stride(-1) != 1:
+        raise OvkError(f"{name}: innermost dimension must be contiguous")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, act: Optional[str] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (kernel: gemm_bf16_kernel, tcgen05).
+
+    `w` has the nn.Linear layout [out_features, in_features]; bias is fp32 [N]; residual may alias `out`."""
+    _require(a, torch.bfloat16, "gemm.a", 2)
+    _require(w, torch.bfloat16, "gemm.w", 2)
+    M, K = a.shape
+    N, K2 = w.shape
+    if K2 != K:
+        raise OvkError(f"gemm: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    else:
+        _require(out, torch.bfloat16, "gemm.out", 2)
+        if tuple(out.shape) != (M, N):
+            raise OvkError("gemm.out has the wrong shape")
+    flags = _ACT[act]
+    if bias is not None:
+        _require(bias, torch.float32, "gemm.bias", 1)
+        if bias.numel() != N:
+            raise OvkError("gemm.bias has the wrong length")
+        flags |= EPI_BIAS
+    ldr = 0
+    if residual is not None:
+        _require(residual, torch.bfloat16, "gemm.residual", 2)
+        if tuple(residual.shape) != (M, N):
+            raise OvkError("gemm.residual has the wrong shape")
+        flags |= EPI_RESIDUAL
+        ldr = residual.stride(0)
+    _lib.call("ovk_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+              _p(residual), ldr, flags, _stream())
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, save_stats: bool = False,
+              out: Optional[torch.Tensor] = None):
+    """LayerNorm over the last dim of x [rows, D] (bf16 in/out, fp32 statistics). Kernel: layernorm_fwd_kernel."""
+    _require(x, torch.bfloat16, "layernorm.x", 2)
+    _require(gamma, torch.float32, "layernorm.gamma", 1)
+    _require(beta, torch.float32, "layernorm.beta", 1)
+    rows, D = x.shape
+    if out is None:
+        out = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _lib.call("ovk_layernorm_fwd", _p(x), x.stride(0), _p(out), out.stride(0), _p(gamma), _p(beta), _p(mean), _p(rstd),
+              rows, D, float(eps), _stream())
+    _count()
+    if save_stats:
+        return out, mean, rstd
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx=None):
+    """dx, and (accumulated) dgamma / dbeta of LayerNorm. Kernel: layernorm_bwd_kernel."""
+    _require(dy, torch.bfloat16, "layernorm_bwd.dy", 2)
+    _require(x, torch.bfloat16, "layernorm_bwd.x", 2)
+    rows, D = x.shape
+    if dx is None:
+        dx = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
+    _lib.call("ovk_layernorm_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(mean), _p(rstd), _p(dx),
+              dx.stride(0), _p(dgamma), _p(dbeta), rows, D, _stream())
+    _count()
+    return dx
+
+
+def im2col_patches(images: torch.Tensor, patch: int, ldc: int) -> torch.Tensor:
+    """images [B,3,H,W] (fp32 or bf16, NCHW contiguous) -> bf16 [B*gh*gw, ldc], columns ordered like
+    conv1.weight.reshape(D, 3*P*P), zero padded to ldc. Kernel: im2col_kernel."""
+    if images.dtype not in (torch.float32, torch.bfloat16):
+        raise OvkError(f"im2col: images must be fp32 or bf16, got {images.dtype}")
+    _require(images, images.dtype, "im2col.images", 4)
+    if not images.is_contiguous():
+        raise OvkError("im2col: images must be NCHW-contiguous")
+    B, C, H, W = images.shape
+    if C != 3:
+        raise OvkError("im2col: expected 3 input channels")
+    rows = B * (H // patch) * (W // patch)
+    cols = torch.empty((rows, ldc), dtype=torch.bfloat16, device=images.device)
+    _lib.call("ovk_im2col_patches", _p(images), int(images.dtype == torch.float32), _p(cols), ldc, B, H, W, patch,
+              _stream())
+    _count()
+    return cols
+
+
+def embed_assemble(patch_tokens: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    """tokens[b,0]=cls+pos[0]; tokens[b,1+n]=patch_tokens[b*N+n]+pos[1+n]  -> bf16 [B, N+1, D]. Kernel: embed_assemble_kernel."""
+    _require(patch_tokens, torch.bfloat16, "embed_assemble.patch", 2)
+    _require(cls, torch.float32, "embed_assemble.cls", 1)
+    _require(pos, torch.float32, "embed_assemble.pos", 2)
+    D = patch_tokens.shape[1]
+    if not patch_tokens.is_contiguous() or not pos.is_contiguous():
+        raise OvkError("embed_assemble: inputs must be contiguous")
+    if patch_tokens.shape[0] != B * N or tuple(pos.shape) != (N + 1, D) or cls.numel() != D:
+        raise OvkError("embed_assemble: shape mismatch")
+    tokens = torch.empty((B, N + 1, D), dtype=torch.bfloat16, device=patch_tokens.device)
+    _lib.call("ovk_embed_assemble", _p(patch_tokens), _p(cls), _p(pos), _p(tokens), B, N, D, _stream())
+    _count()
+    return tokens
+
+
+def attention(qkv: torch.Tensor, B: int, L: int, H: int, hd: int, scale: Optional[float] = None,
+              save_lse: bool = False):
+    """qkv bf16 [B*L, 3*H*hd] (in_proj output) -> bf16 [B*L, H*hd]; optional lse fp32 [B,H,L].
+    Kernel: attention_fwd_kernel (tcgen05 flash attention)."""
+    _require(qkv, torch.bfloat16, "attention.qkv", 2)
+    if not qkv.is_contiguous() or tuple(qkv.shape) != (B * L, 3 * H * hd):
+        raise OvkError(f"attention: qkv must be contiguous [B*L, 3*H*hd], got {tuple(qkv.shape)}")
+    out = torch.empty((B * L, H * hd), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device) if save_lse else None
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    _lib.call("ovk_attention_fwd", _p(qkv), _p(out), _p(lse), B, L, H, hd, float(scale), _stream())
+    _count()
+    return (out, lse) if save_lse else out
+
+
+def pool_tokens(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """x bf16 [B,L,D] -> bf16 [B,D]; mode 'avg' = mean over tokens 1.. (cls excluded), 'tok' = token 0."""
+    _require(x, torch.bfloat16, "pool_tokens.x", 3)
+    if not x.is_contiguous():
+        raise OvkError("pool_tokens: x must be contiguous")
+    B, L, D = x.shape
+    pooled = torch.empty((B, D), dtype=torch.bfloat16, device=x.device)
+    _lib.call("ovk_pool_tokens", _p(x), _p(pooled), B, L, D, {"avg": 0, "tok": 1}[mode], _stream())
+    _count()
+    return pooled
+
+
+def l2_normalize(x: torch.Tensor, out_dtype=torch.float32, eps: float = 1e-12, return_norms: bool = False):
+    """F.normalize(x, dim=-1) for x bf16 [rows,E]; output fp32 or bf16. Kernel: l2_normalize_kernel."""
+    _require(x, torch.bfloat16, "l2_normalize.x", 2)
+    if not x.is_contiguous():
+        raise OvkError("l2_normalize: x must be contiguous")
+    rows, E = x.shape
+    y = torch.empty((rows, E), dtype=out_dtype, device=x.device)
+    norms = torch.empty(rows, dtype=torch.float32, device=x.device) if return_norms else None
+    _lib.call("ovk_l2_normalize", _p(x), _p(y), int(out_dtype == torch.float32), _p(norms), rows, E, float(eps), _stream())
+    _count()
+    return (y, norms) if return_norms else y
