@@ -228,6 +228,116 @@ def case_pool_norm():
     return ok
 
 
+
+def _e2e(cfg_name, batch, check_text=True):
+    import torch
+    import openvision_b200 as ov
+    from oracle import synth, vit_oracle as O
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_state_dict(cfg_name)
+    imgs = synth.make_images(cfg_name, batch)
+    heads = synth.vision_heads(cfg_name)
+    v = cfg["vision"]
+    ref = O.vision_transformer(imgs, sd, heads, pool_type=v["pool_type"], final_ln_after_pool=v["final_ln_after_pool"])
+    ref_n = O.l2_normalize(ref)
+    m = ov.CLIP(cfg["embed_dim"], cfg["vision"], cfg["text"]).cuda().eval()
+    m.load_state_dict(sd)
+    ok = True
+    with torch.no_grad():
+        got = m.encode_image(imgs.cuda()).float().cpu()
+        got_n = m.encode_image(imgs.cuda(), normalize=True).float().cpu()
+    _, bad = _stats(f"e2e {cfg_name} raw", got, ref, 3e-2)
+    err = (got_n - ref_n).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got_n, ref_n, dim=-1).min().item()
+    print(f"[e2e {cfg_name}] normalized max_abs={err:.3e} min_cos={cos:.6f}", flush=True)
+    ok &= err <= 2e-2 and cos >= 0.9995
+    if check_text:
+        t = cfg["text"]
+        text = synth.make_text(cfg_name, batch)
+        if t.get("no_causal_mask", False):
+            tref = O.l2_normalize(O.text_transformer(text, sd, t["heads"], causal=False, pool_type=t["pool_type"],
+                                                     act="tanh" if (t.get("act_kwargs") or {}).get("approximate") == "tanh" else "erf"))
+            with torch.no_grad():
+                tgot = m.encode_text(text.cuda(), normalize=True).float().cpu()
+            terr = (tgot - tref).abs().max().item()
+            tcos = torch.nn.functional.cosine_similarity(tgot, tref, dim=-1).min().item()
+            print(f"[e2e {cfg_name}] text normalized max_abs={terr:.3e} min_cos={tcos:.6f}", flush=True)
+            ok &= terr <= 2e-2 and tcos >= 0.9995
+    return ok
+
+
+def case_e2e_mini():
+    return _e2e("mini-ov", 3) & _e2e("mini-stock", 3)
+
+
+def case_e2e_ti16():
+    return _e2e("Ti16-160", 8)
+
+
+def case_perf_l14():
+    """per-kernel timings at ViT-L/14@224 shapes (batch from OVK_PERF_BATCH, default 256) + whole-tower forward."""
+    import torch
+    from openvision_b200 import ops
+    Bt = int(os.environ.get("OVK_PERF_BATCH", "256"))
+    L, D, H, MLP = 257, 1024, 16, 4096
+    M = Bt * L
+    dev = "cuda"
+    torch.manual_seed(0)
+    x = torch.randn(M, D, device=dev).bfloat16()
+    wqkv = (torch.randn(3 * D, D, device=dev) * 0.03).bfloat16()
+    wo = (torch.randn(D, D, device=dev) * 0.03).bfloat16()
+    w1 = (torch.randn(MLP, D, device=dev) * 0.03).bfloat16()
+    w2 = (torch.randn(D, MLP, device=dev) * 0.03).bfloat16()
+    b3 = torch.randn(3 * D, device=dev)
+    b1 = torch.randn(MLP, device=dev)
+    bD = torch.randn(D, device=dev)
+    g = torch.ones(D, device=dev)
+    qkv = torch.randn(M, 3 * D, device=dev).bfloat16()
+    f = torch.randn(M, MLP, device=dev).bfloat16()
+
+    def timeit(name, fn, flops=None, bytes_=None, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        extra = ""
+        if flops:
+            extra += f" {flops / ms / 1e9:.1f} TFLOP/s"
+        if bytes_:
+            extra += f" {bytes_ / ms / 1e6:.1f} GB/s"
+        print(f"[perf B={Bt}] {name}: {ms:.3f} ms{extra}", flush=True)
+        return ms
+
+    tot = 0.0
+    tot += 2 * timeit("layernorm", lambda: ops.layernorm(x, g, bD, 1e-6), bytes_=2 * M * D * 2)
+    tot += timeit("gemm qkv  (N=3072,K=1024,bias)", lambda: ops.gemm(x, wqkv, bias=b3), flops=2 * M * 3 * D * D)
+    tot += timeit("attention (L=257,H=16)", lambda: ops.attention(qkv, Bt, L, H, 64), flops=4 * Bt * H * L * L * 64)
+    tot += timeit("gemm out  (N=1024,K=1024,bias+res)", lambda: ops.gemm(x, wo, bias=bD, residual=x), flops=2 * M * D * D)
+    tot += timeit("gemm fc1  (N=4096,K=1024,bias+gelu)", lambda: ops.gemm(x, w1, bias=b1, act="gelu"), flops=2 * M * MLP * D)
+    tot += timeit("gemm fc1  (N=4096,K=1024,bias only)", lambda: ops.gemm(x, w1, bias=b1), flops=2 * M * MLP * D) * 0
+    tot += timeit("gemm fc2  (N=1024,K=4096,bias+res)", lambda: ops.gemm(f, w2, bias=bD, residual=x), flops=2 * M * MLP * D)
+    timeit("torch.matmul qkv (cuBLAS, no bias)", lambda: torch.matmul(x, wqkv.t()), flops=2 * M * 3 * D * D)
+    timeit("torch.matmul fc1 (cuBLAS, no bias)", lambda: torch.matmul(x, w1.t()), flops=2 * M * MLP * D)
+    timeit("torch.matmul fc2 (cuBLAS, no bias)", lambda: torch.matmul(f, w2.t()), flops=2 * M * MLP * D)
+    print(f"[perf B={Bt}] per-layer sum {tot:.3f} ms -> 24 layers {24 * tot:.1f} ms -> {Bt / (24 * tot) * 1e3:.0f} img/s (blocks only)", flush=True)
+    # whole tower
+    import openvision_b200 as ov
+    from oracle import synth
+    cfg = synth.CONFIGS["L14-224"]
+    vt = ov.model._build_vision_tower(cfg["embed_dim"], cfg["vision"]).cuda().eval()
+    imgs = torch.randn(Bt, 3, 224, 224, device=dev)
+    with torch.no_grad():
+        ms = timeit("ViT-L/14 tower forward", lambda: vt(imgs), flops=Bt * 162.03e9, iters=5)
+    print(f"[perf B={Bt}] tower: {Bt / ms * 1e3:.0f} img/s", flush=True)
+    return True
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_") and callable(v)}
 
 
