@@ -107,32 +107,6 @@ int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
 int ovk_pool_tokens(const void* x, void* pooled, int B, int L, int D, int mode, void* stream);
 int ovk_l2_normalize(const void* x, void* y, int y_is_f32, float* norms, int rows, int E, float eps, void* stream);
 
-/* ---------------------------------------------------------------------------------------------------------------
- * CLIP contrastive loss, loss.py:102-131 (ClipLoss.get_logits + 2x F.cross_entropy), fused: the N x N logits are
- * never written to memory.
- *   z = scale * I_loc · T_all^T   (rows = local images, cols = all texts);  labels: row i <-> column (row_offset + i)
- *   img_loc : bf16 [n_loc, E]    txt_all : bf16 [n_all, E]
- *   forward outputs (all f32): row_lse[n_loc], diag[n_loc] (z_ii), and per-column partial statistics of THIS row block
- *   col_max[n_all], col_sum[n_all] (sum_i exp(z_ij - col_max_j)) so that ranks can combine column LSEs.
- *   workspace: f32, size from ovk_clip_loss_workspace_floats(n_loc, n_all).
- */
-long long ovk_clip_loss_workspace_floats(int n_loc, int n_all);
-int ovk_clip_loss_fwd(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E, int row_offset,
-                      float scale, float* row_lse, float* diag, float* col_max, float* col_sum, float* workspace,
-                      void* stream);
-/* G[i,j] = w_row * exp(z_ij - row_lse_i) + w_col * exp(z_ij - col_lse_j) - (w_row + w_col) * [j == row_offset + i],
- * written as bf16 [n_loc, n_all] (ldg elements).  Also d_scale_partial (f32[1], accumulated) = sum_ij G_ij * z_ij / scale.
- * The embedding gradients are then two ovk_gemm_* calls: dI = scale * G · T_all, dT = scale * G^T · I_loc. */
-int ovk_clip_loss_grad_logits(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E, int row_offset,
-                              float scale, const float* row_lse, const float* col_lse, float w_row, float w_col,
-                              void* G, long long ldg, float* d_scale_partial, void* stream);
-/* C[M,N] = alpha * A[M,K] · B[K,N]   with B row-major [K,N] (i.e. "NN": dI = s·G·T).        bf16 in, bf16/f32 out */
-int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
-                     int M, int N, int K, float alpha, void* stream);
-/* C[M,N] = alpha * A[K,M]^T · B[K,N] with A, B row-major (i.e. "TN": dT = s·G^T·I, weight gradients dW = dY^T·X). */
-int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
-                     int M, int N, int K, float alpha, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

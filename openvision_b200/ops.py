@@ -18,6 +18,26 @@ _ACT = {None: EPI_NONE, "none": EPI_NONE, "gelu": EPI_GELU_ERF, "gelu_erf": EPI_
 
 launch_count = 0  # number of libovk kernels enqueued since import (bench.py reports it as gpu_launches)
 
+# Optional per-kernel timing hook (bench.py): callable(kind, work) -> context manager that brackets ONE launch with
+# CUDA events on the launching stream.  `work` is the launch's algorithmic FLOPs (tensor kernels) or bytes (bandwidth
+# kernels) as defined in DESIGN.md.  None in normal operation: zero overhead.
+recorder = None
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _Null()
+
+
+def _timed(kind: str, work: float):
+    return recorder(kind, work) if recorder is not None else _NULL
+
 
 def _count(n=1):
     global launch_count
@@ -74,8 +94,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             raise OvkError("gemm.residual has the wrong shape")
         flags |= EPI_RESIDUAL
         ldr = residual.stride(0)
-    _lib.call("ovk_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
-              _p(residual), ldr, flags, _stream())
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+                  _p(residual), ldr, flags, _stream())
     _count()
     return out
 
@@ -93,8 +114,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if save_stats:
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-    _lib.call("ovk_layernorm_fwd", _p(x), x.stride(0), _p(out), out.stride(0), _p(gamma), _p(beta), _p(mean), _p(rstd),
-              rows, D, float(eps), _stream())
+    with _timed("layernorm", 4.0 * rows * D):
+        _lib.call("ovk_layernorm_fwd", _p(x), x.stride(0), _p(out), out.stride(0), _p(gamma), _p(beta), _p(mean),
+                  _p(rstd), rows, D, float(eps), _stream())
     _count()
     if save_stats:
         return out, mean, rstd
@@ -160,7 +182,8 @@ def attention(qkv: torch.Tensor, B: int, L: int, H: int, hd: int, scale: Optiona
     lse = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device) if save_lse else None
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
-    _lib.call("ovk_attention_fwd", _p(qkv), _p(out), _p(lse), B, L, H, hd, float(scale), _stream())
+    with _timed("attention", 4.0 * B * H * L * L * hd):
+        _lib.call("ovk_attention_fwd", _p(qkv), _p(out), _p(lse), B, L, H, hd, float(scale), _stream())
     _count()
     return (out, lse) if save_lse else out
 

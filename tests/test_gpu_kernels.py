@@ -1,0 +1,199 @@
+"""GPU parity tests, kernel by kernel, through the libovk C ABI (openvision_b200.ops -> ctypes -> extern "C").
+The checker is the CPU oracle (oracle/vit_oracle.py restating the reference ops) on the same seeded inputs.
+Tolerance: outputs are bf16 with fp32 accumulation -> max-abs error <= 1e-2 x max|ref| (2e-2 for attention,
+north_star: embeddings max-abs <= 2e-2 in bf16 against fp32); fp32 side outputs (statistics, LSE) <= 1e-3."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openvision_b200 import _lib, ops as _ops
+    lib = _lib.load()
+    assert lib.ovk_device_supported() == 0, lib.ovk_last_error()
+    return _ops
+
+
+def assert_close(got, ref, tol, what=""):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert not torch.isnan(got).any(), f"{what}: NaN in output"
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err <= tol * scale, f"{what}: max-abs err {err:.3e} > {tol} x {scale:.3e}"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+GEMM_CASES = [
+    # M, N, K, flags
+    (128, 256, 64, ""), (128, 256, 256, ""), (512, 512, 256, ""),
+    (808, 576, 192, "b"), (808, 192, 768, "br"), (300, 72, 200, "bg"), (256, 1024, 592, "b"),   # tails: Ti/16, patch K
+    (1024, 1024, 1024, "b"), (1024, 4096, 1024, "bg"), (1024, 1024, 4096, "br"),
+    (128 * 150, 1024, 1024, "br"),                                                               # > 148 tiles: multi-wave
+    (1000, 256, 128, "bt"), (1000, 256, 128, "bq"),                                              # tanh / quick GELU
+    (1, 8, 8, "b"),                                                                               # minimum size
+]
+
+
+@pytest.mark.parametrize("M,N,K,flags", GEMM_CASES)
+def test_gemm_epilogues(ops, M, N, K, flags):
+    a = rnd(M, K, seed=1, scale=0.5).bfloat16()
+    w = rnd(N, K, seed=2, scale=0.5).bfloat16()
+    bias = rnd(N, seed=3) if "b" in flags else None
+    res = rnd(M, N, seed=4).bfloat16() if "r" in flags else None
+    act = {"g": "gelu", "t": "gelu_tanh", "q": "quick_gelu"}.get(next((c for c in flags if c in "gtq"), None))
+    out = ops.gemm(a.cuda(), w.cuda(), bias=None if bias is None else bias.cuda(),
+                   residual=None if res is None else res.cuda(), act=act)
+    ref = a.float() @ w.float().t()                       # F.linear, transformer.py:233-235
+    if bias is not None:
+        ref = ref + bias
+    if act:
+        ref = O.gelu(ref, {"gelu": "erf", "gelu_tanh": "tanh", "quick_gelu": "quick"}[act])
+    if res is not None:
+        ref = ref + res.float()
+    assert_close(out, ref, 1e-2, f"gemm {M}x{N}x{K} '{flags}'")
+
+
+def test_gemm_inplace_residual_stream(ops):
+    M, N, K = 2048, 1024, 1024
+    a = rnd(M, K, seed=1, scale=0.5).bfloat16()
+    w = rnd(N, K, seed=2, scale=0.05).bfloat16()
+    x = rnd(M, N, seed=3).bfloat16()
+    xc = x.cuda()
+    ops.gemm(a.cuda(), w.cuda(), residual=xc, out=xc)
+    assert_close(xc, a.float() @ w.float().t() + x.float(), 1e-2, "in-place residual")
+
+
+def test_gemm_linearity_at_full_size(ops):
+    """Size-independent property at the L/14 fc1 shape (too big for a CPU check): gemm(a1 + a2) == gemm(a1) + gemm(a2)
+    up to bf16 rounding, and a row permutation of A permutes the rows of C bit-exactly."""
+    M, N, K = 32 * 257, 4096, 1024
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a1 = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.03).bfloat16()
+    perm = torch.randperm(M, device="cuda", generator=g)
+    c1 = ops.gemm(a1, w)
+    c2 = ops.gemm(a1[perm].contiguous(), w)
+    assert torch.equal(c1[perm], c2), "row permutation of A must permute C bit-exactly"
+    c3 = ops.gemm((a1.float() * 2).bfloat16(), w)
+    assert_close(c3, c1.float() * 2, 1e-2, "scaling linearity")
+
+
+@pytest.mark.parametrize("rows,D", [(808, 192), (1000, 768), (4096, 1024), (777, 1280), (64, 1152), (1, 8), (33, 2048)])
+def test_layernorm_fwd(ops, rows, D):
+    x = (rnd(rows, D, seed=0) * 2 + 0.5).bfloat16()
+    g, b = rnd(D, seed=1), rnd(D, seed=2)
+    y, mean, rstd = ops.layernorm(x.cuda(), g.cuda(), b.cuda(), 1e-6, save_stats=True)
+    ref = O.layer_norm(x.float(), g, b, 1e-6)
+    assert_close(y, ref, 1e-2, "layernorm y")
+    assert_close(mean, x.float().mean(-1), 1e-4, "layernorm mean")
+    var = x.float().var(-1, unbiased=False)
+    assert_close(rstd, torch.rsqrt(var + 1e-6), 1e-3, "layernorm rstd")
+
+
+@pytest.mark.parametrize("rows,D", [(808, 192), (3000, 768), (4096, 1024), (500, 1280)])
+def test_layernorm_bwd(ops, rows, D):
+    x = (rnd(rows, D, seed=0) * 2 + 0.5).bfloat16()
+    dy = rnd(rows, D, seed=5).bfloat16()
+    g, b = rnd(D, seed=1), rnd(D, seed=2)
+    xc, gc = x.cuda(), g.cuda()
+    _, mean, rstd = ops.layernorm(xc, gc, b.cuda(), 1e-6, save_stats=True)
+    dg = torch.zeros(D, device="cuda")
+    db = torch.zeros(D, device="cuda")
+    dx = ops.layernorm_bwd(dy.cuda(), xc, gc, mean, rstd, dg, db)
+    xf = x.float().requires_grad_(True)
+    gf, bf = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    O.layer_norm(xf, gf, bf, 1e-6).backward(dy.float())
+    assert_close(dx, xf.grad, 1e-2, "ln bwd dx")
+    assert_close(dg, gf.grad, 1e-3, "ln bwd dgamma")
+    assert_close(db, bf.grad, 1e-3, "ln bwd dbeta")
+
+
+@pytest.mark.parametrize("B,H,P,D", [(4, 160, 16, 192), (3, 224, 14, 1024), (2, 48, 16, 128)])
+def test_patch_embed_and_assemble(ops, B, H, P, D):
+    img = rnd(B, 3, H, H, seed=0)
+    wconv = rnd(D, 3, P, P, seed=1, scale=0.05)
+    K = 3 * P * P
+    ldc = (K + 7) // 8 * 8
+    cols = ops.im2col_patches(img.cuda(), P, ldc)
+    gh = H // P
+    ref_cols = img.reshape(B, 3, gh, P, gh, P).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gh, K)
+    assert torch.equal(cols[:, :K].cpu(), ref_cols.bfloat16()), "im2col must be an exact gather + bf16 rounding"
+    assert (cols[:, K:] == 0).all().item()
+    wp = torch.zeros(D, ldc, dtype=torch.bfloat16)
+    wp[:, :K] = wconv.reshape(D, K).bfloat16()
+    tok = ops.gemm(cols, wp.cuda())
+    N = gh * gh
+    cls, pos = rnd(D, seed=2), rnd(N + 1, D, seed=3)
+    x = ops.embed_assemble(tok, cls.cuda(), pos.cuda(), B, N)
+    ref = O.patch_embed(img.bfloat16().float(), wconv.bfloat16().float())        # transformer.py:610-612
+    ref = torch.cat([cls.expand(B, 1, D), ref], 1) + pos                          # :615-617
+    assert_close(x, ref, 1e-2, "patch embed")
+
+
+def _attn_ref(qkv, B, L, H, hd):
+    q, k, v = qkv.float().view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+    p = torch.softmax(s, -1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd), torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 128, 1), (2, 128, 2), (2, 64, 1), (3, 101, 3), (2, 257, 4), (2, 577, 3),
+                                   (1, 16, 1), (1, 200, 2), (1, 1, 1), (2, 129, 2), (1, 8, 16)])
+def test_attention_fwd(ops, B, L, H):
+    hd = 64
+    qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, f"attention B{B} L{L} H{H}")
+    assert_close(lse, lse_ref, 1e-3, "attention lse")
+
+
+def test_attention_large_scores_and_batch_independence(ops):
+    """online-softmax stability with large logits + size-independent property: images do not interact."""
+    B, L, H, hd = 4, 257, 2, 64
+    qkv = (rnd(B * L, 3 * H * hd, seed=7) * 4).bfloat16()
+    out = ops.attention(qkv.cuda(), B, L, H, hd)
+    ref, _ = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, "attention large scores")
+    one = ops.attention(qkv[L:2 * L].contiguous().cuda(), 1, L, H, hd)
+    assert torch.equal(one, out[L:2 * L]), "per-image results must not depend on the batch they are computed in"
+
+
+def test_pool_and_normalize(ops):
+    x = rnd(5, 257, 1024, seed=0).bfloat16()
+    p = ops.pool_tokens(x.cuda(), "avg")
+    assert_close(p, x.float()[:, 1:].mean(1), 1e-2, "pool avg")                  # transformer.py:599-607
+    assert torch.equal(ops.pool_tokens(x.cuda(), "tok").cpu(), x[:, 0])
+    e = (rnd(100, 768, seed=1) * 3).bfloat16()
+    y, n = ops.l2_normalize(e.cuda(), return_norms=True)
+    assert_close(y, O.l2_normalize(e.float()), 1e-5, "l2 normalize fp32")
+    assert_close(n, e.float().norm(dim=-1), 1e-5, "norms")
+    yb = ops.l2_normalize(e.cuda(), out_dtype=torch.bfloat16)
+    assert_close(yb, O.l2_normalize(e.float()), 1e-2, "l2 normalize bf16")
+    z = torch.zeros(8, 64, dtype=torch.bfloat16, device="cuda")                   # eps clamp: 0 / max(0, eps) = 0
+    assert torch.equal(ops.l2_normalize(z), torch.zeros(8, 64, device="cuda"))
+
+
+def test_error_paths_return_codes_not_crashes(ops):
+    from openvision_b200._lib import OvkError
+    a = torch.zeros(16, 12, dtype=torch.bfloat16, device="cuda")     # K = 12 is not a multiple of 8
+    w = torch.zeros(8, 12, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(OvkError):
+        ops.gemm(a, w)
+    with pytest.raises(OvkError):
+        ops.gemm(a.cpu(), w.cpu())
+    with pytest.raises(OvkError):
+        ops.attention(torch.zeros(4, 3 * 48, dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 48)   # hd = 48 unsupported

@@ -1,0 +1,125 @@
+"""GPU parity of the drop-in module surface against (a) the committed outputs of the unmodified reference
+(tests/golden) and (b) the CPU oracle on the same seeded inputs.  Bar (north_star): L2-normalised embeddings
+cosine >= 0.9995 and max-abs <= 2e-2 in bf16 against fp32; loss within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import openvision_b200 as ovb
+from oracle import synth, vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def build(cfg_name):
+    cfg = synth.CONFIGS[cfg_name]
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(synth.make_state_dict(cfg_name, 0), strict=True)
+    return m.cuda().eval()
+
+
+def check_embeddings(got, ref, what):
+    got = got.float().cpu()
+    ref = torch.as_tensor(ref).float()
+    err = (got - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1).min().item()
+    assert err <= 2e-2 and cos >= 0.9995, f"{what}: max-abs {err:.3e}, min cosine {cos:.6f}"
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("mini-ov", 4), ("mini-stock", 4), ("Ti16-160", 8)])
+def test_encode_image_and_text_match_reference_golden(golden, cfg_name, batch):
+    g = golden(f"tower_{cfg_name}.npz")
+    m = build(cfg_name)
+    images = synth.make_images(cfg_name, batch, 0).cuda()
+    text = synth.make_text(cfg_name, batch, 0).cuda()
+    with torch.no_grad():
+        img_n = m.encode_image(images, normalize=True)
+        raw = m.encode_image(images)
+        check_embeddings(img_n, g["image_features_norm"], f"{cfg_name} image")
+        ref_raw = torch.as_tensor(g["image_features"]).float()
+        assert (raw.float().cpu() - ref_raw).abs().max().item() <= 3e-2 * ref_raw.abs().max().item()
+        if synth.CONFIGS[cfg_name]["text"].get("no_causal_mask", False):
+            txt_n = m.encode_text(text, normalize=True)
+            check_embeddings(txt_n, g["text_features_norm"], f"{cfg_name} text")
+            i2, t2, s = m(images, text)
+            assert abs(float(s) - float(g["logit_scale_exp"])) < 1e-4
+            check_embeddings(i2, g["image_features_norm"], "forward image")
+            check_embeddings(t2, g["text_features_norm"], "forward text")
+
+
+def test_piecewise_calls_like_ov_zero_shot(golden):
+    """ov-zero-shot-test.py:103-126 calls conv1 / ln_pre / transformer / ln_post / proj one by one."""
+    cfg_name, batch = "Ti16-160", 8
+    g = golden(f"tower_{cfg_name}.npz")
+    m = build(cfg_name)
+    v = m.visual
+    images = synth.make_images(cfg_name, batch, 0).cuda()
+    with torch.no_grad():
+        x = v.conv1(images)
+        assert x.shape == (batch, 192, 10, 10)
+        x = x.reshape(x.shape[0], x.shape[1], -1).permute(0, 2, 1)
+        x = torch.cat([v.class_embedding.to(x.dtype) + torch.zeros(x.shape[0], 1, x.shape[-1], dtype=x.dtype, device=x.device), x], dim=1)
+        x = x + v.positional_embedding.to(x.dtype)
+        x = v.ln_pre(x)
+        x = v.transformer(x)
+        pooled = x[:, 1:].mean(dim=1)
+        pooled = v.ln_post(pooled)
+        feats = pooled @ v.proj
+    feats = torch.nn.functional.normalize(feats.float(), dim=-1)
+    check_embeddings(feats, g["image_features_norm"], "piecewise tower")
+
+
+def test_gelu_forward_hooks_fire_with_reference_activations(golden):
+    """cliptoolsoptimized.py:1149-1164 hangs forward hooks on every nn.GELU; outputs must be the [B, L, mlp] tensors."""
+    cfg_name, batch = "mini-ov", 4
+    g = golden(f"tower_{cfg_name}.npz")
+    m = build(cfg_name)
+    taps = {}
+    hooks = [blk.mlp.gelu.register_forward_hook(lambda mod, i, o, k=k: taps.__setitem__(k, o.detach()))
+             for k, blk in enumerate(m.visual.transformer.resblocks)]
+    with torch.no_grad():
+        out_hooked = m.encode_image(synth.make_images(cfg_name, batch, 0).cuda(), normalize=True)
+    for h in hooks:
+        h.remove()
+    assert sorted(taps) == [0, 1]
+    ref0 = torch.as_tensor(g["gelu_block0"]).float()
+    assert tuple(taps[0].shape) == tuple(ref0.shape)
+    err = (taps[0].float().cpu() - ref0).abs().max().item()
+    assert err <= 2e-2 * ref0.abs().max().item(), err
+    check_embeddings(out_hooked, g["image_features_norm"], "hooked path")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16", "pure_bf16", "amp_fp16"])
+def test_precision_modes_of_the_surface(golden, prec):
+    """factory.py:275-297 precision modes: fp32 weights, 'bf16' (convert_weights_to_lp), pure bf16, fp16 autocast."""
+    cfg_name, batch = "mini-ov", 4
+    g = golden(f"tower_{cfg_name}.npz")
+    m = build(cfg_name)
+    images = synth.make_images(cfg_name, batch, 0).cuda()
+    with torch.no_grad():
+        if prec == "bf16":
+            ovb.convert_weights_to_lp(m, torch.bfloat16)
+            out = m.encode_image(images.bfloat16(), normalize=True)
+        elif prec == "pure_bf16":
+            m = m.to(torch.bfloat16)
+            out = m.encode_image(images.bfloat16(), normalize=True)
+        elif prec == "amp_fp16":
+            with torch.autocast("cuda", dtype=torch.float16):
+                out = m.encode_image(images, normalize=True)
+        else:
+            out = m.encode_image(images, normalize=True)
+    check_embeddings(out, g["image_features_norm"], prec)
+
+
+def test_batch_shard_independence_full_config():
+    """Size-independent property at a real config (B/16@384, 577 tokens): encoding a batch equals encoding its shards
+    (the data-parallel split of SURVEY.md §8e) bit-exactly."""
+    cfg = synth.CONFIGS["B16-384"]
+    torch.manual_seed(0)
+    v = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"]).cuda().eval()
+    images = torch.randn(6, 3, 384, 384, device="cuda")
+    with torch.no_grad():
+        full = v(images)
+        parts = torch.cat([v(images[:2]), v(images[2:])])
+    assert torch.isfinite(full).all()
+    assert torch.equal(full, parts)

@@ -1,0 +1,93 @@
+"""CPU: host logic of the drop-in module surface — constructor arguments, attribute names and state_dict contract of
+the reference, loud failure without a GPU, and that the product never imports the oracle."""
+import os
+import re
+
+import pytest
+import torch
+from torch import nn
+
+import openvision_b200 as ovb
+from openvision_b200._lib import OvkError
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build(cfg_name):
+    cfg = synth.CONFIGS[cfg_name]
+    return ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+
+
+@pytest.mark.parametrize("cfg_name", ["mini-ov", "mini-stock", "Ti16-160"])
+def test_state_dict_contract(cfg_name):
+    cfg = synth.CONFIGS[cfg_name]
+    model = build(cfg_name)
+    want = dict(synth.vision_shapes(cfg["vision"], cfg["embed_dim"]))
+    want.update(synth.text_shapes(cfg["text"], cfg["embed_dim"]))
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == {k: tuple(v) for k, v in want.items()}
+    # loads the synthetic checkpoint with strict key matching, as a released OpenVision checkpoint would
+    model.load_state_dict(synth.make_state_dict(cfg_name, 0), strict=True)
+
+
+def test_attributes_the_scripts_touch():
+    m = build("mini-ov")
+    v = m.visual
+    for a in ("conv1", "class_embedding", "positional_embedding", "patch_dropout", "ln_pre", "transformer", "attn_pool",
+              "ln_post", "proj", "image_size", "patch_size", "grid_size", "pool_type", "final_ln_after_pool",
+              "output_dim", "output_tokens"):
+        assert hasattr(v, a), a
+    assert isinstance(v.ln_pre, nn.Identity) and v.attn_pool is None
+    blk = v.transformer.resblocks[-1]
+    for a in ("ln_1", "attn", "ls_1", "ln_2", "mlp", "ls_2"):
+        assert hasattr(blk, a)
+    assert isinstance(blk.attn, nn.MultiheadAttention)        # convert_weights_to_lp contract, model.py:405-409
+    assert isinstance(blk.mlp.gelu, nn.GELU)                  # ov-feature-visualization hooks isinstance(m, GELU)
+    assert blk.mlp.c_proj.in_features == 512                  # ov-feature-visualization.py:150-155
+    assert len(v.transformer.resblocks) == 2
+    assert m.logit_scale.shape == () and abs(float(m.logit_scale) - 2.659260) < 1e-5
+    assert v.transformer.get_cast_dtype() == torch.float32
+    for meth in ("encode_image", "encode_text", "get_logits", "forward", "lock_image_tower", "set_grad_checkpointing"):
+        assert callable(getattr(m, meth))
+
+
+def test_convert_weights_to_lp_keeps_layernorm_fp32():
+    m = build("mini-ov")
+    ovb.convert_weights_to_lp(m, torch.bfloat16)
+    blk = m.visual.transformer.resblocks[0]
+    assert blk.attn.in_proj_weight.dtype == torch.bfloat16 and blk.mlp.c_fc.weight.dtype == torch.bfloat16
+    assert m.visual.proj.dtype == torch.bfloat16 and m.visual.conv1.weight.dtype == torch.bfloat16
+    assert blk.ln_1.weight.dtype == torch.float32
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    m = build("mini-ov").eval()
+    with pytest.raises(OvkError):
+        m.encode_image(torch.zeros(1, 3, 48, 48))
+    with pytest.raises(OvkError):
+        m.visual.ln_post(torch.zeros(2, 128))
+    with pytest.raises(OvkError):
+        m.visual.transformer(torch.zeros(1, 10, 128))
+
+
+def test_lock_image_tower_and_gelu_hook_detection():
+    m = build("mini-ov")
+    m.lock_image_tower()
+    assert all(not p.requires_grad for p in m.visual.parameters())
+    blk = m.visual.transformer.resblocks[0]
+    assert blk._fusable()
+    h = blk.mlp.gelu.register_forward_hook(lambda mod, i, o: None)
+    assert not blk._fusable()          # hooks on nn.GELU force the module-by-module path so the hook fires
+    h.remove()
+    assert blk._fusable()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "openvision_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+                assert "vit_oracle" not in src, f"{f} references the oracle"
