@@ -43,7 +43,8 @@ enum {
   OVK_EPI_GELU_QUICK = 3, /* QuickGELU                 transformer.py:33-36   */
   OVK_EPI_ACT_MASK = 3,
   OVK_EPI_BIAS = 4,
-  OVK_EPI_RESIDUAL = 8 /* C = act(A*B^T + bias) + residual (act is applied before the residual add) */
+  OVK_EPI_RESIDUAL = 8,    /* C = A*B^T + bias + residual (not combined with an activation) */
+  OVK_EPI_SAVE_PREACT = 16 /* with an activation: also store the pre-activation A*B^T + bias (saved for backward) */
 };
 
 int ovk_version(void);
@@ -60,6 +61,20 @@ int ovk_device_supported(void);
  */
 int ovk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
                   int K, const float* bias, const void* residual, long long ldr, int flags, void* stream);
+/* Same, plus OVK_EPI_SAVE_PREACT: `preact` (bf16 [M, ldp]) receives A*B^T + bias before the activation — what the
+ * backward of mlp.c_fc -> gelu (transformer.py:232-236) needs. */
+int ovk_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                     int K, const float* bias, const void* residual, long long ldr, void* preact, long long ldp,
+                     int flags, void* stream);
+/* Backward GEMMs (what autograd derives from F.linear): operands are read in place, nothing is transposed in memory.
+ *   ovk_gemm_bf16_nn : C[M,N] = alpha * A[M,K] * B[K,N]      (B row-major [K,N])   dX = dY * W
+ *                      optional fused GELU backward: C = alpha * (A*B) (.) act'(preact), preact bf16 [M, ldp], act = OVK_EPI_GELU_*
+ *   ovk_gemm_bf16_tn : C[M,N] = alpha * A[K,M]^T * B[K,N]    (A, B row-major)      dW = dY^T * X
+ * C is bf16 or (c_is_f32) fp32.  lda/ldb/ldc in elements; M (tn), N multiples of 8. */
+int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
+                     int M, int N, int K, float alpha, const void* preact, long long ldp, int act, void* stream);
+int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
+                     int M, int N, int K, float alpha, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (biased variance, fp32 statistics), transformer.py:15-30 (LayerNorm /

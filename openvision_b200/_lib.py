@@ -19,6 +19,7 @@ EPI_GELU_TANH = 2
 EPI_GELU_QUICK = 3
 EPI_BIAS = 4
 EPI_RESIDUAL = 8
+EPI_SAVE_PREACT = 16
 
 
 class OvkError(RuntimeError):
@@ -34,6 +35,12 @@ _PROTOTYPES = {
     "ovk_device_supported": (c_int, []),
     "ovk_gemm_bf16": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_gemm_bf16_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_gemm_bf16_nn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_gemm_bf16_tn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_int, c_float, c_void_p]),
     "ovk_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_float, c_void_p]),
     "ovk_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,174 +1,286 @@
-// ovk_gemm_bf16: C[M,N] (bf16) = epilogue( A[M,K] * B[N,K]^T ) on tcgen05 tensor cores.
+// ovk_gemm_*: C[M,N] = epilogue( alpha * op(A) * op(B) ) on tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM.
 // Replaces the reference's F.linear / addmm call sites (open_clip/transformer.py:225,233-235,250-252 via
-// nn.MultiheadAttention in_proj/out_proj and mlp.c_fc/c_proj) with fused bias / exact-erf GELU / residual epilogues.
+// nn.MultiheadAttention in_proj/out_proj and mlp.c_fc/c_proj, :645-646 pooled @ proj) and, in the backward pass, the
+// dgrad / wgrad matmuls autograd derives from them, with fused bias / GELU / residual / GELU' epilogues.
 #include "gemm_core.cuh"
 #include "host_utils.h"
 
 namespace ovk {
 
-// gelu(x) = x * Phi(x), exact-erf form (nn.GELU() default, transformer.py:234; JAX approximate=False vit.py:198-202).
-// erfc via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), branch-free, 2 MUFU + ~14 FMA-pipe ops.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float u = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(t, p, 1.421413741f);
-  p = fmaf(t, p, -0.284496736f);
-  p = fmaf(t, p, 0.254829592f);
-  p *= t;
-  const float e = fast_exp2(x * x * -0.72134752044448170f);  // exp(-x^2/2)
-  const float q = 0.5f * p * e;                                // = 0.5*erfc(|x|/sqrt2) = Phi(-|x|)
-  const float xq = x * q;
-  return x >= 0.f ? x - xq : xq;
-}
-// QuickGELU: x * sigmoid(1.702 x) (transformer.py:33-36), only when quick_gelu=True.
-__device__ __forceinline__ float gelu_quick(float x) { return x * __frcp_rn(1.0f + fast_exp2(x * -2.4554669595930157f)); }
-// tanh-approximate GELU (text tower act_kwargs={'approximate':'tanh'}).
-__device__ __forceinline__ float gelu_tanh(float x) {
-  const float k = 0.7978845608028654f * (x + 0.044715f * x * x * x);
-  // tanh(k) = 1 - 2/(1+exp(2k))
-  const float th = 1.0f - 2.0f * __frcp_rn(1.0f + fast_exp2(k * 2.8853900817779268f));
-  return 0.5f * x * (1.0f + th);
+// Activations of the reference surface in ONE functional form:  act(x) = x * sigmoid(2 q(x)),
+//   q(x) = xc (a0 + a1 xc^2 + a2 xc^4), xc = clamp(x, -8, 8)
+//   nn.GELU() exact-erf (transformer.py:232-236, JAX approximate=False vit.py:198-202): Phi(x) = sigmoid(2 atanh(erf(x/sqrt2)))
+//       with the odd function atanh(erf(x/sqrt2)) fitted by a0..a2 below: |act - gelu_erf| <= 3.0e-5 for all x
+//       (an order of magnitude below bf16 rounding of the output).
+//   nn.GELU(approximate='tanh') (text tower act_kwargs): exact, a = (sqrt(2/pi), 0.044715 sqrt(2/pi), 0).
+//   QuickGELU x*sigmoid(1.702x) (transformer.py:33-36): exact, a = (0.851, 0, 0).
+// sigmoid(2q) = 1 / (1 + 2^(t)), t = -2 log2(e) q  -> one ex2 + one rcp (MUFU) and 6 FMA-pipe ops per element.
+struct ActCoef {
+  float b0, b1, b2;  // t(x)  = xc (b0 + b1 x2 + b2 x2^2),  b_i = -2 log2(e) a_i
+  float d0, d1, d2;  // 2q'(x) = d0 + d1 x2 + d2 x2^2,      d = (2 a0, 6 a1, 10 a2)   (0 outside the clamp)
+};
+
+static ActCoef act_coef(int act) {
+  double a0 = 0, a1 = 0, a2 = 0;
+  if (act == OVK_EPI_GELU_ERF) {
+    a0 = 0.7974584707815301, a1 = 0.03705034510095251, a2 = -0.0003587323612208004;
+  } else if (act == OVK_EPI_GELU_TANH) {
+    a0 = 0.7978845608028654, a1 = 0.7978845608028654 * 0.044715;
+  } else if (act == OVK_EPI_GELU_QUICK) {
+    a0 = 0.851;
+  }
+  const double c = -2.0 * 1.4426950408889634;
+  ActCoef k;
+  k.b0 = (float)(c * a0), k.b1 = (float)(c * a1), k.b2 = (float)(c * a2);
+  k.d0 = (float)(2 * a0), k.d1 = (float)(6 * a1), k.d2 = (float)(10 * a2);
+  return k;
 }
 
-template <int BN>
+__device__ __forceinline__ float act_fwd(float x, const ActCoef& k) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  const float t = xc * fmaf(fmaf(k.b2, x2, k.b1), x2, k.b0);
+  return x * fast_rcp(1.f + fast_exp2(t));
+}
+// d/dx [x sigmoid(2q(x))] = s (1 + x (1 - s) 2q'(x)),  1 - s = e s
+__device__ __forceinline__ float act_bwd(float x, const ActCoef& k) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  const float t = xc * fmaf(fmaf(k.b2, x2, k.b1), x2, k.b0);
+  const float e = fast_exp2(t);
+  const float s = fast_rcp(1.f + e);
+  const float qp = (fabsf(x) < 8.f) ? fmaf(fmaf(k.d2, x2, k.d1), x2, k.d0) : 0.f;
+  return s * fmaf(x * qp, e * s, 1.f);
+}
+
+enum { EPI_LINEAR = 0, EPI_ACT = 1, EPI_DACT = 2 };
+
+struct GemmEpi {
+  const float* bias;  // f32[N] or null
+  float alpha;
+  int flags;          // OVK_EPI_BIAS | OVK_EPI_RESIDUAL | act id | OVK_EPI_SAVE_PREACT
+  ActCoef act;
+};
+
+// EPI_LINEAR: C = alpha*acc + bias (+ R)                   R  = residual tile [M,N] bf16 (tmR), may alias C
+// EPI_ACT   : C = act(acc + bias), optionally D = acc+bias  D  = saved pre-activation (tmD) for the backward pass
+// EPI_DACT  : C = alpha*acc * act'(R)                       R  = saved pre-activation
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
-                 const __nv_bfloat16* residual, long long ldr, int M, int N, int K, int flags) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                 const __grid_constant__ CUtensorMap tmD, const GemmEpi ep, int M, int N, int K) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using L = GemmSmemLayout<BN>;
   GemmCtx<BN, L> cx(smem_raw);
-  const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, &tmC);
+  const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, &tmC, &tmR);
   const int warp = threadIdx.x >> 5;
 
   if (warp == 0) {
-    if (elect_one()) gemm_producer(cx, &tmA, &tmB, M, N, K);
+    if (elect_one()) gemm_producer<BN, A_MN, B_MN>(cx, &tmA, &tmB, M, N, K);
   } else if (warp == 1) {
-    if (elect_one()) gemm_mma_issuer(cx, tmem_base, M, N, K);
-  } else if (warp >= 4) {
+    if (elect_one()) gemm_mma_issuer<BN, A_MN, B_MN>(cx, tmem_base, M, N, K);
+  } else if (warp >= GEMM_CTRL_WARPS) {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> smem -> TMA store
-    const int ew = warp - 4;            // TMEM lane quadrant
-    const int et = threadIdx.x - 128;   // 0..127 = row inside the tile
+    constexpr int CW = OUT_F32 ? 32 : 64;         // columns per staged chunk (one 128-byte row)
+    constexpr int GROUP_COLS = BN / 2;
+    constexpr int NCHUNK = GROUP_COLS / CW;
+    const int ew = warp - GEMM_CTRL_WARPS;
+    const int grp = ew >> 2;                       // column half of the tile
+    const int quad = ew & 3;                       // TMEM lane quadrant
     const uint32_t lane = lane_id();
-    float* bias_s = reinterpret_cast<float*>(cx.epi_scratch());
+    const int et = quad * 32 + lane;               // row inside the tile, thread index inside the group
+    const bool leader = et == 0;
+    const uint32_t bar_id = 1 + grp;
+    const uint32_t sbuf = smem_u32(cx.c_stage(grp));
+    const uint32_t bias_base = smem_u32(cx.epi_scratch());
+    uint64_t* rbar = &cx.aux[grp];
+    uint32_t rphase = 0;
+    const bool has_bias = (ep.flags & OVK_EPI_BIAS) != 0;
+    const bool has_res = !OUT_F32 && (EPI == EPI_DACT || (EPI == EPI_LINEAR && (ep.flags & OVK_EPI_RESIDUAL) != 0));
+    const bool save_pre = EPI == EPI_ACT && (ep.flags & OVK_EPI_SAVE_PREACT) != 0;
+    const float alpha = ep.alpha;
     GemmSched sched(M, N, BN);
-    const bool has_bias = (flags & OVK_EPI_BIAS) != 0;
-    const bool has_res = (flags & OVK_EPI_RESIDUAL) != 0;
-    const int act = flags & OVK_EPI_ACT_MASK;
     int it = 0;
-    uint32_t chunk_ctr = 0;
     for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
       const GemmTileInfo ti = sched.tile(t, BN);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // bias tile -> smem (visible after the barrier below)
-      for (int j = et; j < BN; j += GEMM_EPI_THREADS) {
-        const int n = ti.n0 + j;
-        bias_s[j] = (has_bias && n < N) ? bias[n] : 0.f;
+      // bias tile -> smem (double-buffered by tile parity; the 256-thread barrier publishes it)
+      const uint32_t bias_s = bias_base + (it & 1) * (BN * 4);
+      {
+        const int j = threadIdx.x - 32 * GEMM_CTRL_WARPS;
+        if (j < BN) {
+          const int n = ti.n0 + j;
+          sts_f32(bias_s + j * 4, (has_bias && n < N) ? ep.bias[n] : 0.f);
+        }
       }
-      named_bar_sync(1, GEMM_EPI_THREADS);
+      named_bar_sync(3, GEMM_EPI_THREADS);
       mbar_wait(&cx.tmem_full[acc], acc_phase, 4);
       tc_fence_after();
-      const int row = ti.m0 + et;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + grp * GROUP_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c, ++chunk_ctr) {
-        const int ncol0 = ti.n0 + c * 64;
-        if (ncol0 >= N) {  // whole chunk out of range (uniform across the CTA): still release TMEM on the last chunk
-          if (c == BN / 64 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&cx.tmem_empty[acc]);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int col_in_tile = grp * GROUP_COLS + c * CW;
+        const int ncol0 = ti.n0 + col_in_tile;
+        const bool live = ncol0 < N;  // uniform across the group
+        if (live) {
+          // the staging buffer is free once the previous TMA store has finished reading it
+          if (leader) tma_store_wait_read<0>();
+          named_bar_sync(bar_id, GEMM_GROUP_THREADS);
+          if (has_res && leader) {
+            mbar_arrive_expect_tx(rbar, GEMM_BM * 128);
+            tma_load_2d(cx.c_stage(grp), &tmR, rbar, ncol0, ti.m0);
           }
-          continue;
         }
-        uint4 res[8];
-        if (has_res) {
-          const bool rok = row < M;
-          const uint4* rp = reinterpret_cast<const uint4*>(residual + static_cast<long long>(row) * ldr + ncol0);
+        uint32_t v[CW];
+        if (live) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            res[j] = (rok && ncol0 + j * 8 < N) ? rp[j] : make_uint4(0, 0, 0, 0);
+          for (int q = 0; q < CW / 32; ++q) {
+            uint32_t(&vq)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32 * q]);
+            tmem_ld_x32(taddr + c * CW + 32 * q, vq);
           }
-        }
-        uint32_t v[64];
-        {
-          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-          tmem_ld_x32(taddr + c * 64, v0);
-          tmem_ld_x32(taddr + c * 64 + 32, v1);
           tmem_ld_wait();
         }
-        if (c == BN / 64 - 1) {  // accumulator fully drained into registers: hand the buffer back to the MMA warp
+        if (c == NCHUNK - 1) {  // accumulator drained into registers: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&cx.tmem_empty[acc]);
         }
-        uint32_t packed[32];
+        if (!live) continue;
+        float x[CW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x0 = __uint_as_float(v[2 * j]) + bias_s[c * 64 + 2 * j];
-          float x1 = __uint_as_float(v[2 * j + 1]) + bias_s[c * 64 + 2 * j + 1];
-          if (act == OVK_EPI_GELU_ERF) {
-            x0 = gelu_erf(x0);
-            x1 = gelu_erf(x1);
-          } else if (act == OVK_EPI_GELU_TANH) {
-            x0 = gelu_tanh(x0);
-            x1 = gelu_tanh(x1);
-          } else if (act == OVK_EPI_GELU_QUICK) {
-            x0 = gelu_quick(x0);
-            x1 = gelu_quick(x1);
-          }
-          if (has_res) {
-            const uint32_t rv = reinterpret_cast<const uint32_t*>(res)[j];
-            x0 += bf16_lo(rv);
-            x1 += bf16_hi(rv);
-          }
-          packed[j] = pack_bf16x2(x0, x1);
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 b = lds_f32x4(bias_s + (col_in_tile + 4 * j) * 4);
+          x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), alpha, b.x);
+          x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b.y);
+          x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b.z);
+          x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b.w);
         }
-        // staging buffer (c & 1): wait until the TMA store issued two chunks ago has finished reading it
-        uint8_t* sbuf = cx.c_stage(chunk_ctr & 1);
-        if (et == 0) tma_store_wait_read<1>();
-        named_bar_sync(1, GEMM_EPI_THREADS);
+        if constexpr (EPI == EPI_ACT) {
+          if (save_pre) {  // pre-activation out first (same staging buffer), then the activation
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          *reinterpret_cast<uint4*>(sbuf + sw128_offset(et, j)) =
-              make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              sts128(sbuf + sw128_offset(et, j), make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                                            pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7])));
+            fence_proxy_async_smem();
+            named_bar_sync(bar_id, GEMM_GROUP_THREADS);
+            if (leader) {
+              tma_store_2d(&tmD, cx.c_stage(grp), ncol0, ti.m0);
+              tma_store_commit();
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) x[j] = act_fwd(x[j], ep.act);
+          if (save_pre) {
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(bar_id, GEMM_GROUP_THREADS);
+          }
+        }
+        if constexpr (!OUT_F32) if (has_res) {
+          mbar_wait(rbar, rphase, 5);
+          rphase ^= 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 r = lds128(sbuf + sw128_offset(et, j));
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float r0 = bf16_lo(rw[q]), r1 = bf16_hi(rw[q]);
+              if constexpr (EPI == EPI_DACT) {
+                x[8 * j + 2 * q] *= act_bwd(r0, ep.act);
+                x[8 * j + 2 * q + 1] *= act_bwd(r1, ep.act);
+              } else {
+                x[8 * j + 2 * q] += r0;
+                x[8 * j + 2 * q + 1] += r1;
+              }
+            }
+          }
+        }
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(sbuf + sw128_offset(et, j), make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                                          __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(sbuf + sw128_offset(et, j), make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                                                          pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7])));
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, GEMM_EPI_THREADS);
-        if (et == 0) {
-          tma_store_2d(&tmC, sbuf, ncol0, ti.m0);
+        named_bar_sync(bar_id, GEMM_GROUP_THREADS);
+        if (leader) {
+          tma_store_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
           tma_store_commit();
         }
       }
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (leader) tma_store_wait_all<0>();
   }
   gemm_teardown(cx, tmem_base);
 }
 
-template <int BN>
-static int launch_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
-                       int K, const float* bias, const void* residual, long long ldr, int flags, cudaStream_t stream) {
+// ------------------------------------------------------------------------------------------------ host side
+struct GemmArgs {
+  const void* A; long long lda; bool a_mn;   // a_mn: A stored [K, M] (M contiguous)
+  const void* B; long long ldb; bool b_mn;   // b_mn: B stored [K, N] (N contiguous); else [N, K]
+  void* C; long long ldc; bool c_f32;
+  const void* R; long long ldr;              // residual / saved pre-activation (bf16 [M, ldr]) or null
+  void* D; long long ldd;                    // pre-activation output (bf16) or null
+  int M, N, K;
+  GemmEpi ep;
+  int epi;
+};
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   using L = GemmSmemLayout<BN>;
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmR, tmD;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, GEMM_BK, GEMM_BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, GEMM_BK, BN))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmC, C, N, M, ldc, 64, GEMM_BM))) return rc;
+  if (A_MN) rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, g.lda, 64, 64);
+  else rc = make_tmap_2d_bf16(&tmA, g.A, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
+  if (rc) return rc;
+  if (B_MN) rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, g.ldb, 64, 64);
+  else rc = make_tmap_2d_bf16(&tmB, g.B, g.K, g.N, g.ldb, GEMM_BK, BN);
+  if (rc) return rc;
+  if (OUT_F32) rc = make_tmap_2d_f32(&tmC, g.C, g.N, g.M, g.ldc, 32, GEMM_BM);
+  else rc = make_tmap_2d_bf16(&tmC, g.C, g.N, g.M, g.ldc, 64, GEMM_BM);
+  if (rc) return rc;
+  tmR = tmC;
+  tmD = tmC;
+  if (g.R && (rc = make_tmap_2d_bf16(&tmR, g.R, g.N, g.M, g.ldr, 64, GEMM_BM))) return rc;
+  if (g.D && (rc = make_tmap_2d_bf16(&tmD, g.D, g.N, g.M, g.ldd, 64, GEMM_BM))) return rc;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(
-      tmA, tmB, tmC, bias, reinterpret_cast<const __nv_bfloat16*>(residual), ldr, M, N, K, flags);
+  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K);
   return check_launch("gemm_bf16_kernel");
+}
+
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static int launch_gemm_bn(const GemmArgs& g, cudaStream_t s) {
+  if (g.N <= 128) return launch_gemm_t<128, A_MN, B_MN, EPI, OUT_F32>(g, s);
+  return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32>(g, s);
+}
+
+static int check_common(const GemmArgs& g, const char* who) {
+  if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(OVK_ERR_SHAPE, "%s: empty problem M=%d N=%d K=%d", who, g.M, g.N, g.K);
+  if ((g.lda % 8) || (g.ldb % 8) || (g.ldc % (g.c_f32 ? 4 : 8)))
+    return set_error(OVK_ERR_ALIGN, "%s: leading dimensions must be multiples of 16 bytes (TMA strides)", who);
+  if (!g.a_mn && (g.K % 8)) return set_error(OVK_ERR_ALIGN, "%s: K must be a multiple of 8", who);
+  if (g.a_mn && (g.M % 8)) return set_error(OVK_ERR_ALIGN, "%s: M must be a multiple of 8 for a transposed A", who);
+  if (!g.b_mn && (g.K % 8)) return set_error(OVK_ERR_ALIGN, "%s: K must be a multiple of 8", who);
+  if (g.N % 8) return set_error(OVK_ERR_ALIGN, "%s: N must be a multiple of 8", who);
+  if (g.R && (g.ldr % 8)) return set_error(OVK_ERR_ALIGN, "%s: ldr must be a multiple of 8", who);
+  if (g.D && (g.ldd % 8)) return set_error(OVK_ERR_ALIGN, "%s: ldd must be a multiple of 8", who);
+  return OVK_OK;
 }
 
 }  // namespace ovk
@@ -178,13 +290,63 @@ using namespace ovk;
 extern "C" int ovk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M,
                              int N, int K, const float* bias, const void* residual, long long ldr, int flags,
                              void* stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return set_error(OVK_ERR_SHAPE, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (K % 8) || (N % 8))
-    return set_error(OVK_ERR_ALIGN, "gemm: lda/ldb/ldc/K/N must be multiples of 8 elements (16 B TMA strides)");
-  if ((flags & OVK_EPI_RESIDUAL) && (residual == nullptr || (ldr % 8)))
-    return set_error(OVK_ERR_ALIGN, "gemm: residual epilogue needs a pointer and ldr %% 8 == 0");
+  return ovk_gemm_bf16_ex(A, lda, B, ldb, C, ldc, M, N, K, bias, residual, ldr, nullptr, 0, flags, stream);
+}
+
+extern "C" int ovk_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                int M, int N, int K, const float* bias, const void* residual, long long ldr,
+                                void* preact, long long ldp, int flags, void* stream) {
+  GemmArgs g{A, lda, false, B, ldb, false, C, ldc, false, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  const int act = flags & OVK_EPI_ACT_MASK;
+  if ((flags & OVK_EPI_RESIDUAL) && residual == nullptr) return set_error(OVK_ERR_SHAPE, "gemm: residual flag without pointer");
   if ((flags & OVK_EPI_BIAS) && bias == nullptr) return set_error(OVK_ERR_SHAPE, "gemm: bias flag without pointer");
+  if ((flags & OVK_EPI_SAVE_PREACT) && (preact == nullptr || act == 0))
+    return set_error(OVK_ERR_SHAPE, "gemm: SAVE_PREACT needs an activation and an output pointer");
+  if (act && (flags & OVK_EPI_RESIDUAL)) return set_error(OVK_ERR_SHAPE, "gemm: activation + residual in one epilogue is not supported");
+  g.ep.bias = bias;
+  g.ep.alpha = 1.f;
+  g.ep.flags = flags;
+  g.ep.act = act_coef(act);
+  if (flags & OVK_EPI_RESIDUAL) g.R = residual, g.ldr = ldr;
+  if (flags & OVK_EPI_SAVE_PREACT) g.D = preact, g.ldd = ldp;
+  int rc = check_common(g, "gemm");
+  if (rc) return rc;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (N <= 128) return launch_gemm<128>(A, lda, B, ldb, C, ldc, M, N, K, bias, residual, ldr, flags, s);
-  return launch_gemm<256>(A, lda, B, ldb, C, ldc, M, N, K, bias, residual, ldr, flags, s);
+  if (act) return launch_gemm_bn<false, false, EPI_ACT, false>(g, s);
+  return launch_gemm_bn<false, false, EPI_LINEAR, false>(g, s);
+}
+
+extern "C" int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                int c_is_f32, int M, int N, int K, float alpha, const void* preact, long long ldp,
+                                int act, void* stream) {
+  GemmArgs g{A, lda, false, B, ldb, true, C, ldc, c_is_f32 != 0, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  g.ep.bias = nullptr;
+  g.ep.alpha = alpha;
+  g.ep.flags = 0;
+  g.ep.act = act_coef(act & OVK_EPI_ACT_MASK);
+  if (preact) {
+    if (c_is_f32) return set_error(OVK_ERR_SHAPE, "gemm_nn: the act' epilogue writes bf16");
+    if (!(act & OVK_EPI_ACT_MASK)) return set_error(OVK_ERR_SHAPE, "gemm_nn: preact given without an activation id");
+    g.R = preact, g.ldr = ldp;
+  }
+  int rc = check_common(g, "gemm_nn");
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (preact) return launch_gemm_bn<false, true, EPI_DACT, false>(g, s);
+  if (c_is_f32) return launch_gemm_bn<false, true, EPI_LINEAR, true>(g, s);
+  return launch_gemm_bn<false, true, EPI_LINEAR, false>(g, s);
+}
+
+extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                int c_is_f32, int M, int N, int K, float alpha, void* stream) {
+  GemmArgs g{A, lda, true, B, ldb, true, C, ldc, c_is_f32 != 0, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  g.ep.bias = nullptr;
+  g.ep.alpha = alpha;
+  g.ep.flags = 0;
+  g.ep.act = act_coef(0);
+  int rc = check_common(g, "gemm_tn");
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (c_is_f32) return launch_gemm_bn<true, true, EPI_LINEAR, true>(g, s);
+  return launch_gemm_bn<true, true, EPI_LINEAR, false>(g, s);
 }

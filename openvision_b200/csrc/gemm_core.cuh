@@ -1,9 +1,13 @@
 // Persistent warp-specialised tcgen05 GEMM main loop shared by every GEMM-shaped kernel in libovk:
-//   D[M,N] (fp32, TMEM) = A[M,K] (bf16, K-major) * B[N,K]^T (bf16, K-major)
+//   D[M,N] (fp32, TMEM) = A[M,K] (bf16) * B[N,K]^T (bf16)
+// Each operand may be K-major (rows of K, what nn.Linear weights and activations are) or MN-major (stored transposed:
+// [K rows][M or N contiguous]) — the latter is what the backward GEMMs need (dX = dY*W reads W as [N(red), K(out)],
+// dW = dY^T*X reads both operands with the token dimension outermost), so nothing is ever transposed in memory.
 // One CTA per SM, 128 x BN output tile, BK = 64 (one 128-byte swizzle atom), 4-stage TMA->smem ring,
 // two TMEM accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..+31, the hardware's lane-quadrant rule for tcgen05.ld).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warp 3 idle, warps 4..11 = epilogue:
+// two groups of four warps, group g owns columns [g*BN/2, (g+1)*BN/2) of the tile, warp w reads TMEM lanes
+// 32*(w%4)..+31 (the hardware's lane-quadrant rule for tcgen05.ld).
 #pragma once
 #include "ptx.cuh"
 
@@ -12,26 +16,30 @@ namespace ovk {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_EPI_THREADS = 128;
+constexpr int GEMM_CTRL_WARPS = 4;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 32 * (GEMM_CTRL_WARPS + GEMM_EPI_WARPS);  // 384
+constexpr int GEMM_EPI_THREADS = 32 * GEMM_EPI_WARPS;                  // 256
+constexpr int GEMM_GROUP_THREADS = 128;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+constexpr int GEMM_PANEL_BYTES = 64 * 128;                 // MN-major panel: 64 k-rows x 128 B
 
 // C_BYTES: output staging area (TMA store), EPI_BYTES: epilogue scratch (bias tile, column statistics, ...).
-template <int BN, int C_BYTES = 2 * GEMM_BM * 128, int EPI_BYTES = BN * 4>
+template <int BN, int C_BYTES = 2 * GEMM_BM * 128, int EPI_BYTES = 2 * BN * 4>
 struct GemmSmemLayout {
   static constexpr int B_STAGE_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int OFF_A = 0;
   static constexpr int OFF_B = OFF_A + GEMM_STAGES * GEMM_A_STAGE_BYTES;
-  static constexpr int OFF_C = OFF_B + GEMM_STAGES * B_STAGE_BYTES;  // 2 x [128 rows x 128 B] staging
+  static constexpr int OFF_C = OFF_B + GEMM_STAGES * B_STAGE_BYTES;  // [128 rows x 128 B] staging buffers
   static constexpr int C_STAGE_BYTES = GEMM_BM * 128;
   static constexpr int OFF_EPI = OFF_C + C_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
-  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2]  + tmem base slot
-  static constexpr int NUM_BARS = 2 * GEMM_STAGES + 4;
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], aux[2]  + tmem base slot
+  static constexpr int NUM_BARS = 2 * GEMM_STAGES + 6;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
-  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+  static constexpr int DYN_BYTES = TOTAL;  // the dynamic smem window starts 1024-byte aligned (checked in GemmCtx)
   static constexpr int TMEM_COLS = 2 * BN;        // 256 or 512 (power of two)
   static_assert(DYN_BYTES <= 232448, "exceeds 227 KB of dynamic shared memory");
 };
@@ -63,17 +71,21 @@ struct GemmCtx {
   uint64_t* empty;
   uint64_t* tmem_full;
   uint64_t* tmem_empty;
+  uint64_t* aux;  // two spare barriers for the epilogue groups (residual / auxiliary tile loads)
   uint32_t* tmem_slot;
   using L = L_;
   __device__ __forceinline__ explicit GemmCtx(uint8_t* raw) {
-    uintptr_t p = reinterpret_cast<uintptr_t>(raw);
-    p = (p + 1023) & ~static_cast<uintptr_t>(1023);
-    smem = reinterpret_cast<uint8_t*>(p);
+    if ((smem_u32(raw) & 1023u) != 0) {  // SWIZZLE_128B tiles need 1024-byte aligned bases
+      if (threadIdx.x == 0) printf("[ovk] gemm: dynamic smem base not 1024-byte aligned\n");
+      __trap();
+    }
+    smem = raw;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
     full = bars;
     empty = bars + GEMM_STAGES;
     tmem_full = bars + 2 * GEMM_STAGES;
     tmem_empty = bars + 2 * GEMM_STAGES + 2;
+    aux = bars + 2 * GEMM_STAGES + 4;
     tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_SLOT);
   }
   __device__ __forceinline__ uint8_t* a_stage(int s) const { return smem + L::OFF_A + s * GEMM_A_STAGE_BYTES; }
@@ -85,12 +97,13 @@ struct GemmCtx {
 // Prologue executed by all threads: barrier init, TMEM alloc, descriptor prefetch. Returns TMEM base address.
 template <int BN, class L>
 __device__ __forceinline__ uint32_t gemm_prologue(const GemmCtx<BN, L>& cx, const CUtensorMap* tmA, const CUtensorMap* tmB,
-                                                  const CUtensorMap* tmC) {
+                                                  const CUtensorMap* tmC, const CUtensorMap* tmD = nullptr) {
   const int warp = threadIdx.x >> 5;
   if (warp == 0 && lane_id() == 0) {
     tma_prefetch_desc(tmA);
     tma_prefetch_desc(tmB);
     if (tmC) tma_prefetch_desc(tmC);
+    if (tmD) tma_prefetch_desc(tmD);
   }
   if (warp == 1 && lane_id() == 0) {
     for (int i = 0; i < GEMM_STAGES; ++i) {
@@ -99,7 +112,8 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmCtx<BN, L>& cx, cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&cx.tmem_full[i], 1);
-      mbar_init(&cx.tmem_empty[i], GEMM_EPI_THREADS / 32);
+      mbar_init(&cx.tmem_empty[i], GEMM_EPI_WARPS);
+      mbar_init(&cx.aux[i], 1);
     }
     fence_mbar_init();
   }
@@ -121,7 +135,9 @@ __device__ __forceinline__ void gemm_teardown(const GemmCtx<BN, L>& cx, uint32_t
 }
 
 // Warp 0, one elected lane. Streams A/B k-blocks of every tile this CTA owns through the smem ring.
-template <int BN, class L>
+// K-major operand: tensor map (inner = K, outer = rows), one box [rows x 64 k].
+// MN-major operand: tensor map (inner = rows (M or N), outer = K), boxes of [64 k x 64 rows] = 8 KB panels.
+template <int BN, bool A_MN, bool B_MN, class L>
 __device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CUtensorMap* tmA, const CUtensorMap* tmB,
                                               int M, int N, int K) {
   GemmSched sched(M, N, BN);
@@ -133,8 +149,20 @@ __device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CU
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&cx.empty[stage], phase ^ 1, 1);
       mbar_arrive_expect_tx(&cx.full[stage], L::STAGE_BYTES);
-      tma_load_2d(cx.a_stage(stage), tmA, &cx.full[stage], kb * GEMM_BK, ti.m0);
-      tma_load_2d(cx.b_stage(stage), tmB, &cx.full[stage], kb * GEMM_BK, ti.n0);
+      if constexpr (!A_MN) {
+        tma_load_2d(cx.a_stage(stage), tmA, &cx.full[stage], kb * GEMM_BK, ti.m0);
+      } else {
+#pragma unroll
+        for (int p = 0; p < GEMM_BM / 64; ++p)
+          tma_load_2d(cx.a_stage(stage) + p * GEMM_PANEL_BYTES, tmA, &cx.full[stage], ti.m0 + 64 * p, kb * GEMM_BK);
+      }
+      if constexpr (!B_MN) {
+        tma_load_2d(cx.b_stage(stage), tmB, &cx.full[stage], kb * GEMM_BK, ti.n0);
+      } else {
+#pragma unroll
+        for (int p = 0; p < BN / 64; ++p)
+          tma_load_2d(cx.b_stage(stage) + p * GEMM_PANEL_BYTES, tmB, &cx.full[stage], ti.n0 + 64 * p, kb * GEMM_BK);
+      }
       if (++stage == GEMM_STAGES) {
         stage = 0;
         phase ^= 1;
@@ -144,11 +172,11 @@ __device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CU
 }
 
 // Warp 1, one elected lane. Issues BK/16 tcgen05.mma per k-block into the tile's TMEM accumulator buffer.
-template <int BN, class L>
+template <int BN, bool A_MN, bool B_MN, class L>
 __device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32_t tmem_base, int M, int N, int K) {
   GemmSched sched(M, N, BN);
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
-  constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, 0, 0);
+  constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   int stage = 0;
   uint32_t phase = 0;
   int it = 0;
@@ -165,8 +193,11 @@ __device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32
       const uint32_t b_addr = smem_u32(cx.b_stage(stage));
 #pragma unroll
       for (int k = 0; k < GEMM_BK / 16; ++k) {
-        umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32), idesc,
-                     (kb | k) != 0);
+        const uint64_t ad = A_MN ? umma_desc_mnmajor_sw128(a_addr + k * 2048, GEMM_PANEL_BYTES)
+                                 : umma_desc_kmajor_sw128(a_addr + k * 32);
+        const uint64_t bd = B_MN ? umma_desc_mnmajor_sw128(b_addr + k * 2048, GEMM_PANEL_BYTES)
+                                 : umma_desc_kmajor_sw128(b_addr + k * 32);
+        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
       }
       umma_commit(&cx.empty[stage]);
       if (++stage == GEMM_STAGES) {

@@ -51,8 +51,24 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
+static int make_tmap_nd(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 int make_tmap_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  return make_tmap_nd(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
+}
+
+int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                     uint32_t box_inner, uint32_t box_outer) {
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {ld_elems * 4};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap_nd(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int make_tmap_nd(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   auto fn = get_encode_fn();
   if (!fn) return set_error(OVK_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if (reinterpret_cast<uintptr_t>(base) & 15) return set_error(OVK_ERR_ALIGN, "TMA base pointer must be 16-byte aligned");
@@ -70,7 +86,7 @@ int make_tmap_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64
                                              (unsigned long long)gstr[i - 1]);
     }
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(OVK_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);

@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import EPI_BIAS, EPI_GELU_ERF, EPI_GELU_QUICK, EPI_GELU_TANH, EPI_NONE, EPI_RESIDUAL, OvkError
+from ._lib import (EPI_BIAS, EPI_GELU_ERF, EPI_GELU_QUICK, EPI_GELU_TANH, EPI_NONE, EPI_RESIDUAL, EPI_SAVE_PREACT,
+                   OvkError)
 
 _ACT = {None: EPI_NONE, "none": EPI_NONE, "gelu": EPI_GELU_ERF, "gelu_erf": EPI_GELU_ERF, "gelu_tanh": EPI_GELU_TANH,
         "quick_gelu": EPI_GELU_QUICK}
@@ -65,10 +66,11 @@ def _require(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, act: Optional[str] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias) + residual   (kernel: gemm_bf16_kernel, tcgen05).
+         out: Optional[torch.Tensor] = None, preact_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias)  or  a @ w^T + bias + residual   (kernel: gemm_bf16_kernel, tcgen05).
 
-    `w` has the nn.Linear layout [out_features, in_features]; bias is fp32 [N]; residual may alias `out`."""
+    `w` has the nn.Linear layout [out_features, in_features]; bias is fp32 [N]; residual may alias `out`.
+    With an activation, `preact_out` (bf16 [M,N]) additionally receives a @ w^T + bias (saved for backward)."""
     _require(a, torch.bfloat16, "gemm.a", 2)
     _require(w, torch.bfloat16, "gemm.w", 2)
     M, K = a.shape
@@ -94,9 +96,62 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             raise OvkError("gemm.residual has the wrong shape")
         flags |= EPI_RESIDUAL
         ldr = residual.stride(0)
+    ldp = 0
+    if preact_out is not None:
+        _require(preact_out, torch.bfloat16, "gemm.preact_out", 2)
+        if tuple(preact_out.shape) != (M, N):
+            raise OvkError("gemm.preact_out has the wrong shape")
+        flags |= EPI_SAVE_PREACT
+        ldp = preact_out.stride(0)
     with _timed("gemm", 2.0 * M * N * K):
-        _lib.call("ovk_gemm_bf16", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
-                  _p(residual), ldr, flags, _stream())
+        _lib.call("ovk_gemm_bf16_ex", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+                  _p(residual), ldr, _p(preact_out), ldp, flags, _stream())
+    _count()
+    return out
+
+
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torch.bfloat16,
+            preact: Optional[torch.Tensor] = None, act: Optional[str] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = alpha * a[M,K] @ b[K,N]  (b row-major: the dgrad dX = dY @ W with W = nn.Linear weight [out, in]).
+    With `preact` + `act`: out = alpha * (a @ b) * act'(preact)  (GELU backward fused, bf16 out)."""
+    _require(a, torch.bfloat16, "gemm_nn.a", 2)
+    _require(b, torch.bfloat16, "gemm_nn.b", 2)
+    M, K = a.shape
+    K2, N = b.shape
+    if K2 != K:
+        raise OvkError(f"gemm_nn: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _require(out, out_dtype, "gemm_nn.out", 2)
+    ldp = 0
+    if preact is not None:
+        _require(preact, torch.bfloat16, "gemm_nn.preact", 2)
+        if tuple(preact.shape) != (M, N):
+            raise OvkError("gemm_nn.preact has the wrong shape")
+        ldp = preact.stride(0)
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_nn", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0),
+                  int(out_dtype == torch.float32), M, N, K, float(alpha), _p(preact), ldp, _ACT[act], _stream())
+    _count()
+    return out
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torch.bfloat16,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = alpha * a[K,M]^T @ b[K,N]  (both row-major: the wgrad dW = dY^T @ X, the loss dT = s G^T I)."""
+    _require(a, torch.bfloat16, "gemm_tn.a", 2)
+    _require(b, torch.bfloat16, "gemm_tn.b", 2)
+    K, M = a.shape
+    K2, N = b.shape
+    if K2 != K:
+        raise OvkError(f"gemm_tn: reduction dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _require(out, out_dtype, "gemm_tn.out", 2)
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_tn", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0),
+                  int(out_dtype == torch.float32), M, N, K, float(alpha), _stream())
     _count()
     return out
 

@@ -197,3 +197,58 @@ def test_error_paths_return_codes_not_crashes(ops):
         ops.gemm(a.cpu(), w.cpu())
     with pytest.raises(OvkError):
         ops.attention(torch.zeros(4, 3 * 48, dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 48)   # hd = 48 unsupported
+
+
+# ------------------------------------------------------------------------------------------------ backward GEMMs
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (808, 192, 576), (1000, 1024, 4096), (333, 72, 200),
+                                   (128 * 150, 1024, 1024)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_gemm_nn_dgrad(ops, M, N, K, f32):
+    """dX = dY @ W (what autograd derives from F.linear), W read in place as [K(red), N]."""
+    a = rnd(M, K, seed=1, scale=0.5).bfloat16()
+    b = rnd(K, N, seed=2, scale=0.5).bfloat16()
+    out = ops.gemm_nn(a.cuda(), b.cuda(), alpha=0.5, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    assert_close(out, 0.5 * (a.float() @ b.float()), 1e-2 if not f32 else 1e-4, f"gemm_nn {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 128), (576, 192, 808), (4096, 1024, 3000), (72, 200, 333),
+                                   (768, 768, 20000)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_gemm_tn_wgrad(ops, M, N, K, f32):
+    """dW = dY^T @ X: both operands read with the reduction (token) dimension outermost."""
+    a = rnd(K, M, seed=1, scale=0.5).bfloat16()
+    b = rnd(K, N, seed=2, scale=0.5).bfloat16()
+    out = ops.gemm_tn(a.cuda(), b.cuda(), alpha=2.0, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    assert_close(out, 2.0 * (a.float().t() @ b.float()), 1e-2 if not f32 else 1e-4, f"gemm_tn {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("act,kind", [("gelu", "erf"), ("gelu_tanh", "tanh"), ("quick_gelu", "quick")])
+def test_gemm_preact_save_and_fused_act_backward(ops, act, kind):
+    M, N, K = 520, 768, 192
+    a = rnd(M, K, seed=1, scale=0.5).bfloat16()
+    w = rnd(N, K, seed=2, scale=0.3).bfloat16()
+    bias = rnd(N, seed=3)
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a.cuda(), w.cuda(), bias=bias.cuda(), act=act, preact_out=pre)
+    u = a.float() @ w.float().t() + bias
+    assert_close(pre, u, 1e-2, "saved pre-activation")
+    assert_close(out, O.gelu(u, kind), 1e-2, "activation")
+    # backward: dU = (dA @ W2) * act'(u) with u the saved (bf16) pre-activation
+    K2 = 256
+    dy = rnd(M, K2, seed=4, scale=0.5).bfloat16()
+    w2 = rnd(K2, N, seed=5, scale=0.3).bfloat16()
+    du = ops.gemm_nn(dy.cuda(), w2.cuda(), preact=pre, act=act)
+    uf = pre.float().cpu().requires_grad_(True)
+    O.gelu(uf, kind).backward(dy.float() @ w2.float())
+    assert_close(du, uf.grad, 1e-2, "fused act backward")
+
+
+def test_act_matches_exact_erf_gelu_pointwise(ops):
+    """the sigmoid-of-polynomial GELU of the epilogue against the exact erf form over the whole useful range."""
+    x = torch.linspace(-12, 12, 4096 * 8).reshape(4096, 8).bfloat16()
+    eye = torch.eye(8).bfloat16()
+    y = ops.gemm(x.cuda(), eye.cuda(), act="gelu")
+    ref = O.gelu(x.double(), "erf")
+    err = (y.double().cpu() - ref).abs()
+    # bf16 output rounding (rel 2^-9) dominates; the approximation itself is <= 3e-5 absolute
+    assert (err <= 2.0 ** -8 * ref.abs() + 4e-5).all(), err.max()
