@@ -122,6 +122,36 @@ int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
 int ovk_pool_tokens(const void* x, void* pooled, int B, int L, int D, int mode, void* stream);
 int ovk_l2_normalize(const void* x, void* y, int y_is_f32, float* norms, int rows, int E, float eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * CLIP contrastive loss, loss.py:102-131 (ClipLoss.get_logits + 2x F.cross_entropy), fused: the N x N logits are
+ * never written to memory in the forward pass.
+ *   z = scale * A_loc · B_all^T   (rows = this rank's image features, cols = all text features);
+ *   labels: row i <-> column (row_offset + i)                                   (loss.py:89-100 get_ground_truth)
+ *   a_loc : bf16 [n_loc, E]    b_all : bf16 [n_all, E]
+ * ovk_clip_loss_fwd outputs (all f32, natural-log units):
+ *   row_lse[n_loc]  = logsumexp_j z_ij            diag[n_loc] = z_i,label(i)
+ *   col_max[n_all], col_sum[n_all] : THIS row block's column statistics, sum_i exp(z_ij - col_max_j) = col_sum_j,
+ *                                    so that W ranks can merge their row blocks into global column LSEs.
+ *   workspace: f32 scratch of ovk_clip_loss_workspace_floats(n_loc, n_all) elements.
+ * ovk_clip_loss_combine : col_lse[j] = log sum_w exp(col_max[w][j]) * col_sum[w][j]   over `parts` stacked [parts, n_all] arrays
+ * ovk_clip_loss_value   : out3[0] = 0.5/n_loc * (sum_i (row_lse_i - diag_i) + sum_i (col_lse[row_offset+i] - diag_i)),
+ *                         out3[1], out3[2] = the two sums                             (loss.py:126-129)
+ * ovk_clip_loss_grad_logits : G[i,j] = w_row * exp(z_ij - row_lse_i) + w_col * exp(z_ij - col_lse_j)
+ *                                     - (w_row + w_col) * [j == row_offset + i],  bf16 [n_loc, ldg];
+ *                         d_scale_partial (f32[1], ACCUMULATED) += sum_ij G_ij * z_ij / scale.
+ *   The feature gradients are then dA = scale * G · B_all (ovk_gemm_bf16_nn) and dB = scale * G^T · A_loc (ovk_gemm_bf16_tn).
+ */
+long long ovk_clip_loss_workspace_floats(int n_loc, int n_all);
+int ovk_clip_loss_fwd(const void* a_loc, const void* b_all, int n_loc, int n_all, int E, int row_offset, float scale,
+                      float* row_lse, float* diag, float* col_max, float* col_sum, float* workspace, void* stream);
+int ovk_clip_loss_combine(const float* col_max_parts, const float* col_sum_parts, int parts, int n_all, float* col_lse,
+                          void* stream);
+int ovk_clip_loss_value(const float* row_lse, const float* col_lse, const float* diag, int n_loc, int row_offset,
+                        float* out3, void* stream);
+int ovk_clip_loss_grad_logits(const void* a_loc, const void* b_all, int n_loc, int n_all, int E, int row_offset,
+                              float scale, const float* row_lse, const float* col_lse, float w_row, float w_col,
+                              void* G, long long ldg, float* d_scale_partial, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -266,3 +266,66 @@ def l2_normalize(x: torch.Tensor, out_dtype=torch.float32, eps: float = 1e-12, r
     _lib.call("ovk_l2_normalize", _p(x), _p(y), int(out_dtype == torch.float32), _p(norms), rows, E, float(eps), _stream())
     _count()
     return (y, norms) if return_norms else y
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused CLIP contrastive loss (kernels: clip_loss_fwd_kernel, clip_loss_finalize_kernel, clip_loss_combine_kernel,
+# clip_loss_value_kernel, clip_loss_grad_kernel)
+# ----------------------------------------------------------------------------------------------------------------
+def clip_loss_fwd(a_loc: torch.Tensor, b_all: torch.Tensor, row_offset: int, scale: float):
+    """Row LSEs, positive-pair logits and this row block's column statistics of z = scale * a_loc @ b_all^T without
+    materialising z.  a_loc bf16 [n_loc,E], b_all bf16 [n_all,E].  Returns (row_lse, diag, col_max, col_sum), fp32."""
+    _require(a_loc, torch.bfloat16, "clip_loss.a_loc", 2)
+    _require(b_all, torch.bfloat16, "clip_loss.b_all", 2)
+    if not a_loc.is_contiguous() or not b_all.is_contiguous():
+        raise OvkError("clip_loss: features must be contiguous")
+    n_loc, E = a_loc.shape
+    n_all, E2 = b_all.shape
+    if E != E2:
+        raise OvkError("clip_loss: embedding dims differ")
+    dev = a_loc.device
+    row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    diag = torch.empty(n_loc, dtype=torch.float32, device=dev)
+    col_max = torch.empty(n_all, dtype=torch.float32, device=dev)
+    col_sum = torch.empty(n_all, dtype=torch.float32, device=dev)
+    ws = torch.empty(_lib.load().ovk_clip_loss_workspace_floats(n_loc, n_all), dtype=torch.float32, device=dev)
+    with _timed("clip_loss_fwd", 2.0 * n_loc * n_all * E):
+        _lib.call("ovk_clip_loss_fwd", _p(a_loc), _p(b_all), n_loc, n_all, E, int(row_offset), float(scale), _p(row_lse),
+                  _p(diag), _p(col_max), _p(col_sum), _p(ws), _stream())
+    _count(2)
+    return row_lse, diag, col_max, col_sum
+
+
+def clip_loss_combine(col_max_parts: torch.Tensor, col_sum_parts: torch.Tensor) -> torch.Tensor:
+    """[parts, n_all] partial column statistics (one row per rank) -> global column LSE [n_all]."""
+    _require(col_max_parts, torch.float32, "clip_loss_combine.col_max", 2)
+    _require(col_sum_parts, torch.float32, "clip_loss_combine.col_sum", 2)
+    if not col_max_parts.is_contiguous() or not col_sum_parts.is_contiguous():
+        raise OvkError("clip_loss_combine: inputs must be contiguous")
+    parts, n_all = col_max_parts.shape
+    col_lse = torch.empty(n_all, dtype=torch.float32, device=col_max_parts.device)
+    _lib.call("ovk_clip_loss_combine", _p(col_max_parts), _p(col_sum_parts), parts, n_all, _p(col_lse), _stream())
+    _count()
+    return col_lse
+
+
+def clip_loss_value(row_lse, col_lse, diag, row_offset: int) -> torch.Tensor:
+    """out[0] = 0.5/n * (sum(row_lse - diag) + sum(col_lse[labels] - diag)); out[1:3] = the two sums."""
+    out = torch.empty(3, dtype=torch.float32, device=row_lse.device)
+    _lib.call("ovk_clip_loss_value", _p(row_lse), _p(col_lse), _p(diag), row_lse.numel(), int(row_offset), _p(out), _stream())
+    _count()
+    return out
+
+
+def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale: float, row_lse, col_lse, w_row: float, w_col: float,
+                          d_scale: torch.Tensor) -> torch.Tensor:
+    """G = dL/dz for this row block, bf16 [n_loc, n_all]; d_scale (fp32[1]) += sum(G * z) / scale."""
+    n_loc, E = a_loc.shape
+    n_all = b_all.shape[0]
+    ldg = (n_all + 7) // 8 * 8
+    G = torch.empty((n_loc, ldg), dtype=torch.bfloat16, device=a_loc.device)
+    with _timed("clip_loss_grad", 2.0 * n_loc * n_all * E):
+        _lib.call("ovk_clip_loss_grad_logits", _p(a_loc), _p(b_all), n_loc, n_all, E, int(row_offset), float(scale),
+                  _p(row_lse), _p(col_lse), float(w_row), float(w_col), _p(G), ldg, _p(d_scale), _stream())
+    _count()
+    return G[:, :n_all] if ldg != n_all else G
