@@ -75,6 +75,10 @@ int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb,
                      int M, int N, int K, float alpha, const void* preact, long long ldp, int act, void* stream);
 int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
                      int M, int N, int K, float alpha, void* stream);
+/* The activation as a standalone module call (nn.GELU / QuickGELU hooked by the ov-* scripts, transformer.py:33-36,
+ * 232-236): y = act(x), and dx = dy * act'(x); bf16, n elements (multiple of 8), act = OVK_EPI_GELU_*. */
+int ovk_act_fwd(const void* x, void* y, long long n, int act, void* stream);
+int ovk_act_bwd(const void* x, const void* dy, void* dx, long long n, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * LayerNorm over the last dimension (biased variance, fp32 statistics), transformer.py:15-30 (LayerNorm /
@@ -84,23 +88,35 @@ int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb,
  */
 int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
                       float* mean, float* rstd, int rows, int D, float eps, void* stream);
-/* dx = LN'(x)·dy ; dgamma/dbeta (f32[D]) are ACCUMULATED atomically (zero them first).  dx may alias dy. */
+/* dx = LN'(x)·dy (+ dres) ; dgamma/dbeta (f32[D]) are ACCUMULATED atomically (zero them first).  dx may alias dy or
+ * dres.  dres (bf16 [rows, lddres], nullable) is the gradient arriving through the residual connection around the
+ * normalised branch (transformer.py:263-264: x = x + f(ln(x))), added in the same pass. */
 int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
-                      const float* mean, const float* rstd, void* dx, long long lddx, float* dgamma, float* dbeta,
-                      int rows, int D, void* stream);
+                      const float* mean, const float* rstd, const void* dres, long long lddres, void* dx,
+                      long long lddx, float* dgamma, float* dbeta, int rows, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Patch embedding, transformer.py:469,610-617: Conv2d(3->D, kernel = stride = P, no bias) as an im2col GEMM,
  * then x = cat([class_embedding, patches]) + positional_embedding.
- *   ovk_im2col_patches : images [B,3,H,W] (f32 when img_is_f32, else bf16, NCHW contiguous) -> cols bf16 [B*gh*gw, ldc]
- *                        column order (c, ph, pw) = conv1.weight.reshape(D, 3*P*P); columns [3P², ldc) are zero-filled.
- *   ovk_embed_assemble : tokens[b,0,:] = cls + pos[0];  tokens[b,1+n,:] = patch[b*N+n,:] + pos[1+n]   (bf16 out)
- *                        patch: bf16 [B*N, D] (GEMM output); cls f32[D]; pos f32[L,D], L = N+1.
+ *   ovk_im2col_patches : images [B,3,H,W] (f32 when img_is_f32, else bf16, NCHW contiguous) -> cols bf16
+ *                        [B*(gh*gw + lead_rows), ldc], column order (c, ph, pw) = conv1.weight.reshape(D, 3*P*P);
+ *                        columns [3P², ldc) are zero-filled.  lead_rows = 1 puts one all-zero row in front of each
+ *                        image's patches, so that the GEMM output already has the [B, L = N+1, D] token layout.
+ *   ovk_embed_assemble : tokens[b,0,:] = cls + pos[0];  tokens[b,1+n,:] = patch[b,n,:] + pos[1+n]   (bf16 out)
+ *                        patch: bf16 [B*(N + patch_lead_rows), D] (GEMM output; may alias tokens when
+ *                        patch_lead_rows = 1); cls f32[D]; pos f32[L,D], L = N+1.
  */
 int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long ldc, int B, int H, int W, int P,
-                       void* stream);
-int ovk_embed_assemble(const void* patch, const float* cls, const float* pos, void* tokens, int B, int N, int D,
-                       void* stream);
+                       int lead_rows, void* stream);
+int ovk_embed_assemble(const void* patch, int patch_lead_rows, const float* cls, const float* pos, void* tokens, int B,
+                       int N, int D, void* stream);
+/* Backward of the patch embedding w.r.t. the input image (the ov-* scripts optimise the image through the tower):
+ * dimages[b,c,y,x] = dcols[row(b,y/P,x/P), (c*P + y%P)*P + x%P]  (f32 or bf16 out), dcols = dtokens · conv1.weight. */
+int ovk_col2im_patches(const void* dcols, long long ldc, void* dimages, int img_is_f32, int B, int H, int W, int P,
+                       int lead_rows, void* stream);
+/* out[c] += sum_r x[r,c] (bf16 [rows, ldx] -> f32[cols], ACCUMULATED): bias gradients of F.linear, and with rows = B,
+ * cols = L*D the gradient of positional_embedding / class_embedding (transformer.py:615-617). */
+int ovk_colsum_bf16(const void* x, long long ldx, int rows, int cols, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Multi-head self-attention core, nn.MultiheadAttention(need_weights=False, attn_mask=None) between in_proj and
@@ -112,6 +128,11 @@ int ovk_embed_assemble(const void* patch, const float* cls, const float* pos, vo
  * hd must be 64 in this build.
  */
 int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream);
+/* Backward: dqkv (bf16, same [B, L, 3, H, hd] layout) from qkv, the forward output `out`, its gradient `dout`
+ * (bf16 [B, L, H*hd]) and the saved lse.  delta: f32 [B, H, L] scratch (rowsum(dout * out), written then read).
+ * Scores are recomputed tile by tile; two launches (dQ, then dK/dV), no atomics. */
+int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                      int B, int L, int H, int hd, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Pooling head, transformer.py:599-607,638-646.
@@ -121,6 +142,10 @@ int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
  */
 int ovk_pool_tokens(const void* x, void* pooled, int B, int L, int D, int mode, void* stream);
 int ovk_l2_normalize(const void* x, void* y, int y_is_f32, float* norms, int rows, int E, float eps, void* stream);
+/* Backward: dx[b,l,:] of the pooling (every element written), and dx = (dy - y (y·dy)) / max(||x||, eps) of F.normalize
+ * (x bf16 [rows,E]; dy f32 or bf16; dx bf16). */
+int ovk_pool_tokens_bwd(const void* dpooled, void* dx, int B, int L, int D, int mode, void* stream);
+int ovk_l2_normalize_bwd(const void* x, const void* dy, int dy_is_f32, void* dx, int rows, int E, float eps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * CLIP contrastive loss, loss.py:102-131 (ClipLoss.get_logits + 2x F.cross_entropy), fused: the N x N logits are

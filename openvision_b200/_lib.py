@@ -41,12 +41,20 @@ _PROTOTYPES = {
                                  c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_gemm_bf16_tn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p]),
+    "ovk_act_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_float, c_void_p]),
     "ovk_layernorm_bwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "ovk_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p]),
-    "ovk_embed_assemble": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+                                  c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ovk_im2col_patches": (c_int, [c_void_p, c_int, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovk_embed_assemble": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ovk_col2im_patches": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovk_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "ovk_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_float, c_void_p]),
+    "ovk_pool_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovk_l2_normalize_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
     "ovk_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ovk_pool_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ovk_clip_loss_workspace_floats": (c_longlong, [c_int, c_int]),

@@ -1,7 +1,19 @@
-"""Functional layer between the drop-in modules and libovk: packs parameters, sequences kernels, and (when gradients
-are requested) records torch.autograd.Function nodes whose backward is again libovk kernels."""
+"""Functional layer between the drop-in modules and libovk: packs parameters, sequences kernels, and records
+torch.autograd.Function nodes whose backward is again libovk kernels (torch is the tape, never the arithmetic).
+
+Backward of one ResidualAttentionBlock (transformer.py:254-265), given dY (bf16 [B*L, D]):
+    dU   = (dY W2) . act'(u)          gemm_nn + fused GELU'          dW2 = dY^T f   gemm_tn    db2 = colsum(dY)
+    dH2  = dU W1                      gemm_nn                        dW1 = dU^T h2  gemm_tn    db1 = colsum(dU)
+    dXm  = LN2'(dH2) + dY             layernorm_bwd (+ residual grad)
+    dA   = dXm Wo                     gemm_nn                        dWo = dXm^T a  gemm_tn    dbo = colsum(dXm)
+    dQKV = attention_bwd(qkv, a, dA, lse)
+    dH1  = dQKV Wqkv                  gemm_nn                        dWqkv = dQKV^T h1         dbqkv = colsum(dQKV)
+    dX   = LN1'(dH1) + dXm            layernorm_bwd (+ residual grad)
+h1 / h2 (the LayerNorm outputs) are recomputed from the saved statistics rather than stored.
+"""
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
@@ -11,11 +23,7 @@ from ._lib import OvkError
 
 
 def _needs_grad(*tensors) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
-
-
-def _no_backward(what: str):
-    raise OvkError(f"{what}: backward kernels are not part of this build yet; call under torch.no_grad()")
+    return torch.is_grad_enabled() and any(t is not None and torch.is_tensor(t) and t.requires_grad for t in tensors)
 
 
 def _w_bf16(owner, key, w, transpose=False):
@@ -28,47 +36,265 @@ def _v_f32(owner, key, v):
     return _packed(owner, key, v, torch.float32)
 
 
+def _grad_dtype(p: Optional[torch.Tensor]):
+    return torch.float32 if p is None or p.dtype == torch.float32 else torch.bfloat16
+
+
+def _like_param(g: Optional[torch.Tensor], p: Optional[torch.Tensor]):
+    if g is None or p is None:
+        return None
+    g = g.reshape(p.shape)
+    return g if g.dtype == p.dtype else g.to(p.dtype)
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    """upstream gradients arrive in whatever layout autograd built; the kernels want contiguous bf16 rows"""
+    if t.dtype != torch.bfloat16:
+        t = t.to(torch.bfloat16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LayerNorm
+# ----------------------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, weight, bias, eps, owner):
+        g, b = _v_f32(owner, "ln_w", weight), _v_f32(owner, "ln_b", bias)
+        if any(ctx.needs_input_grad):
+            y, mean, rstd = ops.layernorm(x2, g, b, eps, save_stats=True)
+            ctx.save_for_backward(x2, g, mean, rstd)
+            ctx.params = (weight, bias)
+            return y
+        return ops.layernorm(x2, g, b, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, g, mean, rstd = ctx.saved_tensors
+        weight, bias = ctx.params
+        dg = torch.zeros_like(g)
+        db = torch.zeros_like(g)
+        dx = ops.layernorm_bwd(_c(dy), x2, g, mean, rstd, dg, db)
+        return dx, _like_param(dg, weight), _like_param(db, bias), None, None
+
+
 def layer_norm_fn(x2, weight, bias, eps, owner):
-    if _needs_grad(x2, weight, bias):
-        _no_backward("layer_norm")
-    return ops.layernorm(x2, _v_f32(owner, "ln_w", weight), _v_f32(owner, "ln_b", bias), eps)
+    if not _needs_grad(x2, weight, bias):
+        return ops.layernorm(x2, _v_f32(owner, "ln_w", weight), _v_f32(owner, "ln_b", bias), eps)
+    return _LayerNorm.apply(x2, weight, bias, eps, owner)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Linear (+ bias, + residual) and raw projection matrices
+# ----------------------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, weight, bias, residual, owner, transpose_weight):
+        w = _w_bf16(owner, "w_t" if transpose_weight else "w", weight, transpose=transpose_weight)   # [N, K]
+        b = _v_f32(owner, "b", bias) if bias is not None else None
+        y = ops.gemm(x2, w, bias=b, residual=residual)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x2, w)
+            ctx.meta = (weight, bias, residual is not None, transpose_weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        weight, bias, has_res, transposed = ctx.meta
+        dy = _c(dy)
+        dx = ops.gemm_nn(dy, w) if ctx.needs_input_grad[0] else None                      # dX = dY W
+        dw = None
+        if ctx.needs_input_grad[1]:
+            if transposed:   # parameter stored [in, out] (visual.proj, text_projection): d(proj) = X^T dY
+                dw = ops.gemm_tn(x2, dy, out_dtype=_grad_dtype(weight))
+            else:            # nn.Linear layout [out, in]: dW = dY^T X
+                dw = ops.gemm_tn(dy, x2, out_dtype=_grad_dtype(weight))
+        db = ops.colsum(dy) if bias is not None and ctx.needs_input_grad[2] else None
+        return dx, _like_param(dw, weight), _like_param(db, bias), (dy if has_res else None), None, None
 
 
 def linear_fn(x2, weight, bias, residual, act, owner, transpose_weight=False):
-    """x2 @ W^T (+bias)(act)(+residual); `transpose_weight` for raw [in, out] projection matrices (visual.proj)."""
-    if _needs_grad(x2, weight, bias, residual):
-        _no_backward("linear")
-    w = _w_bf16(owner, "w_t" if transpose_weight else "w", weight, transpose=transpose_weight)
-    b = _v_f32(owner, "b", bias) if bias is not None else None
-    return ops.gemm(x2, w, bias=b, residual=residual, act=act)
+    """x2 @ W^T (+bias)(+residual); `transpose_weight` for raw [in, out] projection matrices (visual.proj).
+    Activations are fused only on the block path (block_fn) and are not accepted here."""
+    if act is not None:
+        raise OvkError("linear_fn: fused activations belong to the block path")
+    N = weight.shape[1] if transpose_weight else weight.shape[0]
+    K = weight.shape[0] if transpose_weight else weight.shape[1]
+    if (N % 8) or (K % 8):
+        raise OvkError(f"linear: in/out features must be multiples of 8 (got {K} -> {N})")
+    if not _needs_grad(x2, weight, bias, residual):
+        w = _w_bf16(owner, "w_t" if transpose_weight else "w", weight, transpose=transpose_weight)
+        return ops.gemm(x2, w, bias=_v_f32(owner, "b", bias) if bias is not None else None, residual=residual)
+    return _Linear.apply(x2, weight, bias, residual, owner, transpose_weight)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# activation as a module (hooked nn.GELU / QuickGELU)
+# ----------------------------------------------------------------------------------------------------------------
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kind):
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x)
+            ctx.kind = kind
+        return ops.act_fwd(x, kind)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(x, _c(dy).reshape(x.shape), ctx.kind), None
+
+
+def act_fn(x: torch.Tensor, kind: str) -> torch.Tensor:
+    return _Act.apply(x, kind) if _needs_grad(x) else ops.act_fwd(x, kind)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# patch embedding, cls / pos assembly
+# ----------------------------------------------------------------------------------------------------------------
+class _PatchEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, conv_weight, conv):
+        w, kpad = conv.packed_weight()
+        P = conv.kernel_size[0]
+        cols = ops.im2col_patches(images, P, kpad, lead_rows=1)
+        tok = ops.gemm(cols, w)                      # [B*(N+1), D]; row 0 of every image is 0 (the cls slot)
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(cols, w)
+            ctx.meta = (conv_weight, tuple(images.shape), images.dtype, P)
+        return tok
+
+    @staticmethod
+    def backward(ctx, dtok):
+        cols, w = ctx.saved_tensors
+        conv_weight, ishape, idtype, P = ctx.meta
+        dtok = _c(dtok)
+        dw = dimg = None
+        if ctx.needs_input_grad[1]:
+            k = conv_weight[0].numel()
+            dwp = ops.gemm_tn(dtok, cols, out_dtype=_grad_dtype(conv_weight))          # [D, Kpad]
+            dw = _like_param(dwp[:, :k].contiguous(), conv_weight)
+        if ctx.needs_input_grad[0]:
+            dcols = ops.gemm_nn(dtok, w)                                                # [B*(N+1), Kpad]
+            B, _, H, W = ishape
+            dimg = ops.col2im_patches(dcols, B, H, W, P, 1, torch.float32 if idtype == torch.float32 else torch.bfloat16)
+            if dimg.dtype != idtype:
+                dimg = dimg.to(idtype)
+        return dimg, dw, None
 
 
 def patch_embed_fn(images, conv_weight, conv):
-    if _needs_grad(images, conv_weight):
-        _no_backward("patch_embed")
-    w, kpad = conv.packed_weight()
-    cols = ops.im2col_patches(images, conv.kernel_size[0], kpad)
-    return ops.gemm(cols, w)
+    """images [B,3,H,W] -> bf16 [B*(N+1), D] patch tokens with a zero row in every image's cls slot."""
+    if not _needs_grad(images, conv_weight):
+        w, kpad = conv.packed_weight()
+        return ops.gemm(ops.im2col_patches(images, conv.kernel_size[0], kpad, lead_rows=1), w)
+    return _PatchEmbed.apply(images, conv_weight, conv)
+
+
+class _EmbedAssemble(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok, cls, pos, B, N, owner):
+        x = ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N, inplace=False)
+        ctx.meta = (cls, pos, B, N)
+        return x.view(B * (N + 1), -1)
+
+    @staticmethod
+    def backward(ctx, dx):
+        cls, pos, B, N = ctx.meta
+        dx = _c(dx)
+        D = dx.shape[-1]
+        dpos = dcls = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            s = ops.colsum(dx.view(B, (N + 1) * D)).view(N + 1, D)      # sum over images
+            dpos = _like_param(s, pos) if ctx.needs_input_grad[2] else None
+            dcls = _like_param(s[0].clone(), cls) if ctx.needs_input_grad[1] else None
+        return dx, dcls, dpos, None, None, None
 
 
 def embed_assemble_fn(tok, cls, pos, B, N, owner):
-    if _needs_grad(tok, cls, pos):
-        _no_backward("embed_assemble")
-    return ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N).view(B * (N + 1), -1)
+    if not _needs_grad(tok, cls, pos):
+        x = ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N, inplace=True)
+        return x.view(B * (N + 1), -1)
+    return _EmbedAssemble.apply(tok, cls, pos, B, N, owner)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# pooling, L2 normalisation
+# ----------------------------------------------------------------------------------------------------------------
+class _Pool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, B, L, pool_type):
+        ctx.meta = (B, L, pool_type)
+        return ops.pool_tokens(x2.view(B, L, -1), pool_type)
+
+    @staticmethod
+    def backward(ctx, dp):
+        B, L, pool_type = ctx.meta
+        return ops.pool_tokens_bwd(_c(dp), B, L, pool_type).view(B * L, -1), None, None, None
 
 
 def pool_fn(x2, B, L, pool_type):
-    if _needs_grad(x2):
-        _no_backward("pool")
-    return ops.pool_tokens(x2.view(B, L, -1), pool_type)
+    if not _needs_grad(x2):
+        return ops.pool_tokens(x2.view(B, L, -1), pool_type)
+    return _Pool.apply(x2, B, L, pool_type)
+
+
+class _Normalize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_dtype, eps):
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(x)
+            ctx.eps = eps
+        return ops.l2_normalize(x, out_dtype=out_dtype, eps=eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        if dy.dtype not in (torch.float32, torch.bfloat16):
+            dy = dy.float()
+        return ops.l2_normalize_bwd(x, dy.contiguous(), ctx.eps), None, None
+
+
+def normalize_fn(features: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """F.normalize(features, dim=-1): bf16 rows in, unit rows out in the caller's dtype (fp32 stays fp32)."""
+    if not features.is_cuda:
+        raise OvkError("openvision_b200 runs on CUDA (sm_100a) only; got a CPU tensor")
+    out_dtype = torch.float32 if features.dtype == torch.float32 else torch.bfloat16
+    x = features if features.dtype == torch.bfloat16 else features.to(torch.bfloat16)
+    x = x.contiguous()
+    y = _Normalize.apply(x, out_dtype, eps) if _needs_grad(x) else ops.l2_normalize(x, out_dtype=out_dtype, eps=eps)
+    return y if y.dtype == features.dtype else y.to(features.dtype)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+class _AttentionCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, B, L, H, hd):
+        if any(ctx.needs_input_grad):
+            out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+            ctx.save_for_backward(qkv, out, lse)
+            ctx.meta = (B, L, H, hd)
+            return out
+        return ops.attention(qkv, B, L, H, hd)
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        B, L, H, hd = ctx.meta
+        return ops.attention_bwd(qkv, out, _c(dout), lse, B, L, H, hd), None, None, None, None
 
 
 def attention_block_fn(x2, attn, B, L, residual: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
-    """in_proj GEMM (+bias) -> flash attention -> out_proj GEMM (+bias, +residual)."""
-    if _needs_grad(x2, attn.in_proj_weight, attn.out_proj.weight, residual):
-        _no_backward("attention")
+    """in_proj GEMM (+bias) -> flash attention -> out_proj GEMM (+bias, +residual)  (module-by-module path)."""
     H = attn.num_heads
     hd = attn.embed_dim // H
+    if _needs_grad(x2, attn.in_proj_weight, attn.out_proj.weight, residual):
+        qkv = _Linear.apply(x2, attn.in_proj_weight, attn.in_proj_bias, None, _Sub(attn, "in"), False)
+        a = _AttentionCore.apply(qkv, B, L, H, hd)
+        return _Linear.apply(a, attn.out_proj.weight, attn.out_proj.bias, residual, _Sub(attn, "out"), False)
     wqkv = _w_bf16(attn, "in_w", attn.in_proj_weight)
     bqkv = _v_f32(attn, "in_b", attn.in_proj_bias) if attn.in_proj_bias is not None else None
     wo = _w_bf16(attn, "out_w", attn.out_proj.weight)
@@ -78,29 +304,117 @@ def attention_block_fn(x2, attn, B, L, residual: Optional[torch.Tensor], out: Op
     return ops.gemm(a, wo, bias=bo, residual=residual, out=out)
 
 
+class _Sub:
+    """distinct packing-cache namespace on one owner module (in_proj / out_proj of the same nn.MultiheadAttention)"""
+
+    def __init__(self, owner, prefix):
+        self.__dict__["_ovk_cache"] = owner.__dict__.setdefault("_ovk_cache_" + prefix, {})
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused ResidualAttentionBlock
+# ----------------------------------------------------------------------------------------------------------------
+def _block_params(blk):
+    a = blk.attn
+    return (blk.ln_1.weight, blk.ln_1.bias, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
+            blk.ln_2.weight, blk.ln_2.bias, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias, blk.mlp.c_proj.weight,
+            blk.mlp.c_proj.bias)
+
+
+def _block_packed(blk):
+    a, fc, pj = blk.attn, blk.mlp.c_fc, blk.mlp.c_proj
+    return dict(
+        g1=_v_f32(blk.ln_1, "ln_w", blk.ln_1.weight), b1=_v_f32(blk.ln_1, "ln_b", blk.ln_1.bias),
+        wqkv=_w_bf16(a, "in_w", a.in_proj_weight),
+        bqkv=_v_f32(a, "in_b", a.in_proj_bias) if a.in_proj_bias is not None else None,
+        wo=_w_bf16(a, "out_w", a.out_proj.weight),
+        bo=_v_f32(a, "out_b", a.out_proj.bias) if a.out_proj.bias is not None else None,
+        g2=_v_f32(blk.ln_2, "ln_w", blk.ln_2.weight), b2=_v_f32(blk.ln_2, "ln_b", blk.ln_2.bias),
+        w1=_w_bf16(fc, "w", fc.weight), c1=_v_f32(fc, "b", fc.bias) if fc.bias is not None else None,
+        w2=_w_bf16(pj, "w", pj.weight), c2=_v_f32(pj, "b", pj.bias) if pj.bias is not None else None)
+
+
+def _block_forward(x2, p, blk, B, L, inplace, save):
+    H = blk.attn.num_heads
+    hd = blk.attn.embed_dim // H
+    act = blk._act_kind()
+    if save:
+        h, mean1, rstd1 = ops.layernorm(x2, p["g1"], p["b1"], blk.ln_1.eps, save_stats=True)
+    else:
+        h = ops.layernorm(x2, p["g1"], p["b1"], blk.ln_1.eps)
+    qkv = ops.gemm(h, p["wqkv"], bias=p["bqkv"])
+    if save:
+        a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+    else:
+        a = ops.attention(qkv, B, L, H, hd)
+    x_mid = ops.gemm(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None)
+    if save:
+        h, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True, out=h)
+        u = torch.empty((x2.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x2.device)
+        f = ops.gemm(h, p["w1"], bias=p["c1"], act=act, preact_out=u)
+        y = ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid)
+        return y, (x2, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f)
+    h = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, out=h)
+    f = ops.gemm(h, p["w1"], bias=p["c1"], act=act)
+    return ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid, out=x_mid), None
+
+
+class _Block(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, blk, B, L, *params):
+        p = _block_packed(blk)
+        y, saved = _block_forward(x2, p, blk, B, L, inplace=False, save=True)
+        ctx.save_for_backward(*saved)
+        ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params = blk, B, L, p, params
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_in, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f = ctx.saved_tensors
+        blk, B, L, p, params = ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params
+        (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, pj_w, pj_b) = params
+        H = blk.attn.num_heads
+        hd = blk.attn.embed_dim // H
+        act = blk._act_kind()
+        dy = _c(dy)
+        need_w = any(ctx.needs_input_grad[4:])
+        # ---- MLP branch
+        du = ops.gemm_nn(dy, p["w2"], preact=u, act=act)                                    # (dY W2) . act'(u)
+        g_pj_w = ops.gemm_tn(dy, f, out_dtype=_grad_dtype(pj_w)) if need_w else None
+        g_pj_b = ops.colsum(dy) if need_w and pj_b is not None else None
+        del f, u
+        h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps) if need_w else None      # recomputed, not stored
+        dh = ops.gemm_nn(du, p["w1"])
+        g_fc_w = ops.gemm_tn(du, h2, out_dtype=_grad_dtype(fc_w)) if need_w else None
+        g_fc_b = ops.colsum(du) if need_w and fc_b is not None else None
+        del du, h2
+        dg2, db2 = torch.zeros_like(p["g2"]), torch.zeros_like(p["g2"])
+        dxm = ops.layernorm_bwd(dh, x_mid, p["g2"], mean2, rstd2, dg2, db2, dx=dh, dres=dy)  # + residual gradient
+        # ---- attention branch
+        da = ops.gemm_nn(dxm, p["wo"])
+        g_out_w = ops.gemm_tn(dxm, a, out_dtype=_grad_dtype(out_w)) if need_w else None
+        g_out_b = ops.colsum(dxm) if need_w and out_b is not None else None
+        dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, hd)
+        del da
+        h1 = ops.layernorm(x_in, p["g1"], p["b1"], blk.ln_1.eps) if need_w else None
+        dh1 = ops.gemm_nn(dqkv, p["wqkv"])
+        g_in_w = ops.gemm_tn(dqkv, h1, out_dtype=_grad_dtype(in_w)) if need_w else None
+        g_in_b = ops.colsum(dqkv) if need_w and in_b is not None else None
+        del dqkv, h1
+        dg1, db1 = torch.zeros_like(p["g1"]), torch.zeros_like(p["g1"])
+        dx = ops.layernorm_bwd(dh1, x_in, p["g1"], mean1, rstd1, dg1, db1, dx=dh1, dres=dxm)
+        grads = (_like_param(dg1, ln1_w), _like_param(db1, ln1_b), _like_param(g_in_w, in_w), _like_param(g_in_b, in_b),
+                 _like_param(g_out_w, out_w), _like_param(g_out_b, out_b), _like_param(dg2, ln2_w),
+                 _like_param(db2, ln2_b), _like_param(g_fc_w, fc_w), _like_param(g_fc_b, fc_b),
+                 _like_param(g_pj_w, pj_w), _like_param(g_pj_b, pj_b))
+        return (dx, None, None, None) + grads
+
+
 def block_fn(x2, blk, B, L, inplace):
-    """One ResidualAttentionBlock on a bf16 [B*L, D] residual stream: 7 kernels
+    """One ResidualAttentionBlock on a bf16 [B*L, D] residual stream: 7 kernels forward
     (LN, QKV GEMM, attention, out-proj GEMM+residual, LN, fc1 GEMM+GELU, fc2 GEMM+residual)."""
-    params = [p for p in blk.parameters()]
+    params = _block_params(blk)
     if _needs_grad(x2, *params):
-        _no_backward("ResidualAttentionBlock")
-    h = ops.layernorm(x2, _v_f32(blk.ln_1, "ln_w", blk.ln_1.weight), _v_f32(blk.ln_1, "ln_b", blk.ln_1.bias), blk.ln_1.eps)
-    x_mid = attention_block_fn(h, blk.attn, B, L, residual=x2, out=x2 if inplace else None)
-    h = ops.layernorm(x_mid, _v_f32(blk.ln_2, "ln_w", blk.ln_2.weight), _v_f32(blk.ln_2, "ln_b", blk.ln_2.bias), blk.ln_2.eps, out=h)
-    fc, pj = blk.mlp.c_fc, blk.mlp.c_proj
-    f = ops.gemm(h, _w_bf16(fc, "w", fc.weight), bias=_v_f32(fc, "b", fc.bias) if fc.bias is not None else None,
-                 act=blk._act_kind())
-    return ops.gemm(f, _w_bf16(pj, "w", pj.weight), bias=_v_f32(pj, "b", pj.bias) if pj.bias is not None else None,
-                    residual=x_mid, out=x_mid)
-
-
-def normalize_fn(features: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
-    """F.normalize(features, dim=-1): bf16 rows in, unit rows out in the caller's dtype (fp32 stays fp32)."""
-    if _needs_grad(features):
-        _no_backward("l2_normalize")
-    if not features.is_cuda:
-        raise OvkError("openvision_b200 runs on CUDA (sm_100a) only; got a CPU tensor")
-    out_dtype = torch.float32 if features.dtype == torch.float32 else torch.bfloat16
-    x = features if features.dtype == torch.bfloat16 else features.to(torch.bfloat16)
-    y = ops.l2_normalize(x.contiguous(), out_dtype=out_dtype, eps=eps)
-    return y if y.dtype == features.dtype else y.to(features.dtype)
+        return _Block.apply(x2, blk, B, L, *params)
+    y, _ = _block_forward(x2, _block_packed(blk), blk, B, L, inplace=inplace, save=False)
+    return y

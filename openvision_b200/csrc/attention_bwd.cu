@@ -1,0 +1,328 @@
+// Backward of the fused self-attention (what autograd derives from nn.MultiheadAttention's softmax(QK^T/sqrt(hd))V,
+// open_clip/transformer.py:225,239-252) on tcgen05, flash-style: scores are recomputed tile by tile from Q, K and the
+// saved log-sum-exp; nothing of size L x L is ever stored.
+//   P = exp(S*scale - LSE),  dP = dO V^T,  D = rowsum(dO . O),  dS = P . (dP - D)
+//   dV = P^T dO,  dK = scale * dS^T Q,  dQ = scale * dS K
+// Two launches, no atomics, outputs written once as bf16 straight into the packed d(qkv) [B, L, 3, H, 64] layout that
+// the in_proj backward GEMMs read:
+//   MODE_DQ  : one CTA per (128-query tile, head, batch); streams K/V tiles; also computes D and stores it.
+//   MODE_DKV : one CTA per (128-key tile, head, batch);   streams Q/dO tiles; reads D.
+// The bf16 P / dS tile lives in shared memory as [q rows][kv cols] with 128-byte swizzled rows: the same bytes serve as
+// a K-major A operand (dS K) and as an MN-major A operand (P^T dO, dS^T Q), so no transpose is ever materialised.
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace ovk {
+
+constexpr int AB_T = 128;                   // tile rows (queries or keys)
+constexpr int AB_HD = 64;
+constexpr int AB_TILE = AB_T * 128;         // 16 KB: [128 rows x 64 bf16]
+constexpr int AB_SOFTMAX_WARPS = 8;
+constexpr int AB_THREADS = 32 * (AB_SOFTMAX_WARPS + 2);  // + TMA producer warp + MMA warp
+constexpr int AB_OFF_ST0 = 0;               // stationary tile 0 (DQ: Q_i   | DKV: K_j)
+constexpr int AB_OFF_ST1 = AB_OFF_ST0 + AB_TILE;  //            1 (DQ: dO_i  | DKV: V_j)
+constexpr int AB_OFF_SA = AB_OFF_ST1 + AB_TILE;   // streamed A x2 (DQ: K_j | DKV: Q_i)
+constexpr int AB_OFF_SB = AB_OFF_SA + 2 * AB_TILE;  // streamed B x2 (DQ: V_j | DKV: dO_i)
+constexpr int AB_OFF_P = AB_OFF_SB + 2 * AB_TILE;   // P  bf16 [128 x 128] as two 64-column atoms
+constexpr int AB_OFF_DS = AB_OFF_P + 2 * AB_TILE;   // dS bf16, same layout
+constexpr int AB_OFF_X = AB_OFF_DS + 2 * AB_TILE;   // extra tile (DQ: O_i for D = rowsum(dO . O))
+constexpr int AB_OFF_BAR = AB_OFF_X + AB_TILE;
+constexpr int AB_NUM_BARS = 10;
+constexpr int AB_SMEM_BYTES = AB_OFF_BAR + AB_NUM_BARS * 8 + 16;
+constexpr int AB_TMEM_COLS = 512;
+constexpr uint32_t AB_TM_S = 0, AB_TM_DP = 128, AB_TM_ACC0 = 256, AB_TM_ACC1 = 320;
+enum { MODE_DQ = 0, MODE_DKV = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
+                     const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
+                     const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (threadIdx.x == 0) printf("[ovk] attention_bwd: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
+  uint64_t* st_full = bars + 0;
+  uint64_t* sf = bars + 1;        // stream_full[2]
+  uint64_t* se = bars + 3;        // stream_empty[2]
+  uint64_t* s_full = bars + 5;    // S and dP of this iteration are in TMEM
+  uint64_t* pds_ready = bars + 6; // softmax wrote P / dS (and finished reading S / dP)
+  uint64_t* mma_done = bars + 7;  // accumulating MMAs of this iteration finished (P / dS smem reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + AB_OFF_BAR + AB_NUM_BARS * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t lane = lane_id();
+  const int t0 = blockIdx.x * AB_T;  // first row of the stationary tile
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nt = (L + AB_T - 1) / AB_T;  // number of streamed tiles
+  const float s2 = scale * 1.4426950408889634f;
+
+  if (warp == AB_SOFTMAX_WARPS && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQKV);
+    mbar_init(st_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sf[i], 1);
+      mbar_init(&se[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_ready, 32 * AB_SOFTMAX_WARPS);
+    mbar_init(mma_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == AB_SOFTMAX_WARPS + 1) tmem_alloc<AB_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == AB_SOFTMAX_WARPS) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ TMA producer
+      if (MODE == MODE_DQ) {
+        mbar_arrive_expect_tx(st_full, 3 * AB_TILE);
+        tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, h, t0, b);          // Q_i
+        tma_load_4d(smem + AB_OFF_ST1, &tmDO, st_full, 0, h, t0, b);           // dO_i
+        tma_load_4d(smem + AB_OFF_X, &tmO, st_full, 0, h, t0, b);              // O_i
+      } else {
+        mbar_arrive_expect_tx(st_full, 2 * AB_TILE);
+        tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, H + h, t0, b);      // K_j
+        tma_load_4d(smem + AB_OFF_ST1, &tmQKV, st_full, 0, 2 * H + h, t0, b);  // V_j
+      }
+      for (int it = 0; it < nt; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&se[s], ph ^ 1, 20);
+        mbar_arrive_expect_tx(&sf[s], 2 * AB_TILE);
+        if (MODE == MODE_DQ) {
+          tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, H + h, it * AB_T, b);      // K_j
+          tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmQKV, &sf[s], 0, 2 * H + h, it * AB_T, b);  // V_j
+        } else {
+          tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, h, it * AB_T, b);          // Q_i
+          tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmDO, &sf[s], 0, h, it * AB_T, b);           // dO_i
+        }
+      }
+    }
+  } else if (warp == AB_SOFTMAX_WARPS + 1) {
+    if (elect_one()) {
+      // ------------------------------------------------------------------ MMA issuer
+      mbar_wait(st_full, 0, 21);
+      const uint32_t st0 = smem_u32(smem + AB_OFF_ST0), st1 = smem_u32(smem + AB_OFF_ST1);
+      const uint32_t p_addr = smem_u32(smem + AB_OFF_P), ds_addr = smem_u32(smem + AB_OFF_DS);
+      for (int it = 0; it < nt; ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        const uint32_t sa = smem_u32(smem + AB_OFF_SA + s * AB_TILE), sb = smem_u32(smem + AB_OFF_SB + s * AB_TILE);
+        // key extent of this iteration's S / dP tiles
+        const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
+        const int q0 = (MODE == MODE_DQ) ? t0 : it * AB_T;
+        const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
+        const int nq = (min(AB_T, L - q0) + 15) & ~15;
+        const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
+        const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
+        const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
+        const uint32_t v_addr = (MODE == MODE_DQ) ? sb : st1;
+        mbar_wait(&sf[s], ph, 22);
+        tc_fence_after();
+        const uint32_t idesc_s = umma_idesc_bf16(AB_T, nkv, 0, 0);
+#pragma unroll
+        for (int k = 0; k < AB_HD / 16; ++k)   // S = Q K^T
+          umma_bf16_ss(tmem_base + AB_TM_S, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
+                       idesc_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < AB_HD / 16; ++k)   // dP = dO V^T
+          umma_bf16_ss(tmem_base + AB_TM_DP, umma_desc_kmajor_sw128(do_addr + k * 32), umma_desc_kmajor_sw128(v_addr + k * 32),
+                       idesc_s, k != 0);
+        umma_commit(s_full);
+        mbar_wait(pds_ready, it & 1, 23);
+        tc_fence_after();
+        if (MODE == MODE_DQ) {
+          // dQ += dS K_j : A = dS K-major (two 64-column atoms), B = K_j MN-major (rows = keys)
+          constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 0, 1);
+          for (int kk = 0; kk < nkv / 16; ++kk)
+            umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                         umma_desc_mnmajor_sw128(k_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+        } else {
+          // dV += P^T dO_i, dK += dS^T Q_i : A = (P | dS)^T MN-major (M = keys: two 64-key panels), B MN-major (rows = queries)
+          constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 1, 1);
+          for (int kk = 0; kk < nq / 16; ++kk)
+            umma_bf16_ss(tmem_base + AB_TM_ACC1, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
+                         umma_desc_mnmajor_sw128(do_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+          for (int kk = 0; kk < nq / 16; ++kk)
+            umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
+                         umma_desc_mnmajor_sw128(q_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+        }
+        umma_commit(&se[s]);
+        umma_commit(mma_done);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax / dS warps
+    const int quad = warp & 3;
+    const int hsel = warp >> 2;           // which 64 of the 128 key columns this thread handles
+    const int r = quad * 32 + lane;       // query row inside the tile = TMEM lane
+    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    const long long bh = static_cast<long long>(b) * H + h;
+    float lse2 = INFINITY, dlt = 0.f;
+    if (MODE == MODE_DQ) {
+      // D_i = rowsum(dO_i . O_i) from the stationary tiles (each of the two threads of a row computes all 64 terms)
+      mbar_wait(st_full, 0, 24);
+      const uint32_t o_s = smem_u32(smem + AB_OFF_X), do_s = smem_u32(smem + AB_OFF_ST1);
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 a = lds128(o_s + sw128_offset(r, c));
+        const uint4 g = lds128(do_s + sw128_offset(r, c));
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d = fmaf(bf16_lo(aw[q]), bf16_lo(gw[q]), fmaf(bf16_hi(aw[q]), bf16_hi(gw[q]), d));
+      }
+      dlt = d;
+      const int row = t0 + r;
+      if (row < L) {
+        lse2 = lse[bh * L + row] * 1.4426950408889634f;
+        if (hsel == 0) delta[bh * L + row] = d;
+      }
+    }
+    for (int it = 0; it < nt; ++it) {
+      const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
+      const int valid_kv = min(AB_T, L - kv0);
+      if (MODE == MODE_DKV) {
+        const int row = it * AB_T + r;
+        lse2 = row < L ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
+        dlt = row < L ? delta[bh * L + row] : 0.f;
+      }
+      mbar_wait(s_full, it & 1, 25);
+      tc_fence_after();
+      if (it > 0) mbar_wait(mma_done, (it - 1) & 1, 26);  // previous accumulating MMAs no longer read P / dS
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        const int col = hsel * 64 + c;
+        uint32_t sv[32], dv[32];
+        tmem_ld_x32(tmem_base + t_lane + AB_TM_S + col, sv);
+        tmem_ld_x32(tmem_base + t_lane + AB_TM_DP + col, dv);
+        tmem_ld_wait();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
+          float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
+          p0 = (col + 2 * j < valid_kv) ? p0 : 0.f;
+          p1 = (col + 2 * j + 1 < valid_kv) ? p1 : 0.f;
+          const float d0 = (col + 2 * j < valid_kv) ? p0 * (__uint_as_float(dv[2 * j]) - dlt) : 0.f;
+          const float d1 = (col + 2 * j + 1 < valid_kv) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dlt) : 0.f;
+          pp[j] = pack_bf16x2(p0, p1);
+          dd[j] = pack_bf16x2(d0, d1);
+        }
+        const uint32_t chunk0 = c >> 3;  // 16-byte chunk inside the 64-column atom
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (MODE == MODE_DKV)
+            sts128(smem_u32(smem + AB_OFF_P + hsel * AB_TILE) + sw128_offset(r, chunk0 + q),
+                   make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]));
+          sts128(smem_u32(smem + AB_OFF_DS + hsel * AB_TILE) + sw128_offset(r, chunk0 + q),
+                 make_uint4(dd[4 * q], dd[4 * q + 1], dd[4 * q + 2], dd[4 * q + 3]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_ready);
+    }
+    // -------------------------------------------------------------------- epilogue: accumulators -> bf16 -> TMA store
+    mbar_wait(mma_done, (nt - 1) & 1, 27);
+    tc_fence_after();
+    // staging reuses the P region: atom 0 <- ACC0 (dQ or dK), atom 1 <- ACC1 (dV)
+    if (MODE == MODE_DQ) {
+      uint32_t o[32];
+      tmem_ld_x32(tmem_base + t_lane + AB_TM_ACC0 + hsel * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sts128(smem_u32(smem + AB_OFF_P) + sw128_offset(r, hsel * 4 + q),
+               make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * scale, __uint_as_float(o[8 * q + 1]) * scale),
+                          pack_bf16x2(__uint_as_float(o[8 * q + 2]) * scale, __uint_as_float(o[8 * q + 3]) * scale),
+                          pack_bf16x2(__uint_as_float(o[8 * q + 4]) * scale, __uint_as_float(o[8 * q + 5]) * scale),
+                          pack_bf16x2(__uint_as_float(o[8 * q + 6]) * scale, __uint_as_float(o[8 * q + 7]) * scale)));
+    } else {
+      const float mul = hsel == 0 ? scale : 1.f;   // hsel 0: dK (scaled), hsel 1: dV
+      const uint32_t src = hsel == 0 ? AB_TM_ACC0 : AB_TM_ACC1;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t o[32];
+        tmem_ld_x32(tmem_base + t_lane + src + c, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          sts128(smem_u32(smem + AB_OFF_P + hsel * AB_TILE) + sw128_offset(r, (c >> 3) + q),
+                 make_uint4(pack_bf16x2(__uint_as_float(o[8 * q]) * mul, __uint_as_float(o[8 * q + 1]) * mul),
+                            pack_bf16x2(__uint_as_float(o[8 * q + 2]) * mul, __uint_as_float(o[8 * q + 3]) * mul),
+                            pack_bf16x2(__uint_as_float(o[8 * q + 4]) * mul, __uint_as_float(o[8 * q + 5]) * mul),
+                            pack_bf16x2(__uint_as_float(o[8 * q + 6]) * mul, __uint_as_float(o[8 * q + 7]) * mul)));
+      }
+    }
+    fence_proxy_async_smem();
+    named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
+    if (threadIdx.x == 0) {
+      if (MODE == MODE_DQ) {
+        tma_store_4d(&tmDQKV, smem + AB_OFF_P, 0, h, t0, b);
+      } else {
+        tma_store_4d(&tmDQKV, smem + AB_OFF_P, 0, H + h, t0, b);
+        tma_store_4d(&tmDQKV, smem + AB_OFF_P + AB_TILE, 0, 2 * H + h, t0, b);
+      }
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AB_SOFTMAX_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<AB_TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace ovk
+
+using namespace ovk;
+
+extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                 float* delta, int B, int L, int H, int hd, float scale, void* stream) {
+  if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
+  if (hd != AB_HD) return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (this build: 64)", hd);
+  if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention_bwd: B and H must be <= 65535");
+  if (!lse || !delta) return set_error(OVK_ERR_SHAPE, "attention_bwd: lse and delta buffers are required");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  CUtensorMap tmQKV, tmDQKV, tmO, tmDO;
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * H), (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)3 * H * hd * 2, (uint64_t)L * 3 * H * hd * 2};
+    const uint32_t box[4] = {(uint32_t)hd, 1, AB_T, 1};
+    if ((rc = make_tmap_nd_bf16(&tmQKV, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmDQKV, dqkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)H * hd * 2, (uint64_t)L * H * hd * 2};
+    const uint32_t box[4] = {(uint32_t)hd, 1, AB_T, 1};
+    if ((rc = make_tmap_nd_bf16(&tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmDO, dout, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((L + AB_T - 1) / AB_T, H, B);
+  attention_bwd_kernel<MODE_DQ><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, lse, delta, L, H, scale);
+  if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
+  attention_bwd_kernel<MODE_DKV><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, lse, delta, L, H, scale);
+  return check_launch("attention_bwd_kernel<dKdV>");
+}

@@ -2,56 +2,11 @@
 // Replaces the reference's F.linear / addmm call sites (open_clip/transformer.py:225,233-235,250-252 via
 // nn.MultiheadAttention in_proj/out_proj and mlp.c_fc/c_proj, :645-646 pooled @ proj) and, in the backward pass, the
 // dgrad / wgrad matmuls autograd derives from them, with fused bias / GELU / residual / GELU' epilogues.
+#include "act.cuh"
 #include "gemm_core.cuh"
 #include "host_utils.h"
 
 namespace ovk {
-
-// Activations of the reference surface in ONE functional form:  act(x) = x * sigmoid(2 q(x)),
-//   q(x) = xc (a0 + a1 xc^2 + a2 xc^4), xc = clamp(x, -8, 8)
-//   nn.GELU() exact-erf (transformer.py:232-236, JAX approximate=False vit.py:198-202): Phi(x) = sigmoid(2 atanh(erf(x/sqrt2)))
-//       with the odd function atanh(erf(x/sqrt2)) fitted by a0..a2 below: |act - gelu_erf| <= 3.0e-5 for all x
-//       (an order of magnitude below bf16 rounding of the output).
-//   nn.GELU(approximate='tanh') (text tower act_kwargs): exact, a = (sqrt(2/pi), 0.044715 sqrt(2/pi), 0).
-//   QuickGELU x*sigmoid(1.702x) (transformer.py:33-36): exact, a = (0.851, 0, 0).
-// sigmoid(2q) = 1 / (1 + 2^(t)), t = -2 log2(e) q  -> one ex2 + one rcp (MUFU) and 6 FMA-pipe ops per element.
-struct ActCoef {
-  float b0, b1, b2;  // t(x)  = xc (b0 + b1 x2 + b2 x2^2),  b_i = -2 log2(e) a_i
-  float d0, d1, d2;  // 2q'(x) = d0 + d1 x2 + d2 x2^2,      d = (2 a0, 6 a1, 10 a2)   (0 outside the clamp)
-};
-
-static ActCoef act_coef(int act) {
-  double a0 = 0, a1 = 0, a2 = 0;
-  if (act == OVK_EPI_GELU_ERF) {
-    a0 = 0.7974584707815301, a1 = 0.03705034510095251, a2 = -0.0003587323612208004;
-  } else if (act == OVK_EPI_GELU_TANH) {
-    a0 = 0.7978845608028654, a1 = 0.7978845608028654 * 0.044715;
-  } else if (act == OVK_EPI_GELU_QUICK) {
-    a0 = 0.851;
-  }
-  const double c = -2.0 * 1.4426950408889634;
-  ActCoef k;
-  k.b0 = (float)(c * a0), k.b1 = (float)(c * a1), k.b2 = (float)(c * a2);
-  k.d0 = (float)(2 * a0), k.d1 = (float)(6 * a1), k.d2 = (float)(10 * a2);
-  return k;
-}
-
-__device__ __forceinline__ float act_fwd(float x, const ActCoef& k) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  const float t = xc * fmaf(fmaf(k.b2, x2, k.b1), x2, k.b0);
-  return x * fast_rcp(1.f + fast_exp2(t));
-}
-// d/dx [x sigmoid(2q(x))] = s (1 + x (1 - s) 2q'(x)),  1 - s = e s
-__device__ __forceinline__ float act_bwd(float x, const ActCoef& k) {
-  const float xc = fminf(fmaxf(x, -8.f), 8.f);
-  const float x2 = xc * xc;
-  const float t = xc * fmaf(fmaf(k.b2, x2, k.b1), x2, k.b0);
-  const float e = fast_exp2(t);
-  const float s = fast_rcp(1.f + e);
-  const float qp = (fabsf(x) < 8.f) ? fmaf(fmaf(k.d2, x2, k.d1), x2, k.d0) : 0.f;
-  return s * fmaf(x * qp, e * s, 1.f);
-}
 
 enum { EPI_LINEAR = 0, EPI_ACT = 1, EPI_DACT = 2 };
 
@@ -274,10 +229,7 @@ static int check_common(const GemmArgs& g, const char* who) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return set_error(OVK_ERR_SHAPE, "%s: empty problem M=%d N=%d K=%d", who, g.M, g.N, g.K);
   if ((g.lda % 8) || (g.ldb % 8) || (g.ldc % (g.c_f32 ? 4 : 8)))
     return set_error(OVK_ERR_ALIGN, "%s: leading dimensions must be multiples of 16 bytes (TMA strides)", who);
-  if (!g.a_mn && (g.K % 8)) return set_error(OVK_ERR_ALIGN, "%s: K must be a multiple of 8", who);
-  if (g.a_mn && (g.M % 8)) return set_error(OVK_ERR_ALIGN, "%s: M must be a multiple of 8 for a transposed A", who);
-  if (!g.b_mn && (g.K % 8)) return set_error(OVK_ERR_ALIGN, "%s: K must be a multiple of 8", who);
-  if (g.N % 8) return set_error(OVK_ERR_ALIGN, "%s: N must be a multiple of 8", who);
+  // extents need no alignment (TMA zero-fills out-of-bounds box elements); only strides and base pointers do
   if (g.R && (g.ldr % 8)) return set_error(OVK_ERR_ALIGN, "%s: ldr must be a multiple of 8", who);
   if (g.D && (g.ldd % 8)) return set_error(OVK_ERR_ALIGN, "%s: ldd must be a multiple of 8", who);
   return OVK_OK;

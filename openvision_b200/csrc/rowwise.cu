@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
                                                             const __nv_bfloat16* __restrict__ x, long long ldx,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            __nv_bfloat16* __restrict__ dx, long long lddx,
+                                                            const __nv_bfloat16* dres, long long lddres,
+                                                            __nv_bfloat16* dx, long long lddx,
                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                             int rows, int D, int rows_per_block) {
   extern __shared__ float red[];  // [2][D]
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const float m1 = warp_sum(s1) / static_cast<float>(D);
     const float m2 = warp_sum(s2) / static_cast<float>(D);
     uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+    const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
@@ -162,6 +164,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
+        if (drr) {  // gradient arriving through the residual connection around the normalised branch
+          float r[8];
+          unpack8(drr[v], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
         dxr[v] = pack8(o);
       }
     }
@@ -189,24 +197,26 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
 // k = (c*P + ph)*P + pw  <->  images[b, c, gy*P + ph, gx*P + pw].   transformer.py:469,610-612.
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ img, __nv_bfloat16* __restrict__ cols,
-                                                     long long ldc, int B, int H, int W, int P) {
+                                                     long long ldc, int B, int H, int W, int P, int lead) {
   const int gh = H / P, gw = W / P;
   const int K = 3 * P * P;
   const int vec_per_row = static_cast<int>(ldc >> 3);
-  const long long total = static_cast<long long>(B) * gh * gw * vec_per_row;
+  const int rpi = gh * gw + lead;  // rows per image; the `lead` rows in front of each image's patches are zero
+  const long long total = static_cast<long long>(B) * rpi * vec_per_row;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int v = static_cast<int>(idx % vec_per_row);
     const long long r = idx / vec_per_row;
-    const int gx = static_cast<int>(r % gw);
-    const int gy = static_cast<int>((r / gw) % gh);
-    const int b = static_cast<int>(r / (static_cast<long long>(gw) * gh));
+    const int rr = static_cast<int>(r % rpi) - lead;
+    const int b = static_cast<int>(r / rpi);
+    const int gx = rr % gw;
+    const int gy = rr / gw;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = v * 8 + j;
       float val = 0.f;
-      if (k < K) {
+      if (k < K && rr >= 0) {
         const int pw = k % P;
         const int ph = (k / P) % P;
         const int c = k / (P * P);
@@ -221,9 +231,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ img, 
 
 // ------------------------------------------------------------------------------------------------ cls / pos assembly
 // transformer.py:615-617: x = cat([class_embedding, patches]) + positional_embedding.
-__global__ void __launch_bounds__(256) embed_assemble_kernel(const __nv_bfloat16* __restrict__ patch,
-                                                             const float* __restrict__ cls, const float* __restrict__ pos,
-                                                             __nv_bfloat16* __restrict__ tokens, int B, int N, int D) {
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const __nv_bfloat16* patch, const float* __restrict__ cls,
+                                                             const float* __restrict__ pos, __nv_bfloat16* tokens,
+                                                             int B, int N, int D, int lead) {
   const int L = N + 1;
   const int dv = D >> 3;
   const long long total = static_cast<long long>(B) * L * dv;
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const __nv_bfloat16
       const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls) + 2 * v + 1);
       f[0] = c0.x; f[1] = c0.y; f[2] = c0.z; f[3] = c0.w; f[4] = c1.x; f[5] = c1.y; f[6] = c1.z; f[7] = c1.w;
     } else {
-      unpack8(*reinterpret_cast<const uint4*>(patch + (b * N + (l - 1)) * D + v * 8), f);
+      unpack8(*reinterpret_cast<const uint4*>(patch + (b * (N + lead) + (l - 1 + lead)) * D + v * 8), f);
     }
     const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D) + 2 * v);
     const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + static_cast<long long>(l) * D) + 2 * v + 1);
@@ -355,10 +365,10 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
 }
 
 extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,
-                                 const float* mean, const float* rstd, void* dx, long long lddx, float* dgamma,
-                                 float* dbeta, int rows, int D, void* stream) {
+                                 const float* mean, const float* rstd, const void* dres, long long lddres, void* dx,
+                                 long long lddx, float* dgamma, float* dbeta, int rows, int D, void* stream) {
   if (rows <= 0 || D <= 0) return set_error(OVK_ERR_SHAPE, "layernorm_bwd: empty input");
-  if ((D % 8) || (ldx % 8) || (lddy % 8) || (lddx % 8))
+  if ((D % 8) || (ldx % 8) || (lddy % 8) || (lddx % 8) || (dres && (lddres % 8)))
     return set_error(OVK_ERR_ALIGN, "layernorm_bwd: D and leading dimensions must be multiples of 8");
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm_bwd: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -371,36 +381,42 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
-  if (D <= 256) layernorm_bwd_kernel<1><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else if (D <= 512) layernorm_bwd_kernel<2><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else if (D <= 1024) layernorm_bwd_kernel<4><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else layernorm_bwd_kernel<8><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  auto drp = reinterpret_cast<const __nv_bfloat16*>(dres);
+  if (D <= 256) layernorm_bwd_kernel<1><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else if (D <= 512) layernorm_bwd_kernel<2><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else if (D <= 1024) layernorm_bwd_kernel<4><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
+  else layernorm_bwd_kernel<8><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
   return check_launch("layernorm_bwd_kernel");
 }
 
 extern "C" int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long ldc, int B, int H, int W,
-                                  int P, void* stream) {
+                                  int P, int lead_rows, void* stream) {
   if (B <= 0 || P <= 0 || H % P || W % P) return set_error(OVK_ERR_SHAPE, "im2col: H=%d W=%d not divisible by P=%d", H, W, P);
   if (ldc % 8 || ldc < 3LL * P * P) return set_error(OVK_ERR_ALIGN, "im2col: ldc must be a multiple of 8 and >= 3*P*P");
+  if (lead_rows < 0 || lead_rows > 1) return set_error(OVK_ERR_SHAPE, "im2col: lead_rows must be 0 or 1");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const long long total = static_cast<long long>(B) * (H / P) * (W / P) * (ldc / 8);
+  const long long total = static_cast<long long>(B) * ((H / P) * (W / P) + lead_rows) * (ldc / 8);
   const int grid = grid_for(total, 256);
   if (img_is_f32)
     im2col_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(images),
-                                              reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P);
+                                              reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P, lead_rows);
   else
     im2col_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(images),
-                                                      reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P);
+                                                      reinterpret_cast<__nv_bfloat16*>(cols), ldc, B, H, W, P, lead_rows);
   return check_launch("im2col_kernel");
 }
 
-extern "C" int ovk_embed_assemble(const void* patch, const float* cls, const float* pos, void* tokens, int B, int N,
-                                  int D, void* stream) {
+extern "C" int ovk_embed_assemble(const void* patch, int patch_lead_rows, const float* cls, const float* pos,
+                                  void* tokens, int B, int N, int D, void* stream) {
   if (B <= 0 || N <= 0 || D <= 0 || D % 8) return set_error(OVK_ERR_SHAPE, "embed_assemble: bad shape B=%d N=%d D=%d", B, N, D);
+  if (patch_lead_rows < 0 || patch_lead_rows > 1) return set_error(OVK_ERR_SHAPE, "embed_assemble: lead rows must be 0 or 1");
+  if (patch == tokens && patch_lead_rows != 1)
+    return set_error(OVK_ERR_SHAPE, "embed_assemble: in-place operation needs the [B, N+1, D] patch layout");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(B) * (N + 1) * (D / 8);
   embed_assemble_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(patch), cls, pos,
-                                                             reinterpret_cast<__nv_bfloat16*>(tokens), B, N, D);
+                                                             reinterpret_cast<__nv_bfloat16*>(tokens), B, N, D,
+                                                             patch_lead_rows);
   return check_launch("embed_assemble_kernel");
 }
 

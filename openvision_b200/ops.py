@@ -178,22 +178,28 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx=None):
-    """dx, and (accumulated) dgamma / dbeta of LayerNorm. Kernel: layernorm_bwd_kernel."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx=None, dres=None):
+    """dx (+ dres: the gradient coming through the residual connection), and (accumulated) dgamma / dbeta of LayerNorm.
+    Kernel: layernorm_bwd_kernel."""
     _require(dy, torch.bfloat16, "layernorm_bwd.dy", 2)
     _require(x, torch.bfloat16, "layernorm_bwd.x", 2)
     rows, D = x.shape
     if dx is None:
         dx = torch.empty((rows, D), dtype=torch.bfloat16, device=x.device)
-    _lib.call("ovk_layernorm_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(mean), _p(rstd), _p(dx),
-              dx.stride(0), _p(dgamma), _p(dbeta), rows, D, _stream())
+    if dres is not None:
+        _require(dres, torch.bfloat16, "layernorm_bwd.dres", 2)
+    with _timed("layernorm_bwd", (8.0 if dres is not None else 6.0) * rows * D):
+        _lib.call("ovk_layernorm_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(mean), _p(rstd), _p(dres),
+                  dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), _p(dgamma), _p(dbeta), rows, D,
+                  _stream())
     _count()
     return dx
 
 
-def im2col_patches(images: torch.Tensor, patch: int, ldc: int) -> torch.Tensor:
-    """images [B,3,H,W] (fp32 or bf16, NCHW contiguous) -> bf16 [B*gh*gw, ldc], columns ordered like
-    conv1.weight.reshape(D, 3*P*P), zero padded to ldc. Kernel: im2col_kernel."""
+def im2col_patches(images: torch.Tensor, patch: int, ldc: int, lead_rows: int = 0) -> torch.Tensor:
+    """images [B,3,H,W] (fp32 or bf16, NCHW contiguous) -> bf16 [B*(gh*gw + lead_rows), ldc], columns ordered like
+    conv1.weight.reshape(D, 3*P*P), zero padded to ldc; lead_rows=1 inserts a zero row per image (the cls slot).
+    Kernel: im2col_kernel."""
     if images.dtype not in (torch.float32, torch.bfloat16):
         raise OvkError(f"im2col: images must be fp32 or bf16, got {images.dtype}")
     _require(images, images.dtype, "im2col.images", 4)
@@ -202,26 +208,33 @@ def im2col_patches(images: torch.Tensor, patch: int, ldc: int) -> torch.Tensor:
     B, C, H, W = images.shape
     if C != 3:
         raise OvkError("im2col: expected 3 input channels")
-    rows = B * (H // patch) * (W // patch)
+    rows = B * ((H // patch) * (W // patch) + lead_rows)
     cols = torch.empty((rows, ldc), dtype=torch.bfloat16, device=images.device)
     _lib.call("ovk_im2col_patches", _p(images), int(images.dtype == torch.float32), _p(cols), ldc, B, H, W, patch,
-              _stream())
+              int(lead_rows), _stream())
     _count()
     return cols
 
 
-def embed_assemble(patch_tokens: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, N: int) -> torch.Tensor:
-    """tokens[b,0]=cls+pos[0]; tokens[b,1+n]=patch_tokens[b*N+n]+pos[1+n]  -> bf16 [B, N+1, D]. Kernel: embed_assemble_kernel."""
+def embed_assemble(patch_tokens: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, N: int,
+                   inplace: bool = False) -> torch.Tensor:
+    """tokens[b,0]=cls+pos[0]; tokens[b,1+n]=patch[b,n]+pos[1+n]  -> bf16 [B, N+1, D]. patch_tokens is [B*N, D] or, with
+    one lead row per image (GEMM output of im2col(lead_rows=1)), [B*(N+1), D]; the latter may be updated in place.
+    Kernel: embed_assemble_kernel."""
     _require(patch_tokens, torch.bfloat16, "embed_assemble.patch", 2)
     _require(cls, torch.float32, "embed_assemble.cls", 1)
     _require(pos, torch.float32, "embed_assemble.pos", 2)
     D = patch_tokens.shape[1]
     if not patch_tokens.is_contiguous() or not pos.is_contiguous():
         raise OvkError("embed_assemble: inputs must be contiguous")
-    if patch_tokens.shape[0] != B * N or tuple(pos.shape) != (N + 1, D) or cls.numel() != D:
+    lead = 1 if patch_tokens.shape[0] == B * (N + 1) else 0
+    if patch_tokens.shape[0] != B * (N + lead) or tuple(pos.shape) != (N + 1, D) or cls.numel() != D:
         raise OvkError("embed_assemble: shape mismatch")
-    tokens = torch.empty((B, N + 1, D), dtype=torch.bfloat16, device=patch_tokens.device)
-    _lib.call("ovk_embed_assemble", _p(patch_tokens), _p(cls), _p(pos), _p(tokens), B, N, D, _stream())
+    if inplace and not lead:
+        raise OvkError("embed_assemble: in-place needs the [B*(N+1), D] layout")
+    tokens = patch_tokens.view(B, N + 1, D) if inplace else torch.empty((B, N + 1, D), dtype=torch.bfloat16,
+                                                                        device=patch_tokens.device)
+    _lib.call("ovk_embed_assemble", _p(patch_tokens), lead, _p(cls), _p(pos), _p(tokens), B, N, D, _stream())
     _count()
     return tokens
 
@@ -329,3 +342,99 @@ def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale: float, row_lse, 
                   _p(row_lse), _p(col_lse), float(w_row), float(w_col), _p(G), ldg, _p(d_scale), _stream())
     _count()
     return G[:, :n_all] if ldg != n_all else G
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# backward kernels of the image tower
+# ----------------------------------------------------------------------------------------------------------------
+def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: Optional[float] = None) -> torch.Tensor:
+    """dqkv bf16 [B*L, 3*H*hd] from qkv, the forward output, its gradient and the saved lse.
+    Kernels: attention_bwd_kernel<dQ>, attention_bwd_kernel<dKdV>."""
+    for t, name, cols in ((qkv, "qkv", 3 * H * hd), (out, "out", H * hd), (dout, "dout", H * hd)):
+        _require(t, torch.bfloat16, f"attention_bwd.{name}", 2)
+        if not t.is_contiguous() or tuple(t.shape) != (B * L, cols):
+            raise OvkError(f"attention_bwd: {name} must be contiguous [B*L, {cols}], got {tuple(t.shape)}")
+    _require(lse, torch.float32, "attention_bwd.lse", 3)
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device)
+    if scale is None:
+        scale = 1.0 / math.sqrt(hd)
+    with _timed("attention_bwd", 14.0 * B * H * L * L * hd):
+        _lib.call("ovk_attention_bwd", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), B, L, H, hd,
+                  float(scale), _stream())
+    _count(2)
+    return dqkv
+
+
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[c] (+)= sum_r x[r,c]; x bf16 [rows, cols] -> fp32 [cols]. Kernel: colsum_kernel."""
+    _require(x, torch.bfloat16, "colsum.x", 2)
+    rows, cols = x.shape
+    if out is None:
+        out = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    with _timed("colsum", 2.0 * rows * cols):
+        _lib.call("ovk_colsum_bf16", _p(x), x.stride(0), rows, cols, _p(out), _stream())
+    _count()
+    return out
+
+
+def pool_tokens_bwd(dpooled: torch.Tensor, B: int, L: int, mode: str) -> torch.Tensor:
+    """gradient of pool_tokens: bf16 [B,D] -> bf16 [B,L,D] (every element written). Kernel: pool_tokens_bwd_kernel."""
+    _require(dpooled, torch.bfloat16, "pool_tokens_bwd.dpooled", 2)
+    if not dpooled.is_contiguous():
+        raise OvkError("pool_tokens_bwd: dpooled must be contiguous")
+    D = dpooled.shape[1]
+    dx = torch.empty((B, L, D), dtype=torch.bfloat16, device=dpooled.device)
+    _lib.call("ovk_pool_tokens_bwd", _p(dpooled), _p(dx), B, L, D, {"avg": 0, "tok": 1}[mode], _stream())
+    _count()
+    return dx
+
+
+def l2_normalize_bwd(x: torch.Tensor, dy: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """gradient of F.normalize w.r.t. x (bf16 [rows,E]); dy fp32 or bf16. Kernel: l2_normalize_bwd_kernel."""
+    _require(x, torch.bfloat16, "l2_normalize_bwd.x", 2)
+    if dy.dtype not in (torch.float32, torch.bfloat16):
+        raise OvkError("l2_normalize_bwd: dy must be fp32 or bf16")
+    _require(dy, dy.dtype, "l2_normalize_bwd.dy", 2)
+    if not x.is_contiguous() or not dy.is_contiguous() or dy.shape != x.shape:
+        raise OvkError("l2_normalize_bwd: x and dy must be contiguous and of the same shape")
+    rows, E = x.shape
+    dx = torch.empty_like(x)
+    _lib.call("ovk_l2_normalize_bwd", _p(x), _p(dy), int(dy.dtype == torch.float32), _p(dx), rows, E, float(eps), _stream())
+    _count()
+    return dx
+
+
+def col2im_patches(dcols: torch.Tensor, B: int, H: int, W: int, patch: int, lead_rows: int, out_dtype) -> torch.Tensor:
+    """gradient w.r.t. the images from the gradient of the im2col matrix. Kernel: col2im_kernel."""
+    _require(dcols, torch.bfloat16, "col2im.dcols", 2)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise OvkError("col2im: output dtype must be fp32 or bf16")
+    dimg = torch.empty((B, 3, H, W), dtype=out_dtype, device=dcols.device)
+    _lib.call("ovk_col2im_patches", _p(dcols), dcols.stride(0), _p(dimg), int(out_dtype == torch.float32), B, H, W, patch,
+              int(lead_rows), _stream())
+    _count()
+    return dimg
+
+
+def act_fwd(x: torch.Tensor, act: str) -> torch.Tensor:
+    """y = act(x) elementwise (bf16; numel % 8 == 0). Kernel: act_kernel<fwd>."""
+    _require(x, torch.bfloat16, "act_fwd.x")
+    if not x.is_contiguous():
+        raise OvkError("act_fwd: x must be contiguous")
+    y = torch.empty_like(x)
+    _lib.call("ovk_act_fwd", _p(x), _p(y), x.numel(), _ACT[act], _stream())
+    _count()
+    return y
+
+
+def act_bwd(x: torch.Tensor, dy: torch.Tensor, act: str) -> torch.Tensor:
+    """dx = dy * act'(x) elementwise (bf16). Kernel: act_kernel<bwd>."""
+    _require(x, torch.bfloat16, "act_bwd.x")
+    _require(dy, torch.bfloat16, "act_bwd.dy")
+    if not x.is_contiguous() or not dy.is_contiguous() or x.shape != dy.shape:
+        raise OvkError("act_bwd: x and dy must be contiguous and of the same shape")
+    dx = torch.empty_like(x)
+    _lib.call("ovk_act_bwd", _p(x), _p(dy), _p(dx), x.numel(), _ACT[act], _stream())
+    _count()
+    return dx

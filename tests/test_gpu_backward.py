@@ -1,0 +1,198 @@
+"""GPU parity of the backward pass: kernel by kernel against autograd of the CPU oracle, and end to end (tower + loss)
+against the gradients of the unmodified reference (tests/golden/tower_*.npz).  The whole chain runs in bf16 with fp32
+accumulation, so gradients are compared in relative L2 norm (<= 5e-2) and max-abs relative to the largest entry."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import openvision_b200 as ovb
+from oracle import synth, vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from openvision_b200 import ops as _ops
+    return _ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def rel_l2(got, ref):
+    got = torch.as_tensor(got).double().cpu().reshape(-1)
+    ref = torch.as_tensor(ref).double().cpu().reshape(-1)
+    return float((got - ref).norm() / (ref.norm() + 1e-30))
+
+
+def assert_grad(got, ref, what, tol=5e-2, abs_floor=1e-6):
+    """||got - ref|| <= tol * ||ref|| + abs_floor * sqrt(n)  (the floor covers gradients that are exactly zero)"""
+    assert torch.isfinite(torch.as_tensor(got).float()).all(), f"{what}: non-finite gradient"
+    g = torch.as_tensor(got).double().cpu().reshape(-1)
+    r = torch.as_tensor(ref).double().cpu().reshape(-1)
+    err, bound = float((g - r).norm()), tol * float(r.norm()) + abs_floor * math.sqrt(r.numel())
+    assert err <= bound, f"{what}: L2 error {err:.3e} > {bound:.3e} (relative {rel_l2(got, ref):.3e})"
+
+
+@pytest.mark.parametrize("B,L,H", [(1, 128, 1), (2, 64, 2), (3, 101, 3), (2, 257, 4), (1, 577, 2), (1, 16, 1), (2, 129, 1),
+                                   (1, 1, 1), (2, 200, 2)])
+def test_attention_bwd(ops, B, L, H):
+    hd = 64
+    qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
+    dout = rnd(B * L, H * hd, seed=L + 1).bfloat16()
+    qc = qkv.cuda()
+    out, lse = ops.attention(qc, B, L, H, hd, save_lse=True)
+    dqkv = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), -1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd)
+    o.backward(dout.float())
+    g = dqkv.float().cpu().view(B, L, 3, H, hd)
+    r = qf.grad.view(B, L, 3, H, hd)
+    for i, name in enumerate("qkv"):
+        assert_grad(g[:, :, i], r[:, :, i], f"attention d{name} B{B} L{L} H{H}", 3e-2)
+
+
+def test_small_backward_kernels(ops):
+    # colsum
+    x = rnd(1000, 776, seed=0).bfloat16()
+    s = ops.colsum(x.cuda())
+    np.testing.assert_allclose(s.cpu().numpy(), x.float().sum(0).numpy(), rtol=1e-4, atol=1e-3)
+    # layernorm bwd with the residual gradient folded in
+    rows, D = 515, 1024
+    xx = (rnd(rows, D, seed=1) * 2 + 0.3).bfloat16()
+    dy, dres = rnd(rows, D, seed=2).bfloat16(), rnd(rows, D, seed=3).bfloat16()
+    g, b = rnd(D, seed=4), rnd(D, seed=5)
+    _, mean, rstd = ops.layernorm(xx.cuda(), g.cuda(), b.cuda(), 1e-6, save_stats=True)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dx = ops.layernorm_bwd(dy.cuda(), xx.cuda(), g.cuda(), mean, rstd, dg, db, dres=dres.cuda())
+    xf = xx.float().requires_grad_(True)
+    O.layer_norm(xf, g, b, 1e-6).backward(dy.float())
+    assert_grad(dx, xf.grad + dres.float(), "layernorm bwd + residual", 1e-2)
+    # l2 normalise bwd
+    e = (rnd(300, 768, seed=6) * 3).bfloat16()
+    d = rnd(300, 768, seed=7)
+    dxn = ops.l2_normalize_bwd(e.cuda(), d.cuda())
+    ef = e.float().requires_grad_(True)
+    O.l2_normalize(ef).backward(d)
+    assert_grad(dxn, ef.grad, "l2 normalise bwd", 1e-2)
+    # pooling bwd
+    dp = rnd(4, 256, seed=8).bfloat16()
+    dxa = ops.pool_tokens_bwd(dp.cuda(), 4, 11, "avg").float().cpu()
+    assert torch.equal(dxa[:, 0], torch.zeros(4, 256)) and torch.allclose(dxa[:, 3], (dp.float() / 10).bfloat16().float())
+    dxt = ops.pool_tokens_bwd(dp.cuda(), 4, 11, "tok").float().cpu()
+    assert torch.equal(dxt[:, 0], dp.float()) and dxt[:, 1:].abs().sum() == 0
+    # activation module fwd / bwd
+    u = (rnd(64, 512, seed=9) * 2).bfloat16()
+    gy = rnd(64, 512, seed=10).bfloat16()
+    for kind, okind in (("gelu", "erf"), ("gelu_tanh", "tanh"), ("quick_gelu", "quick")):
+        y = ops.act_fwd(u.cuda(), kind)
+        uf = u.float().requires_grad_(True)
+        ref = O.gelu(uf, okind)
+        ref.backward(gy.float())
+        assert (y.float().cpu() - ref.detach()).abs().max() <= 1e-2 * ref.abs().max()
+        assert_grad(ops.act_bwd(u.cuda(), gy.cuda(), kind), uf.grad, f"act bwd {kind}", 1e-2)
+
+
+@pytest.mark.parametrize("B,H,P,D", [(2, 48, 16, 128), (2, 56, 14, 128)])
+def test_patch_embed_backward(ops, B, H, P, D):
+    from openvision_b200.transformer import PatchEmbedConv
+    conv = PatchEmbedConv(3, D, P, P, bias=False).cuda()
+    img = rnd(B, 3, H, H, seed=0).cuda().requires_grad_(True)
+    out = conv(img)                                            # stock contract: [B, D, gh, gw]
+    gy = rnd(*out.shape, seed=1).cuda()
+    out.backward(gy)
+    wf = conv.weight.detach().float().cpu().requires_grad_(True)
+    xf = img.detach().float().cpu().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xf, wf, stride=P)         # reference call site transformer.py:469,610
+    ref.backward(gy.float().cpu())
+    assert_grad(out.detach(), ref.detach(), "conv1 forward", 1e-2)
+    assert_grad(img.grad, xf.grad, "d images", 2e-2)
+    assert_grad(conv.weight.grad, wf.grad, "d conv1.weight", 2e-2)
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("mini-ov", 4), ("mini-stock", 4)])
+def test_tower_and_loss_gradients_match_reference(golden, cfg_name, batch):
+    g = golden(f"tower_{cfg_name}.npz")
+    cfg = synth.CONFIGS[cfg_name]
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(synth.make_state_dict(cfg_name, 0), strict=True)
+    m = m.cuda().train()
+    images = synth.make_images(cfg_name, batch, 0).cuda().requires_grad_(True)
+    text = synth.make_text(cfg_name, batch, 0).cuda()
+    if cfg["text"].get("no_causal_mask", False):
+        img_n, txt_n, scale = m(images, text)
+    else:   # stock config has a causal text tower (outside the hot path): feed the reference's text features
+        img_n = m.encode_image(images, normalize=True)
+        txt_n = torch.as_tensor(g["text_features_norm"]).float().cuda()
+        scale = m.logit_scale.exp()
+    loss = ovb.ClipLoss()(img_n, txt_n, scale)
+    loss.backward()
+    ref_loss = float(g["loss"])
+    assert abs(float(loss) - ref_loss) <= 2e-2 * abs(ref_loss) + 1e-3, (float(loss), ref_loss)
+    assert_grad(images.grad, g["grad_images"], "d images")
+    checked = 0
+    for name, p in m.named_parameters():
+        key = "grad/" + name
+        if key not in g or not name.startswith(("visual.", "logit_scale")):
+            continue
+        assert p.grad is not None, name
+        ref = g[key]
+        got = p.grad.detach().float().cpu().numpy()
+        if got.size > 4096:
+            got = got.reshape(-1)[::5]
+        tol = 6e-2 if "ln_" not in name else 8e-2
+        assert_grad(got, ref, name, tol)
+        checked += 1
+    assert checked >= 25, checked
+
+
+def test_ti16_image_gradient_and_checkpointing(golden):
+    """12-layer tower: gradient w.r.t. the images (what ov-gradient-ascent / feature-visualisation optimise) against
+    the reference; and activation checkpointing (set_grad_checkpointing) must give the same gradients."""
+    cfg_name, batch = "Ti16-160", 8
+    g = golden(f"tower_{cfg_name}.npz")
+    cfg = synth.CONFIGS[cfg_name]
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(synth.make_state_dict(cfg_name, 0), strict=True)
+    m = m.cuda().train()
+    text = synth.make_text(cfg_name, batch, 0).cuda()
+    grads = []
+    for ckpt in (False, True):
+        m.set_grad_checkpointing(ckpt)
+        m.zero_grad(set_to_none=True)
+        images = synth.make_images(cfg_name, batch, 0).cuda().requires_grad_(True)
+        img_n, txt_n, scale = m(images, text)
+        ovb.ClipLoss()(img_n, txt_n, scale).backward()
+        grads.append((images.grad.clone(), m.visual.conv1.weight.grad.clone()))
+    got = grads[0][0].float().cpu().numpy().reshape(-1)[::5]
+    assert_grad(got, g["grad_images"], "Ti16 d images", 8e-2)
+    assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1]), "checkpointed != plain"
+
+
+def test_gelu_hook_gradients_reach_the_image():
+    """ov-feature-visualization: loss = -mean(post-GELU feature of layer l) optimised w.r.t. the input image."""
+    cfg_name = "mini-ov"
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_state_dict(cfg_name, 0)
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    feats = {}
+    hook = m.visual.transformer.resblocks[1].mlp.gelu.register_forward_hook(lambda mod, i, o: feats.__setitem__("f", o))
+    images = synth.make_images(cfg_name, 2, 0).cuda().requires_grad_(True)
+    m.encode_image(images)
+    loss = -feats["f"][:, :, 7].float().mean()
+    loss.backward()
+    hook.remove()
+    xf = synth.make_images(cfg_name, 2, 0).requires_grad_(True)
+    taps = {}
+    O.vision_transformer(xf, sd, synth.vision_heads(cfg_name), taps=taps)
+    (-taps["visual.transformer.resblocks.1.mlp.gelu"][:, :, 7].mean()).backward()
+    assert_grad(images.grad, xf.grad, "d image through hooked GELU", 6e-2)
