@@ -37,6 +37,17 @@ CFG_NAME = "L14-224"
 FWD_FLOPS_PER_IMAGE = 162.03e9   # 2*M*N*K of every GEMM-shaped op, L/14@224
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))["mean_dram_bytes_per_launch"]
+        except Exception:
+            return None
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -233,7 +244,7 @@ def bench_loss(torch, ovb, n_global, embed, world, rank, steps, warmup, peaks):
     flops = 6.0 * n_global * n_global * embed / world
     tf = flops / ms / 1e9
     return {"metric": "clip_loss_fwd_bwd_ms", "value": ms, "unit": "ms", "global_batch": n_global, "embed_dim": embed,
-            "mode": "local_loss+gather_with_grad" if world > 1 else "single", "loss": float(loss),
+            "mode": "local_loss+gather_with_grad" if world > 1 else "single", "loss": float(loss.detach()),
             "achieved_tflops_per_gpu": tf, "frac_of_measured_sustained": tf / peaks["tf_sustained"]}
 
 
@@ -355,7 +366,8 @@ def run_ours(args):
             "model_tflops": value * FWD_FLOPS_PER_IMAGE / 1e12 / world,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (QKV / out-proj / fc1+GELU / fc2 projections)",
                          "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": gemm_tf / peaks["tf_sustained"], "traffic": None,
+                         "frac": gemm_tf / peaks["tf_sustained"], "traffic": load_traffic(),
+                         "traffic_note": "mean dram__bytes_read+write per launch over the four projection shapes, profiles/r01_gemm_ncu_full.csv",
                          "peak_source": f"{peaks['src']} sustained cuBLAS bf16 (kernel timed inside a long step)",
                          "launches_timed": gm["launches"]},
             "kernels": kernels,
