@@ -16,22 +16,31 @@ namespace ovk {
 constexpr int ATT_BQ = 128;
 constexpr int ATT_BKV = 128;
 constexpr int ATT_HD = 64;
-constexpr int ATT_THREADS = 192;  // warps 0-3 softmax, warp 4 TMA producer, warp 5 MMA issuer / TMEM owner
+constexpr int ATT_SM_WARPS = 8;    // softmax warps: warp w owns TMEM lane quadrant w % 4 and key columns [64*(w/4), +64)
+constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);  // + warp 8 TMA producer, warp 9 MMA issuer / TMEM owner
 constexpr int ATT_TILE_BYTES = 128 * 128;  // [128 rows x 64 bf16]
 constexpr int ATT_OFF_Q = 0;
 constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;
 constexpr int ATT_OFF_V = ATT_OFF_K + 2 * ATT_TILE_BYTES;
 constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;
-constexpr int ATT_OFF_BAR = ATT_OFF_P + 2 * ATT_TILE_BYTES;
-constexpr int ATT_NUM_BARS = 12;
+constexpr int ATT_OFF_XCHG = ATT_OFF_P + 2 * ATT_TILE_BYTES;   // bf16 [2][128]: per-row maxima of the two column halves
+constexpr int ATT_OFF_TAIL = ATT_OFF_XCHG + 512;   // remainder key row (128 B) + its value row, double-buffered (2 x 128 B)
+constexpr int ATT_OFF_BAR = ATT_OFF_TAIL + 384;
+constexpr int ATT_NUM_BARS = 14;
 constexpr int ATT_SMEM_BYTES = ATT_OFF_BAR + ATT_NUM_BARS * 8 + 16;
+constexpr int ATT_MAX_TAIL = 1;     // remainder key / query row (L mod 128 == 1: cls + power-of-two grid) handled outside the tiles
+constexpr int ATT_TAIL_MAX_L = 1040;  // longest sequence the remainder-row kernel keeps scores for (16 KB of smem)     // remainder keys / query rows (L mod 128) handled outside the 128-wide tiles
 constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
-                     float* __restrict__ lse_out, int L, int H, float scale_log2) {
+                     const __grid_constant__ CUtensorMap tmTail, float* __restrict__ lse_out, int L, int Lm, int H,
+                     int nq, int total_items, float scale_log2) {
+  // PERSISTENT: each CTA walks work items (query tile, head, image) with stride gridDim.x, keeping its TMEM allocation,
+  // barriers and the K/V TMA ring alive across items, so the next item's Q/K/V loads run under the current item's
+  // softmax.  Query rows [0, nq * 128) are handled here; a short remainder of rows goes to attention_tail_kernel.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention: dynamic smem base not 1024-byte aligned\n");
@@ -50,19 +59,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* s_full = bars + 9;
   uint64_t* p_ready = bars + 10;
   uint64_t* pv_done = bars + 11;
+  uint64_t* q_empty = bars + 12;
+  uint64_t* o_free = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ATT_OFF_BAR + ATT_NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const int q0 = blockIdx.x * ATT_BQ;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (L + ATT_BKV - 1) / ATT_BKV;
+  // keys [0, Lm) go through the tensor-core blocks; the (few) keys [Lm, L) are folded in on the FMA pipe (see below)
+  const int nkv = (Lm + ATT_BKV - 1) / ATT_BKV;
+  const int ntail = L - Lm;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == ATT_SM_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmO);
+    tma_prefetch_desc(&tmTail);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1 + (L > Lm ? 32 * ATT_SM_WARPS : 0));  // MMA commit (+ the softmax threads' read of Q for remainder keys)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -70,176 +82,362 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 32 * ATT_SM_WARPS);
     mbar_init(pv_done, 1);
+    mbar_init(o_free, 32 * ATT_SM_WARPS);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
+  if (warp == ATT_SM_WARPS + 1) tmem_alloc<ATT_TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == ATT_SM_WARPS) {
     if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_4d(sQ, &tmQKV, q_full, 0, h, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&k_empty[s], ph ^ 1, 10);
-        mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
-        tma_load_4d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], 0, H + h, j * ATT_BKV, b);
-        mbar_wait(&v_empty[s], ph ^ 1, 11);
-        mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
-        tma_load_4d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], 0, 2 * H + h, j * ATT_BKV, b);
+      int n = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        const int qt = item % nq, h = (item / nq) % H, b = item / (nq * H);
+        mbar_wait(q_empty, (n & 1) ^ 1, 9);
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0));
+        tma_load_4d(sQ, &tmQKV, q_full, 0, h, qt * ATT_BQ, b);
+        if (ntail > 0) {  // remainder key row and its value row (1 x 128 B each, unswizzled)
+          tma_load_4d(smem + ATT_OFF_TAIL, &tmTail, q_full, 0, H + h, Lm, b);
+          tma_load_4d(smem + ATT_OFF_TAIL + 128 + (n & 1) * 128, &tmTail, q_full, 0, 2 * H + h, Lm, b);
+        }
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int s = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1, 10);
+          mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+          tma_load_4d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], 0, H + h, j * ATT_BKV, b);
+          mbar_wait(&v_empty[s], ph ^ 1, 11);
+          mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+          tma_load_4d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], 0, 2 * H + h, j * ATT_BKV, b);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ATT_SM_WARPS + 1) {
     if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
-      mbar_wait(q_full, 0, 12);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        const int valid = min(ATT_BKV, L - j * ATT_BKV);
-        const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
-        const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + s * ATT_TILE_BYTES);
-        // S = Q K_j^T
-        mbar_wait(&k_full[s], ph, 13);
-        tc_fence_after();
-        const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, nblk, 0, 0);
+      int n = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        mbar_wait(q_full, n & 1, 12);
+        for (int j = 0; j < nkv; ++j, ++g) {
+          const int s = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          const int valid = min(ATT_BKV, Lm - j * ATT_BKV);
+          const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
+          const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+          const uint32_t v_addr = smem_u32(sV + s * ATT_TILE_BYTES);
+          // S = Q K_j^T   (the S columns are free: p_ready of the previous block was waited on below)
+          mbar_wait(&k_full[s], ph, 13);
+          tc_fence_after();
+          const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, nblk, 0, 0);
 #pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k) {
-          umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
-                       umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
+          for (int k = 0; k < ATT_HD / 16; ++k) {
+            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
+                         umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
+          }
+          umma_commit(&k_empty[s]);
+          umma_commit(s_full);
+          if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
+          // O += P V_j   (P: K-major [128 x nblk] in two 64-column swizzle atoms; V: MN-major [nblk x 64])
+          mbar_wait(p_ready, g & 1, 14);
+          mbar_wait(&v_full[s], ph, 15);
+          if (j == 0) mbar_wait(o_free, (n & 1) ^ 1, 8);  // previous item's epilogue has read the O accumulator
+          tc_fence_after();
+          constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
+          const int ksteps = nblk / 16;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
+            const uint32_t bb = v_addr + kk * 16 * 128;
+            umma_bf16_ss(tmem_base + ATT_TMEM_O, umma_desc_kmajor_sw128(a), umma_desc_mnmajor_sw128(bb, ATT_TILE_BYTES),
+                         idesc_pv, (j | kk) != 0);
+          }
+          umma_commit(&v_empty[s]);
+          umma_commit(pv_done);
         }
-        umma_commit(&k_empty[s]);
-        umma_commit(s_full);
-        // O += P V_j   (P: K-major [128 x nblk] in two 64-column swizzle atoms; V: MN-major [nblk x 64])
-        mbar_wait(p_ready, j & 1, 14);
-        mbar_wait(&v_full[s], ph, 15);
-        tc_fence_after();
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
-        const int ksteps = nblk / 16;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
-          const uint32_t bb = v_addr + kk * 16 * 128;
-          umma_bf16_ss(tmem_base + ATT_TMEM_O, umma_desc_kmajor_sw128(a), umma_desc_mnmajor_sw128(bb, ATT_TILE_BYTES),
-                       idesc_pv, (j | kk) != 0);
-        }
-        umma_commit(&v_empty[s]);
-        umma_commit(pv_done);
       }
     }
   } else {
-    // -------------------------------------------------------------------- softmax warps: thread <-> query row
-    const int r = threadIdx.x;  // 0..127 = row in tile = TMEM lane
-    const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
-    float m = -INFINITY;  // running max (log2 domain, already scaled)
-    float l = 0.f;        // running sum
-    for (int j = 0; j < nkv; ++j) {
-      const int valid = min(ATT_BKV, L - j * ATT_BKV);
-      const int nblk = (valid + 15) & ~15;
-      mbar_wait(s_full, j & 1, 16);
-      tc_fence_after();
-      // pass 1: row maximum over the valid columns
-      float mx = -INFINITY;
-      for (int c = 0; c < nblk; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_S + c, v);
-        tmem_ld_wait();
+    // -------------------------------------------------------------------- softmax warps
+    // Two threads per query row: thread (quad, lane, half) owns TMEM lane 32*quad + lane and key columns
+    // [64*half, 64*half + 64) of the block, plus output columns [32*half, +32).  One TMEM pass per key block (the 64
+    // scores stay in registers between the max and the exp); the two halves agree on the exponent reference through a
+    // 512-byte exchange.  Lazy rescaling: the reference only moves when the row maximum grew by more than 2^8, so the
+    // O accumulator is rescaled (TMEM load / multiply / store) rarely instead of once per key block.
+    const int quad = warp & 3;
+    const int half = warp >> 2;
+    const int r = quad * 32 + lane;  // row in tile = TMEM lane
+    const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t p_base = smem_u32(sP) + half * ATT_TILE_BYTES;
+    const uint32_t xchg = smem_u32(smem + ATT_OFF_XCHG);
+    constexpr uint32_t SMT = 32 * ATT_SM_WARPS;
+    int g = 0, n = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+      const int qt = item % nq, h = (item / nq) % H, b = item / (nq * H);
+      const int q0 = qt * ATT_BQ;
+      // the previous item's output tile (staged in the P region) must have left shared memory
+      if (threadIdx.x == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, SMT);
+      float m_ref = -INFINITY;  // exponent reference (log2 domain, already scaled), identical in both halves of a row
+      float l = 0.f;            // this half's running sum of 2^(s - m_ref)
+      // Remainder keys [Lm, L) (e.g. the 257th token): their scores are a 64-long dot product per query row, computed
+      // here on the FMA pipe while the first S MMA runs, and folded into the output in the epilogue — instead of a
+      // whole extra TMA -> MMA -> softmax -> MMA round for a 1-column block.
+      float s_tail = 0.f;
+      if (ntail > 0) {
+        mbar_wait(q_full, n & 1, 19);
+        const uint32_t kt = smem_u32(smem + ATT_OFF_TAIL);
+        float d = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int c = 0; c < 8; ++c) {
+          const uint4 qv = lds128(smem_u32(sQ) + sw128_offset(r, c));
+          const uint4 kv = lds128(kt + c * 16);
+          d = fmaf(bf16_lo(qv.x), bf16_lo(kv.x), d); d = fmaf(bf16_hi(qv.x), bf16_hi(kv.x), d);
+          d = fmaf(bf16_lo(qv.y), bf16_lo(kv.y), d); d = fmaf(bf16_hi(qv.y), bf16_hi(kv.y), d);
+          d = fmaf(bf16_lo(qv.z), bf16_lo(kv.z), d); d = fmaf(bf16_hi(qv.z), bf16_hi(kv.z), d);
+          d = fmaf(bf16_lo(qv.w), bf16_lo(kv.w), d); d = fmaf(bf16_hi(qv.w), bf16_hi(kv.w), d);
         }
+        s_tail = d * scale_log2;
+        mbar_arrive(q_empty);
       }
-      const float m_new = fmaxf(m, mx * scale_log2);
-      const float alpha = fast_exp2(m - m_new);  // first block: exp2(-inf) = 0
-      // P buffer and the O accumulator are owned by PV(j-1) until it completes
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1, 17);
+      for (int j = 0; j < nkv; ++j, ++g) {
+        const int valid = min(ATT_BKV, Lm - j * ATT_BKV) - 64 * half;   // valid columns of this half (may be <= 0)
+        const int nblk = ((min(ATT_BKV, Lm - j * ATT_BKV) + 15) & ~15) - 64 * half;
+        mbar_wait(s_full, g & 1, 16);
         tc_fence_after();
-      }
-      // pass 2: P = exp2(S*scale - m_new) -> bf16 -> swizzled smem; row sum in fp32
-      float rowsum = 0.f;
-      for (int c = 0; c < nblk; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_S + c, v);
-        tmem_ld_wait();
-        float p[16];
+        // pass 1: half-row maximum (two 32-column TMEM loads; the scores are re-read in pass 2 to stay within the
+        // 96-register budget that two resident CTAs of 320 threads allow)
+        float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float e = fast_exp2(fmaf(__uint_as_float(v[i]), scale_log2, -m_new));
-          p[i] = (c + i < valid) ? e : 0.f;
-          rowsum += p[i];
-        }
-        uint8_t* atom = sP + (c >> 6) * ATT_TILE_BYTES;
-        const uint32_t chunk = (c & 63) >> 3;
-        *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk)) =
-            make_uint4(pack_bf16x2(p[0], p[1]), pack_bf16x2(p[2], p[3]), pack_bf16x2(p[4], p[5]), pack_bf16x2(p[6], p[7]));
-        *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk + 1)) =
-            make_uint4(pack_bf16x2(p[8], p[9]), pack_bf16x2(p[10], p[11]), pack_bf16x2(p[12], p[13]),
-                       pack_bf16x2(p[14], p[15]));
-      }
-      l = l * alpha + rowsum;
-      m = m_new;
-      if (j > 0) {
-        // rescale the running output: O *= alpha
-        for (int c = 0; c < ATT_HD; c += 16) {
-          uint32_t o[16];
-          tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_O + c, o);
-          tmem_ld_wait();
+        for (int c = 0; c < 64; c += 32) {
+          if (c < nblk) {
+            uint32_t sv[32];
+            tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_S + 64 * half + c, sv);
+            tmem_ld_wait();
+            if (c + 32 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_x16(tmem_base + t_lane + ATT_TMEM_O + c, o);
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            } else if (c < valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = (c + i < valid) ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
+            }
+          }
         }
-        tmem_st_wait();
+        // exchange the half-row maxima (rounded UP to bf16: any reference >= the true maximum - 2^8 is valid, and both
+        // halves must derive the SAME reference)
+        {
+          float mt = mx * scale_log2;
+          uint32_t bits = __float_as_uint(mt);
+          uint32_t up = (bits + ((mt >= 0.f) ? 0xFFFFu : 0u)) & 0xFFFF0000u;   // toward +inf for either sign
+          if (mt == -INFINITY) up = 0xFF800000u;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(xchg + (half * 128 + r) * 2), "h"(static_cast<unsigned short>(up >> 16)) : "memory");
+        }
+        named_bar_sync(2, SMT);
+        float m_tile;
+        {
+          unsigned short a, bb;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(a) : "r"(xchg + r * 2));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(bb) : "r"(xchg + (128 + r) * 2));
+          m_tile = fmaxf(__uint_as_float(static_cast<uint32_t>(a) << 16), __uint_as_float(static_cast<uint32_t>(bb) << 16));
+        }
+        // P buffer and the O accumulator are owned by PV(j-1) until it completes
+        if (j > 0) {
+          mbar_wait(pv_done, (g - 1) & 1, 17);
+          tc_fence_after();
+        }
+        if (j == 0) {
+          m_ref = m_tile;
+        } else {
+          const bool grow = m_tile > m_ref + 8.f;
+          if (__any_sync(0xffffffffu, grow)) {  // rescale the running output of the rows whose reference moves
+            const float alpha = grow ? fast_exp2(m_ref - m_tile) : 1.f;
+            m_ref = grow ? m_tile : m_ref;
+            l *= alpha;
+            uint32_t o[32];
+            tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
+            tmem_st_wait();
+          }
+        }
+        // pass 2: P = 2^(S*scale - m_ref) -> bf16 -> swizzled smem (this half's 64-column atom); row sum in fp32
+        float rowsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          if (c < nblk) {
+            uint32_t sv[32];
+            tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_S + 64 * half + c, sv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 32; cc += 8) {
+              if (c + cc < nblk) {
+                float pv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float e = fast_exp2(fmaf(__uint_as_float(sv[cc + i]), scale_log2, -m_ref));
+                  pv[i] = (c + cc + i < valid) ? e : 0.f;
+                  rowsum += pv[i];
+                }
+                sts128(p_base + sw128_offset(r, (c + cc) >> 3),
+                       make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
+              }
+            }
+          }
+        }
+        l += rowsum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+      }
+      // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> smem -> TMA store
+      mbar_wait(pv_done, (g - 1) & 1, 18);
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(o_free);  // the accumulator may be overwritten by the next item's first P V
+      if (ntail > 0) {      // fold the remainder key in: one more online-softmax step, entirely in registers
+        const uint32_t vt = smem_u32(smem + ATT_OFF_TAIL + 128 + (n & 1) * 128) + 64 * half;
+        const float m_fin = fmaxf(m_ref, s_tail);
+        const float a = fast_exp2(m_ref - m_fin);
+        const float pt = fast_exp2(s_tail - m_fin);
+        l = fmaf(l, a, half == 0 ? pt : 0.f);
+        m_ref = m_fin;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 vv = lds128(vt + c * 16);
+          const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o[8 * c + 2 * q] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * q]), a, pt * bf16_lo(w4[q])));
+            o[8 * c + 2 * q + 1] = __float_as_uint(fmaf(__uint_as_float(o[8 * c + 2 * q + 1]), a, pt * bf16_hi(w4[q])));
+          }
+        }
+      }
+      // combine the two halves' sums through the (now idle) second P atom
+      const uint32_t lx = smem_u32(sP) + ATT_TILE_BYTES;
+      sts_f32(lx + (half * 128 + r) * 4, l);
+      named_bar_sync(2, SMT);
+      const float l_tot = lds_f32(lx + r * 4) + lds_f32(lx + (128 + r) * 4);
+      const float inv_l = 1.f / l_tot;
+      // staging in the first P atom (every MMA that read P has completed: pv_done)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts128(smem_u32(sP) + sw128_offset(r, 4 * half + c),
+               make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * inv_l, __uint_as_float(o[8 * c + 1]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv_l, __uint_as_float(o[8 * c + 3]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv_l, __uint_as_float(o[8 * c + 5]) * inv_l),
+                          pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv_l, __uint_as_float(o[8 * c + 7]) * inv_l)));
+      if (half == 0 && lse_out != nullptr && q0 + r < L) {
+        lse_out[(static_cast<long long>(b) * H + h) * L + q0 + r] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
       }
       fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_ready);
+      named_bar_sync(1, SMT);
+      if (threadIdx.x == 0) {
+        tma_store_4d(&tmO, sP, 0, h, q0, b);
+        tma_store_commit();
+      }
     }
-    // -------------------------------------------------------------------- epilogue: O / l -> bf16 -> smem -> TMA store
-    mbar_wait(pv_done, (nkv - 1) & 1, 18);
-    tc_fence_after();
-    const float inv_l = 1.f / l;
-    uint8_t* sO = sQ;  // every MMA that read Q has completed (pv_done tracks all earlier MMAs of the issuing thread)
-    for (int c = 0; c < ATT_HD; c += 16) {
-      uint32_t o[16];
-      tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_O + c, o);
-      tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(o[i]) * inv_l;
-      const uint32_t chunk = c >> 3;
-      *reinterpret_cast<uint4*>(sO + sw128_offset(r, chunk)) =
-          make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(sO + sw128_offset(r, chunk + 1)) =
-          make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                     pack_bf16x2(f[14], f[15]));
-    }
-    if (lse_out != nullptr && q0 + r < L) {
-      lse_out[(static_cast<long long>(b) * H + h) * L + q0 + r] = (m + log2f(l)) * 0.69314718055994531f;
-    }
-    fence_proxy_async_smem();
-    named_bar_sync(1, 128);
-    if (threadIdx.x == 0) {
-      tma_store_4d(&tmO, sO, 0, h, q0, b);
-      tma_store_commit();
-      tma_store_wait_all<0>();
-    }
+    if (threadIdx.x == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == ATT_SM_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc<ATT_TMEM_COLS>(tmem_base);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ remainder rows
+// The (few) query rows left over after the last full 128-row tile (L = 257 = 2*128 + 1 for a 16x16 grid + cls) are a
+// [1 x L] x [L x 64] product per head: one warp per (row, head, image) on the FMA pipe, instead of a tcgen05 tile that
+// would be 99% padding.  K / V rows are read coalesced: lane l holds 16-byte chunk (l % 8) of key row 4*step + l / 8,
+// i.e. 512 contiguous-per-row bytes per load instruction; the 8 lanes of a row reduce their partial dot by shuffles.
+__global__ void __launch_bounds__(128)
+attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
+                      int L, int H, int row0, int nrows, float scale_log2) {
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= nrows * H) return;
+  const int lane = threadIdx.x & 31;
+  const int ch = lane & 7;    // 16-byte chunk of the 128-byte head row
+  const int sub = lane >> 3;  // which of the 4 rows of a step
+  const int row = row0 + w / H;
+  const int h = w % H;
+  const long long b = blockIdx.y;
+  const long long tok = 3LL * H * ATT_HD;  // elements per token in the packed qkv tensor
+  const __nv_bfloat16* base = qkv + b * L * tok + h * ATT_HD + ch * 8;
+  float q[8];
+  {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + row * tok));
+    q[0] = bf16_lo(u.x); q[1] = bf16_hi(u.x); q[2] = bf16_lo(u.y); q[3] = bf16_hi(u.y);
+    q[4] = bf16_lo(u.z); q[5] = bf16_hi(u.z); q[6] = bf16_lo(u.w); q[7] = bf16_hi(u.w);
+  }
+  const int steps = (L + 3) / 4;
+  // pass 1: scores (kept in shared memory: one float per key), running maximum
+  __shared__ float sc[4][ATT_TAIL_MAX_L];
+  float* my = sc[threadIdx.x >> 5];
+  float mx = -INFINITY;
+  const __nv_bfloat16* kb = base + H * ATT_HD;
+#pragma unroll 4
+  for (int t = 0; t < steps; ++t) {
+    const int j = 4 * t + sub;
+    float d = 0.f;
+    if (j < L) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(kb + j * tok));
+      d = fmaf(q[0], bf16_lo(u.x), d); d = fmaf(q[1], bf16_hi(u.x), d); d = fmaf(q[2], bf16_lo(u.y), d);
+      d = fmaf(q[3], bf16_hi(u.y), d); d = fmaf(q[4], bf16_lo(u.z), d); d = fmaf(q[5], bf16_hi(u.z), d);
+      d = fmaf(q[6], bf16_lo(u.w), d); d = fmaf(q[7], bf16_hi(u.w), d);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    d = (j < L) ? d * scale_log2 : -INFINITY;
+    if (ch == 0 && j < L) my[j] = d;
+    mx = fmaxf(mx, d);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  __syncwarp();
+  // pass 2: P V with the same coalesced addressing; each lane accumulates its 8 output dims for its row subset
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float l = 0.f;
+  const __nv_bfloat16* vb = base + 2 * H * ATT_HD;
+#pragma unroll 4
+  for (int t = 0; t < steps; ++t) {
+    const int j = 4 * t + sub;
+    if (j < L) {
+      const float p = fast_exp2(my[j] - mx);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(vb + j * tok));
+      l += p;
+      acc[0] = fmaf(p, bf16_lo(u.x), acc[0]); acc[1] = fmaf(p, bf16_hi(u.x), acc[1]);
+      acc[2] = fmaf(p, bf16_lo(u.y), acc[2]); acc[3] = fmaf(p, bf16_hi(u.y), acc[3]);
+      acc[4] = fmaf(p, bf16_lo(u.z), acc[4]); acc[5] = fmaf(p, bf16_hi(u.z), acc[5]);
+      acc[6] = fmaf(p, bf16_lo(u.w), acc[6]); acc[7] = fmaf(p, bf16_hi(u.w), acc[7]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+    acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+  }
+  l += __shfl_xor_sync(0xffffffffu, l, 8);    // every chunk lane of a row group carries the same p: sum over the 4 groups
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+  const float inv = 1.f / l;
+  if (sub == 0) {
+    *reinterpret_cast<uint4*>(out + (b * L + row) * (static_cast<long long>(H) * ATT_HD) + h * ATT_HD + ch * 8) =
+        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                   pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  }
+  if (lse_out != nullptr && lane == 0) lse_out[(b * H + h) * L + row] = (mx + log2f(l)) * 0.69314718055994531f;
 }
 
 }  // namespace ovk
@@ -252,13 +450,15 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   if (hd != ATT_HD) return set_error(OVK_ERR_SHAPE, "attention: head dim %d not supported (this build: 64)", hd);
   if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention: B and H must be <= 65535");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tmQKV, tmO;
+  CUtensorMap tmQKV, tmO, tmTail;
   int rc;
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * H), (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)3 * H * hd * 2, (uint64_t)L * 3 * H * hd * 2};
     const uint32_t box[4] = {(uint32_t)hd, 1, ATT_BKV, 1};
     if ((rc = make_tmap_nd_bf16(&tmQKV, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const uint32_t box1[4] = {(uint32_t)hd, 1, 1, 1};   // one head row (128 B), unswizzled: the remainder key / value
+    if ((rc = make_tmap_nd_bf16(&tmTail, qkv, 4, dims, strides, box1, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
@@ -272,7 +472,24 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((L + ATT_BQ - 1) / ATT_BQ, H, B);
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tmQKV, tmO, lse, L, H, scale * 1.4426950408889634f);
-  return check_launch("attention_fwd_kernel");
+  // a short remainder of query rows goes to the FMA-pipe tail kernel instead of a padded 128-row tile
+  int tail = L % ATT_BQ;
+  if (L <= ATT_BQ || tail > ATT_MAX_TAIL || L > ATT_TAIL_MAX_L) tail = 0;
+  const int l_main = L - tail;
+  const int nq = (l_main + ATT_BQ - 1) / ATT_BQ;
+  const long long items = static_cast<long long>(nq) * H * B;
+  if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
+  const int grid = static_cast<int>(items < 2LL * num_sms() ? items : 2LL * num_sms());   // persistent, 2 CTAs per SM
+  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, lse, L, l_main, H, nq,
+                                                                 static_cast<int>(items),
+                                                                 scale * 1.4426950408889634f);
+  if ((rc = check_launch("attention_fwd_kernel"))) return rc;
+  if (tail) {
+    dim3 tgrid((tail * H + 3) / 4, B);
+    attention_tail_kernel<<<tgrid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                reinterpret_cast<__nv_bfloat16*>(out), lse, L, H, l_main, tail,
+                                                scale * 1.4426950408889634f);
+    return check_launch("attention_tail_kernel");
+  }
+  return OVK_OK;
 }
