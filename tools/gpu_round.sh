@@ -15,4 +15,6 @@ echo "ncu launches rc=$?"
 echo "== ncu full (top kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 100 -c 4 -o gpurun_out/prof_gemm_${TAG} $NCU_CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_fwd|clip_loss_fwd|clip_loss_grad" -s 30 -c 3 -o gpurun_out/prof_attn_loss_${TAG} $NCU_CMD > gpurun_out/ncu_full2_${TAG}.log 2>&1
+echo "ncu full (attention/loss) rc=$?"
 ls -la gpurun_out | tail -20

@@ -67,3 +67,24 @@ if os.path.exists(rep):
                "mean_dram_bytes_per_launch": sum(traffic) / max(1, len(traffic))},
               open(os.path.join(dst, "gemm_traffic.json"), "w"), indent=1)
     print("wrote gemm ncu full csv,", len(rows) - 2, "launches")
+
+
+# ---- attention / loss kernels: key metrics
+rep2 = os.path.join(src, f"prof_attn_loss_{tag}.ncu-rep")
+if os.path.exists(rep2):
+    raw = subprocess.run(["ncu", "-i", rep2, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+    idx = [hdr.index(w) for w in want if w in hdr]
+    with open(os.path.join(dst, f"{out_tag}_attention_loss_ncu_full.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx])
+        w.writerow([units[i] for i in idx])
+        for r in rows[2:]:
+            w.writerow([r[i][:90] for i in idx])
+    print("wrote attention/loss ncu csv,", len(rows) - 2, "launches")
