@@ -291,12 +291,33 @@ def run_ours(args):
         with torch.no_grad():
             return model.encode_image(images_dev, normalize=True)
 
-    def step_e2e():
+    # End-to-end: every step copies ITS batch from pinned host memory (H2D, 616 MB) and reads its embeddings back (D2H),
+    # all inside the timed region.  The copy of batch i+1 runs on a side stream into the other of two device buffers
+    # while batch i is being encoded (ordinary input double-buffering around the public encode_image call).
+    copy_stream = torch.cuda.Stream()
+    bufs = [torch.empty_like(images_dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream()
         with torch.no_grad():
-            x = images_host.to("cuda", non_blocking=True)
-            y = model.encode_image(x, normalize=True)
-            out_host.copy_(y.float(), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(copy_stream):
+                bufs[0].copy_(images_host, non_blocking=True)
+                ready[0].record(copy_stream)
+            for i in range(steps):
+                cur, nxt = i % 2, (i + 1) % 2
+                if i + 1 < steps:
+                    with torch.cuda.stream(copy_stream):
+                        if i >= 1:
+                            copy_stream.wait_event(consumed[nxt])
+                        bufs[nxt].copy_(images_host, non_blocking=True)
+                        ready[nxt].record(copy_stream)
+                main.wait_event(ready[cur])
+                y = model.encode_image(bufs[cur], normalize=True)
+                consumed[cur].record(main)
+                out_host.copy_(y.float(), non_blocking=True)
+        main.synchronize()
         return out_host
 
     def barrier():
@@ -305,15 +326,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, record=False):
+    def timed(fn, steps, record=False, runner=False):
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = ops.launch_count
         rec.enabled = record
         w0 = time.time()
         s.record()
-        for _ in range(steps):
-            fn()
+        if runner:
+            fn(steps)
+        else:
+            for _ in range(steps):
+                fn()
         e.record()
         barrier()
         rec.enabled = False
@@ -336,9 +360,8 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * batch * args.steps / (total_ms / 1e3)
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_e2e()
-    e2e_ms, _, _, _ = timed(step_e2e, args.steps)
+    run_e2e(max(2, min(args.warmup, 3)))
+    e2e_ms, _, _, _ = timed(run_e2e, args.steps, runner=True)
     e2e_value = world * batch * args.steps / (e2e_ms / 1e3)
 
     ksum = rec.summary()
@@ -375,7 +398,8 @@ def run_ours(args):
                              "sample": "8-image L/14@224 forward, fp32 oracle port (torch CPU ops), median of 3"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": images_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
-                    "api": "CLIP.encode_image(images, normalize=True) on pinned host fp32 NCHW images"},
+                    "api": "CLIP.encode_image(images, normalize=True); every step's fp32 NCHW batch comes from pinned host memory "
+                           "(H2D of batch i+1 double-buffered under the encode of batch i), embeddings read back to the host"},
             "gpu_launches": launches, "clocks": clocks,
         }
         if loss_line is not None:

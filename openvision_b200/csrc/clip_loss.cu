@@ -74,7 +74,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t bar_id = 1 + grp;
     const uint32_t scol = smem_u32(cx.epi_scratch());  // float2 [4][256]
     const float s2 = scale * LOG2E;
-    GemmSched sched(n_loc, n_all, CL_BN);
+    GemmSched sched(n_loc, n_all, CL_BN, E);
     int it = 0;
     for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
       const GemmTileInfo ti = sched.tile(t, CL_BN);
@@ -294,7 +294,7 @@ clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const float s2 = scale * LOG2E;
     const float w_diag = w_row + w_col;
     float ds = 0.f;  // sum G_ij * acc_ij  (= sum G * z / scale)
-    GemmSched sched(n_loc, n_all, CL_BN);
+    GemmSched sched(n_loc, n_all, CL_BN, E);
     int it = 0;
     for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
       const GemmTileInfo ti = sched.tile(t, CL_BN);

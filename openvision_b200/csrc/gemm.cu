@@ -24,7 +24,7 @@ template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
-                 const __grid_constant__ CUtensorMap tmD, const GemmEpi ep, int M, int N, int K) {
+                 const __grid_constant__ CUtensorMap tmD, const GemmEpi ep, int M, int N, int K, int splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using L = GemmSmemLayout<BN>;
   GemmCtx<BN, L> cx(smem_raw);
@@ -32,9 +32,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
 
   if (warp == 0) {
-    if (elect_one()) gemm_producer<BN, A_MN, B_MN>(cx, &tmA, &tmB, M, N, K);
+    if (elect_one()) gemm_producer<BN, A_MN, B_MN>(cx, &tmA, &tmB, M, N, K, splits);
   } else if (warp == 1) {
-    if (elect_one()) gemm_mma_issuer<BN, A_MN, B_MN>(cx, tmem_base, M, N, K);
+    if (elect_one()) gemm_mma_issuer<BN, A_MN, B_MN>(cx, tmem_base, M, N, K, splits);
   } else if (warp >= GEMM_CTRL_WARPS) {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> smem -> TMA store
     constexpr int CW = OUT_F32 ? 32 : 64;         // columns per staged chunk (one 128-byte row)
@@ -55,7 +55,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_res = !OUT_F32 && (EPI == EPI_DACT || (EPI == EPI_LINEAR && (ep.flags & OVK_EPI_RESIDUAL) != 0));
     const bool save_pre = EPI == EPI_ACT && (ep.flags & OVK_EPI_SAVE_PREACT) != 0;
     const float alpha = ep.alpha;
-    GemmSched sched(M, N, BN);
+    GemmSched sched(M, N, BN, K, splits);
+    const bool reduce_out = OUT_F32 && sched.splits > 1;   // split-K partial sums are ADDED into a zeroed C
     int it = 0;
     for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
       const GemmTileInfo ti = sched.tile(t, BN);
@@ -166,7 +167,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(bar_id, GEMM_GROUP_THREADS);
         if (leader) {
-          tma_store_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
+          if (reduce_out) tma_reduce_add_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
+          else tma_store_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
           tma_store_commit();
         }
       }
@@ -214,8 +216,22 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
     attr_set = true;
   }
   const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K);
+  // split-K (fp32 outputs only: the weight-gradient GEMMs have few output tiles and a huge K = tokens): partial sums
+  // are added into a zeroed C by TMA reduce-add stores
+  int splits = 1;
+  if (OUT_F32 && tiles * 10 < num_sms() * 7) {
+    const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+    splits = num_sms() / tiles;
+    if (splits > num_kb / 8) splits = num_kb / 8;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    cudaError_t e = cudaMemset2DAsync(g.C, static_cast<size_t>(g.ldc) * 4, 0, static_cast<size_t>(g.N) * 4, g.M, stream);
+    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaMemset2DAsync(gemm split-K): %s", cudaGetErrorString(e));
+  }
+  const int items = tiles * splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K, splits);
   return check_launch("gemm_bf16_kernel");
 }
 

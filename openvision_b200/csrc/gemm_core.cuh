@@ -46,20 +46,29 @@ struct GemmSmemLayout {
 
 struct GemmTileInfo {
   int m0, n0;
+  int kb0, kb1;  // k-block range of this work item (split-K: several items share an output tile)
 };
 
 struct GemmSched {
-  int tiles_m, tiles_n, total;
-  __device__ __forceinline__ GemmSched(int M, int N, int BN) {
+  int tiles_m, tiles_n, splits, kb_per, num_kb, total;
+  __device__ __forceinline__ GemmSched(int M, int N, int BN, int K = GEMM_BK, int want_splits = 1) {
     tiles_m = (M + GEMM_BM - 1) / GEMM_BM;
     tiles_n = (N + BN - 1) / BN;
-    total = tiles_m * tiles_n;
+    num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+    kb_per = (num_kb + want_splits - 1) / want_splits;
+    splits = (num_kb + kb_per - 1) / kb_per;
+    total = tiles_m * tiles_n * splits;
   }
-  // n fastest: the CTAs resident at one moment share A row-blocks through L2, B (weights) stays L2-resident.
+  // split fastest (the partial sums of one output tile are produced concurrently), then n (the CTAs resident at one
+  // moment share A row-blocks through L2, B (weights) stays L2-resident).
   __device__ __forceinline__ GemmTileInfo tile(int t, int BN) const {
     GemmTileInfo ti;
-    ti.n0 = (t % tiles_n) * BN;
-    ti.m0 = (t / tiles_n) * GEMM_BM;
+    const int ks = t % splits;
+    const int tt = t / splits;
+    ti.n0 = (tt % tiles_n) * BN;
+    ti.m0 = (tt / tiles_n) * GEMM_BM;
+    ti.kb0 = ks * kb_per;
+    ti.kb1 = min(num_kb, ti.kb0 + kb_per);
     return ti;
   }
 };
@@ -139,14 +148,13 @@ __device__ __forceinline__ void gemm_teardown(const GemmCtx<BN, L>& cx, uint32_t
 // MN-major operand: tensor map (inner = rows (M or N), outer = K), boxes of [64 k x 64 rows] = 8 KB panels.
 template <int BN, bool A_MN, bool B_MN, class L>
 __device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CUtensorMap* tmA, const CUtensorMap* tmB,
-                                              int M, int N, int K) {
-  GemmSched sched(M, N, BN);
-  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+                                              int M, int N, int K, int splits = 1) {
+  GemmSched sched(M, N, BN, K, splits);
   int stage = 0;
   uint32_t phase = 0;
   for (int t = blockIdx.x; t < sched.total; t += gridDim.x) {
     GemmTileInfo ti = sched.tile(t, BN);
-    for (int kb = 0; kb < num_kb; ++kb) {
+    for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
       mbar_wait(&cx.empty[stage], phase ^ 1, 1);
       mbar_arrive_expect_tx(&cx.full[stage], L::STAGE_BYTES);
       if constexpr (!A_MN) {
@@ -173,9 +181,9 @@ __device__ __forceinline__ void gemm_producer(const GemmCtx<BN, L>& cx, const CU
 
 // Warp 1, one elected lane. Issues BK/16 tcgen05.mma per k-block into the tile's TMEM accumulator buffer.
 template <int BN, bool A_MN, bool B_MN, class L>
-__device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32_t tmem_base, int M, int N, int K) {
-  GemmSched sched(M, N, BN);
-  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+__device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32_t tmem_base, int M, int N, int K,
+                                                int splits = 1) {
+  GemmSched sched(M, N, BN, K, splits);
   constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   int stage = 0;
   uint32_t phase = 0;
@@ -186,7 +194,8 @@ __device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32
     mbar_wait(&cx.tmem_empty[acc], acc_phase ^ 1, 2);
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + acc * BN;
-    for (int kb = 0; kb < num_kb; ++kb) {
+    const GemmTileInfo ti = sched.tile(t, BN);
+    for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
       mbar_wait(&cx.full[stage], phase, 3);
       tc_fence_after();
       const uint32_t a_addr = smem_u32(cx.a_stage(stage));
@@ -197,7 +206,7 @@ __device__ __forceinline__ void gemm_mma_issuer(const GemmCtx<BN, L>& cx, uint32
                                  : umma_desc_kmajor_sw128(a_addr + k * 32);
         const uint64_t bd = B_MN ? umma_desc_mnmajor_sw128(b_addr + k * 2048, GEMM_PANEL_BYTES)
                                  : umma_desc_kmajor_sw128(b_addr + k * 32);
-        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0);
+        umma_bf16_ss(d_tmem, ad, bd, idesc, ((kb - ti.kb0) | k) != 0);
       }
       umma_commit(&cx.empty[stage]);
       if (++stage == GEMM_STAGES) {

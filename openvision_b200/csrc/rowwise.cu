@@ -30,165 +30,192 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int rows, int D, float eps) {
+  // one warp owns LN_RPW consecutive rows and issues all their loads before touching any of them (more bytes in
+  // flight per SM: the kernel is pure HBM streaming)
+  constexpr int RPW = 2;
   const int warps_per_block = blockDim.x >> 5;
-  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
-  uint4 raw[MAXV];
+  uint4 raw[RPW][MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    raw[i] = v < nvec ? xr[v] : make_uint4(0, 0, 0, 0);
-  }
-  float s = 0.f;
+  for (int rr = 0; rr < RPW; ++rr) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row0 + rr) * ldx);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    float f[8];
-    unpack8(raw[i], f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s += f[j];
-  }
-  const float mean = warp_sum(s) / static_cast<float>(D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    if (lane + i * 32 < nvec) {
-      float f[8];
-      unpack8(raw[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[j] - mean;
-        q = fmaf(d, d, q);
-      }
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      raw[rr][i] = (v < nvec && row0 + rr < rows) ? xr[v] : make_uint4(0, 0, 0, 0);
     }
   }
-  const float var = warp_sum(q) / static_cast<float>(D);
-  const float rstd = rsqrtf(var + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
-  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int row = row0 + rr;
+    if (row >= rows) break;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
       float f[8];
-      unpack8(raw[i], f);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
-      f[0] = fmaf((f[0] - mean) * rstd, g0.x, b0.x);
-      f[1] = fmaf((f[1] - mean) * rstd, g0.y, b0.y);
-      f[2] = fmaf((f[2] - mean) * rstd, g0.z, b0.z);
-      f[3] = fmaf((f[3] - mean) * rstd, g0.w, b0.w);
-      f[4] = fmaf((f[4] - mean) * rstd, g1.x, b1.x);
-      f[5] = fmaf((f[5] - mean) * rstd, g1.y, b1.y);
-      f[6] = fmaf((f[6] - mean) * rstd, g1.z, b1.z);
-      f[7] = fmaf((f[7] - mean) * rstd, g1.w, b1.w);
-      yr[v] = pack8(f);
+      unpack8(raw[rr][i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    const float mean = warp_sum(s) / static_cast<float>(D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (lane + i * 32 < nvec) {
+        float f[8];
+        unpack8(raw[rr][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    const float var = warp_sum(q) / static_cast<float>(D);
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float f[8];
+        unpack8(raw[rr][i], f);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+        f[0] = fmaf((f[0] - mean) * rstd, g0.x, b0.x);
+        f[1] = fmaf((f[1] - mean) * rstd, g0.y, b0.y);
+        f[2] = fmaf((f[2] - mean) * rstd, g0.z, b0.z);
+        f[3] = fmaf((f[3] - mean) * rstd, g0.w, b0.w);
+        f[4] = fmaf((f[4] - mean) * rstd, g1.x, b1.x);
+        f[5] = fmaf((f[5] - mean) * rstd, g1.y, b1.y);
+        f[6] = fmaf((f[6] - mean) * rstd, g1.z, b1.z);
+        f[7] = fmaf((f[7] - mean) * rstd, g1.w, b1.w);
+        yr[v] = pack8(f);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm bwd
-// g = dy*gamma ; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) ; dgamma += sum_rows dy*xhat ; dbeta += sum_rows dy.
-// Each block handles ROWS_PER_BLOCK consecutive rows; per-block dgamma/dbeta partials live in registers of the
-// owning lane (lane <-> column mapping is fixed), reduced across the block's warps in smem, then one atomicAdd per
-// column per block.
+// g = dy*gamma ; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) (+ dres) ; dgamma = sum_rows dy*xhat ; dbeta = sum_rows dy.
+// Two streaming kernels instead of one register-heavy one (which ran at a single block per SM):
+//   layernorm_bwd_dx_kernel   : one warp per row, like the forward (reads dy, x [, dres], writes dx)
+//   layernorm_bwd_dgdb_kernel : column sums of dy*xhat and dy; block (32, 8): lane <-> one 16-byte column vector,
+//                               8 row groups reduced through smem, one atomicAdd per column per block.
 template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
-                                                            const __nv_bfloat16* __restrict__ x, long long ldx,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                            const __nv_bfloat16* dres, long long lddres,
-                                                            __nv_bfloat16* dx, long long lddx,
-                                                            float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                            int rows, int D, int rows_per_block) {
-  extern __shared__ float red[];  // [2][D]
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                               const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                               const __nv_bfloat16* dres, long long lddres,
+                                                               __nv_bfloat16* dx, long long lddx, int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
   const int nvec = D >> 3;
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-  float dg[MAXV][8], db[MAXV][8];
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+  const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
+  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
+  uint4 rx[MAXV], rd[MAXV], rr[MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
-
-  const int row_begin = blockIdx.x * rows_per_block;
-  const int row_end = min(rows, row_begin + rows_per_block);
-  for (int row = row_begin + warp; row < row_end; row += nwarps) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
-    const float mu = mean[row], rs = rstd[row];
-    float xh[MAXV][8], g[MAXV][8];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        float fx[8], fd[8];
-        unpack8(xr[v], fx);
-        unpack8(dyr[v], fd);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (fx[j] - mu) * rs;
-          g[i][j] = fd[j] * gm[j];
-          s1 += g[i][j];
-          s2 = fmaf(g[i][j], xh[i][j], s2);
-          dg[i][j] = fmaf(fd[j], xh[i][j], dg[i][j]);
-          db[i][j] += fd[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xh[i][j] = g[i][j] = 0.f;
-      }
-    }
-    const float m1 = warp_sum(s1) / static_cast<float>(D);
-    const float m2 = warp_sum(s2) / static_cast<float>(D);
-    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
-    const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - m1 - xh[i][j] * m2);
-        if (drr) {  // gradient arriving through the residual connection around the normalised branch
-          float r[8];
-          unpack8(drr[v], r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
-        dxr[v] = pack8(o);
-      }
-    }
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    const bool ok = v < nvec;
+    rx[i] = ok ? xr[v] : make_uint4(0, 0, 0, 0);
+    rd[i] = ok ? dyr[v] : make_uint4(0, 0, 0, 0);
+    rr[i] = (ok && drr) ? drr[v] : make_uint4(0, 0, 0, 0);
   }
+  const float mu = mean[row], rs = rstd[row];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
     if (v < nvec) {
+      float fx[8], fd[8];
+      unpack8(rx[i], fx);
+      unpack8(rd[i], fd);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[v * 8 + j], dg[i][j]);
-        atomicAdd(&red[D + v * 8 + j], db[i][j]);
+        const float g = fd[j] * gm[j];
+        s1 += g;
+        s2 = fmaf(g, (fx[j] - mu) * rs, s2);
       }
     }
   }
+  const float m1 = warp_sum(s1) / static_cast<float>(D);
+  const float m2 = warp_sum(s2) / static_cast<float>(D);
+  uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float fx[8], fd[8], fr[8], o[8];
+      unpack8(rx[i], fx);
+      unpack8(rd[i], fd);
+      unpack8(rr[i], fr);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gm[j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
+      dxr[v] = pack8(o);
+    }
+  }
+}
+
+constexpr int LNB_TY = 8;
+__global__ void __launch_bounds__(32 * LNB_TY) layernorm_bwd_dgdb_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                                          const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                          const float* __restrict__ mean,
+                                                                          const float* __restrict__ rstd,
+                                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                          int rows, int D, int rows_per_block) {
+  __shared__ float red[2][LNB_TY][32][8];
+  const int v = blockIdx.y * 32 + threadIdx.x;
+  const int nvec = D >> 3;
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float dg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, db[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (v < nvec) {
+    for (int r = r0 + threadIdx.y; r < r1; r += LNB_TY) {
+      float fx[8], fd[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ldx + v * 8), fx);
+      unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<long long>(r) * lddy + v * 8), fd);
+      const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dg[j] = fmaf(fd[j], (fx[j] - mu) * rs, dg[j]);
+        db[j] += fd[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.y][threadIdx.x][j] = dg[j];
+    red[1][threadIdx.y][threadIdx.x][j] = db[j];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    atomicAdd(&dgamma[i], red[i]);
-    atomicAdd(&dbeta[i], red[D + i]);
+  if (threadIdx.y < 2 && v < nvec) {
+    float* dst = threadIdx.y == 0 ? dgamma : dbeta;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int t = 0; t < LNB_TY; ++t) s += red[threadIdx.y][t][threadIdx.x][j];
+      atomicAdd(&dst[v * 8 + j], s);
+    }
   }
 }
 
@@ -353,8 +380,8 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   if ((D % 8) || (ldx % 8) || (ldy % 8)) return set_error(OVK_ERR_ALIGN, "layernorm: D, ldx, ldy must be multiples of 8");
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int wpb = 8;
-  const int grid = (rows + wpb - 1) / wpb;
+  const int rpb = 8 * 2;  // 8 warps x 2 rows
+  const int grid = (rows + rpb - 1) / rpb;
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (D <= 256) layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
@@ -372,21 +399,27 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
     return set_error(OVK_ERR_ALIGN, "layernorm_bwd: D and leading dimensions must be multiples of 8");
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm_bwd: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // ~4 blocks per SM; each block reduces its rows' dgamma/dbeta before touching global atomics
-  int nblocks = num_sms() * 4;
-  int rpb = (rows + nblocks - 1) / nblocks;
-  if (rpb < 8) rpb = 8;
-  nblocks = (rows + rpb - 1) / rpb;
-  const size_t smem = 2 * static_cast<size_t>(D) * sizeof(float);
   auto dyp = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   auto drp = reinterpret_cast<const __nv_bfloat16*>(dres);
-  if (D <= 256) layernorm_bwd_kernel<1><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else if (D <= 512) layernorm_bwd_kernel<2><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else if (D <= 1024) layernorm_bwd_kernel<4><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  else layernorm_bwd_kernel<8><<<nblocks, 256, smem, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, dgamma, dbeta, rows, D, rpb);
-  return check_launch("layernorm_bwd_kernel");
+  if (dgamma != nullptr && dbeta != nullptr) {   // parameter gradients first: dx may alias dy
+    const int gy = (D / 8 + 31) / 32;
+    int gx = (num_sms() * 8 + gy - 1) / gy;
+    int rpb = (rows + gx - 1) / gx;
+    if (rpb < LNB_TY) rpb = LNB_TY;
+    gx = (rows + rpb - 1) / rpb;
+    dim3 grid(gx, gy), block(32, LNB_TY);
+    layernorm_bwd_dgdb_kernel<<<grid, block, 0, s>>>(dyp, lddy, xp, ldx, mean, rstd, dgamma, dbeta, rows, D, rpb);
+    int rc = check_launch("layernorm_bwd_dgdb_kernel");
+    if (rc) return rc;
+  }
+  const int grid = (rows + 7) / 8;
+  if (D <= 256) layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  else if (D <= 512) layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  else if (D <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  else layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  return check_launch("layernorm_bwd_dx_kernel");
 }
 
 extern "C" int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long ldc, int B, int H, int W,

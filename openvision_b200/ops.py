@@ -192,7 +192,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dx=None, dres=None):
         _lib.call("ovk_layernorm_bwd", _p(dy), dy.stride(0), _p(x), x.stride(0), _p(gamma), _p(mean), _p(rstd), _p(dres),
                   dres.stride(0) if dres is not None else 0, _p(dx), dx.stride(0), _p(dgamma), _p(dbeta), rows, D,
                   _stream())
-    _count()
+    _count(2)
     return dx
 
 
