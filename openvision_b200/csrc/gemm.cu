@@ -2,6 +2,8 @@
 // Replaces the reference's F.linear / addmm call sites (open_clip/transformer.py:225,233-235,250-252 via
 // nn.MultiheadAttention in_proj/out_proj and mlp.c_fc/c_proj, :645-646 pooled @ proj) and, in the backward pass, the
 // dgrad / wgrad matmuls autograd derives from them, with fused bias / GELU / residual / GELU' epilogues.
+#include <stdlib.h>
+
 #include "act.cuh"
 #include "gemm_core.cuh"
 #include "host_utils.h"
@@ -20,13 +22,13 @@ struct GemmEpi {
 // EPI_LINEAR: C = alpha*acc + bias (+ R)                   R  = residual tile [M,N] bf16 (tmR), may alias C
 // EPI_ACT   : C = act(acc + bias), optionally D = acc+bias  D  = saved pre-activation (tmD) for the backward pass
 // EPI_DACT  : C = alpha*acc * act'(R)                       R  = saved pre-activation
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmD, const GemmEpi ep, int M, int N, int K, int splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using L = GemmSmemLayout<BN>;
+  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4, PAIR>;
   GemmCtx<BN, L> cx(smem_raw);
   const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, &tmC, &tmR);
   const int warp = threadIdx.x >> 5;
@@ -55,10 +57,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_res = !OUT_F32 && (EPI == EPI_DACT || (EPI == EPI_LINEAR && (ep.flags & OVK_EPI_RESIDUAL) != 0));
     const bool save_pre = EPI == EPI_ACT && (ep.flags & OVK_EPI_SAVE_PREACT) != 0;
     const float alpha = ep.alpha;
-    GemmSched sched(M, N, BN, K, splits);
+    GemmSched sched(M, N, BN, K, splits, PAIR, cx.rank);
     const bool reduce_out = OUT_F32 && sched.splits > 1;   // split-K partial sums are ADDED into a zeroed C
     int it = 0;
-    for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
+    for (int t = cx.first; t < sched.total; t += cx.stride, ++it) {
       const GemmTileInfo ti = sched.tile(t, BN);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -101,7 +103,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (c == NCHUNK - 1) {  // accumulator drained into registers: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cx.tmem_empty[acc]);
+          if (lane == 0) cx.release_accumulator(acc);
         }
         if (!live) continue;
         float x[CW];
@@ -190,16 +192,25 @@ struct GemmArgs {
   int epi;
 };
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+static bool pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OVK_GEMM_PAIR");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;   // default on; OVK_GEMM_PAIR=0 selects the single-CTA kernels
+  }
+  return v == 1;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR>
 static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
-  using L = GemmSmemLayout<BN>;
+  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4, PAIR>;
   CUtensorMap tmA, tmB, tmC, tmR, tmD;
   int rc;
   if (A_MN) rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, g.lda, 64, 64);
   else rc = make_tmap_2d_bf16(&tmA, g.A, g.K, g.M, g.lda, GEMM_BK, GEMM_BM);
   if (rc) return rc;
   if (B_MN) rc = make_tmap_2d_bf16(&tmB, g.B, g.N, g.K, g.ldb, 64, 64);
-  else rc = make_tmap_2d_bf16(&tmB, g.B, g.K, g.N, g.ldb, GEMM_BK, BN);
+  else rc = make_tmap_2d_bf16(&tmB, g.B, g.K, g.N, g.ldb, GEMM_BK, L::B_ROWS);
   if (rc) return rc;
   if (OUT_F32) rc = make_tmap_2d_f32(&tmC, g.C, g.N, g.M, g.ldc, 32, GEMM_BM);
   else rc = make_tmap_2d_bf16(&tmC, g.C, g.N, g.M, g.ldc, 64, GEMM_BM);
@@ -208,20 +219,22 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   tmD = tmC;
   if (g.R && (rc = make_tmap_2d_bf16(&tmR, g.R, g.N, g.M, g.ldr, 64, GEMM_BM))) return rc;
   if (g.D && (rc = make_tmap_2d_bf16(&tmD, g.D, g.N, g.M, g.ldd, 64, GEMM_BM))) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ((g.M + GEMM_BM - 1) / GEMM_BM) * ((g.N + BN - 1) / BN);
+  const int bm = PAIR ? 2 * GEMM_BM : GEMM_BM;
+  const int tiles = ((g.M + bm - 1) / bm) * ((g.N + BN - 1) / BN);
+  const int units = PAIR ? num_sms() / 2 : num_sms();   // CTA pairs or CTAs that can be resident
   // split-K (fp32 outputs only: the weight-gradient GEMMs have few output tiles and a huge K = tokens): partial sums
   // are added into a zeroed C by TMA reduce-add stores
   int splits = 1;
-  if (OUT_F32 && tiles * 10 < num_sms() * 7) {
+  if (OUT_F32 && tiles * 10 < units * 7) {
     const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
-    splits = num_sms() / tiles;
+    splits = units / tiles;
     if (splits > num_kb / 8) splits = num_kb / 8;
     if (splits < 1) splits = 1;
   }
@@ -230,15 +243,34 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaMemset2DAsync(gemm split-K): %s", cudaGetErrorString(e));
   }
   const int items = tiles * splits;
-  const int grid = items < num_sms() ? items : num_sms();
-  kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K, splits);
+  const int nunits = items < units ? items : units;
+  if (!PAIR) {
+    kern<<<nunits, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K, splits);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * nunits, 1, 1);
+    cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = L::DYN_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, tmD, g.ep, g.M, g.N, g.K, splits);
+    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaLaunchKernelEx(gemm pair): %s", cudaGetErrorString(e));
+  }
   return check_launch("gemm_bf16_kernel");
 }
 
 template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
 static int launch_gemm_bn(const GemmArgs& g, cudaStream_t s) {
-  if (g.N <= 128) return launch_gemm_t<128, A_MN, B_MN, EPI, OUT_F32>(g, s);
-  return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32>(g, s);
+  if (g.N <= 128) return launch_gemm_t<128, A_MN, B_MN, EPI, OUT_F32, false>(g, s);
+  // CTA pairs (256-row tiles) once there are enough rows to fill them; small problems stay on single CTAs
+  if (pair_mode_enabled() && g.M >= 512) return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, true>(g, s);
+  return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, false>(g, s);
 }
 
 static int check_common(const GemmArgs& g, const char* who) {

@@ -293,3 +293,73 @@ __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 }  // namespace ovk
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters
+namespace ovk {
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // shared::cluster address -> same offset in the pair's leader (even) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier addressed in the shared::cluster window (e.g. the leader CTA's barrier)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_out) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// TMA load; PAIR: executed by both CTAs of a pair, the transaction bytes are credited to the LEADER's mbarrier
+template <bool PAIR>
+__device__ __forceinline__ void tma_load_2d_x(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (PAIR) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    tma_load_2d(smem_dst, m, bar, c0, c1);
+  }
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; PAIR: one instruction drives both SMs of the pair (M = 256)
+template <bool PAIR>
+__device__ __forceinline__ void umma_bf16_ss_x(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if constexpr (PAIR) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+  } else {
+    umma_bf16_ss(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
+// completion of all previously issued MMAs -> mbarrier arrive; PAIR: at the same offset in BOTH CTAs of the pair
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_x(uint64_t* bar) {
+  if constexpr (PAIR) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+  } else {
+    umma_commit(bar);
+  }
+}
+}  // namespace ovk
