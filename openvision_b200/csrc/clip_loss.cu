@@ -49,14 +49,16 @@ __device__ __forceinline__ float warp_column_sums(float (&e)[32], uint32_t lane)
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-using FwdLayout = GemmSmemLayout<CL_BN, 0, 4 * CL_BN * 8>;  // epilogue scratch: [4 quads][256 cols] (ref, sum)
+template <bool PAIR>
+using FwdLayout = GemmSmemLayout<CL_BN, 0, 4 * CL_BN * 8, PAIR>;  // epilogue scratch: [4 quads][256 cols] (ref, sum)
 
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      float2* __restrict__ ws_row, float2* __restrict__ ws_col, float* __restrict__ diag, int n_loc,
                      int n_all, int E, int row_offset, float scale) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using L = FwdLayout;
+  using L = FwdLayout<PAIR>;
   GemmCtx<CL_BN, L> cx(smem_raw);
   const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, nullptr);
   const int warp = threadIdx.x >> 5;
@@ -74,9 +76,9 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t bar_id = 1 + grp;
     const uint32_t scol = smem_u32(cx.epi_scratch());  // float2 [4][256]
     const float s2 = scale * LOG2E;
-    GemmSched sched(n_loc, n_all, CL_BN, E);
+    GemmSched sched(n_loc, n_all, CL_BN, E, 1, PAIR, cx.rank);
     int it = 0;
-    for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
+    for (int t = cx.first; t < sched.total; t += cx.stride, ++it) {
       const GemmTileInfo ti = sched.tile(t, CL_BN);
       const int tile_n = ti.n0 / CL_BN;
       const int tile_m = ti.m0 / GEMM_BM;
@@ -102,12 +104,13 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         tmem_ld_x32(taddr + c * 32, v);
         tmem_ld_wait();
         float z[32];
-        float cmax = NEG_INF;
+        float cm[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF};   // four independent chains (the epilogue is latency-bound)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           z[j] = (row_valid && col0 + j < n_all) ? __uint_as_float(v[j]) * s2 : NEG_INF;
-          cmax = fmaxf(cmax, z[j]);
+          cm[j & 3] = fmaxf(cm[j & 3], z[j]);
         }
+        const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
         // positive-pair logit z_ii (natural units) when this chunk crosses the label diagonal
         if (__any_sync(0xffffffffu, row_valid && label >= col0 && label < col0 + 32)) {
           const int dj = label - col0;
@@ -122,12 +125,13 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           continue;
         }
         float e[32];
-        float rs = 0.f;
+        float rsp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           e[j] = fast_exp2(z[j] - c_ref);
-          rs += e[j];
+          rsp[j & 3] += e[j];
         }
+        const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
         if (cmax > NEG_INF) {  // row update (online softmax over the chunks / tiles this thread sees)
           const float m_new = fmaxf(m_row, cmax);
           float add;
@@ -163,7 +167,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       // accumulator fully consumed: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&cx.tmem_empty[acc]);
+      if (lane == 0) cx.release_accumulator(acc);
       if (row_valid) ws_row[static_cast<long long>(tile_n * 2 + grp) * n_loc + row] = make_float2(m_row, l_row);
       named_bar_sync(bar_id, GEMM_GROUP_THREADS);
       {  // merge the four row-quadrants of this group's 128 columns
@@ -264,15 +268,17 @@ clip_loss_value_kernel(const float* __restrict__ row_lse, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------ backward: G = dL/dz
-using GradLayout = GemmSmemLayout<CL_BN, 2 * GEMM_BM * 128, 2 * CL_BN * 4>;
+template <bool PAIR>
+using GradLayout = GemmSmemLayout<CL_BN, 2 * GEMM_BM * 128, 2 * CL_BN * 4, PAIR>;
 
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmG, const float* __restrict__ row_lse,
                       const float* __restrict__ col_lse, float* __restrict__ d_scale, int n_loc, int n_all, int E,
                       int row_offset, float scale, float w_row, float w_col) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using L = GradLayout;
+  using L = GradLayout<PAIR>;
   GemmCtx<CL_BN, L> cx(smem_raw);
   const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, &tmG);
   const int warp = threadIdx.x >> 5;
@@ -294,9 +300,9 @@ clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const float s2 = scale * LOG2E;
     const float w_diag = w_row + w_col;
     float ds = 0.f;  // sum G_ij * acc_ij  (= sum G * z / scale)
-    GemmSched sched(n_loc, n_all, CL_BN, E);
+    GemmSched sched(n_loc, n_all, CL_BN, E, 1, PAIR, cx.rank);
     int it = 0;
-    for (int t = blockIdx.x; t < sched.total; t += gridDim.x, ++it) {
+    for (int t = cx.first; t < sched.total; t += cx.stride, ++it) {
       const GemmTileInfo ti = sched.tile(t, CL_BN);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -329,7 +335,7 @@ clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (c == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cx.tmem_empty[acc]);
+          if (lane == 0) cx.release_accumulator(acc);
         }
         if (!live) continue;
         float g[64];
@@ -376,6 +382,30 @@ clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
 using namespace ovk;
 
+// launch with (PAIR) a 2-CTA cluster per SM pair, or one CTA per SM
+template <bool PAIR, class Kern, class... Args>
+static int launch_loss_kernel(Kern kern, int smem_bytes, int tiles, cudaStream_t stream, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(clip_loss): %s", cudaGetErrorString(e));
+  const int units = PAIR ? num_sms() / 2 : num_sms();
+  const int n = tiles < units ? tiles : units;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? 2 * n : n, 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaLaunchKernelEx(clip_loss): %s", cudaGetErrorString(e));
+  return check_launch("clip_loss kernel");
+}
+
 static inline int cl_tiles_m(int n_loc) { return (n_loc + GEMM_BM - 1) / GEMM_BM; }
 static inline int cl_tiles_n(int n_all) { return (n_all + CL_BN - 1) / CL_BN; }
 
@@ -396,21 +426,19 @@ extern "C" int ovk_clip_loss_fwd(const void* img_loc, const void* txt_all, int n
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmA, img_loc, E, n_loc, E, GEMM_BK, GEMM_BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmB, txt_all, E, n_all, E, GEMM_BK, CL_BN))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(clip_loss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout::DYN_BYTES);
-    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(clip_loss_fwd): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  if ((rc = make_tmap_2d_bf16(&tmB, txt_all, E, n_all, E, GEMM_BK, n_loc >= 512 ? CL_BN / 2 : CL_BN))) return rc;
   const int tm = cl_tiles_m(n_loc), tn = cl_tiles_n(n_all);
   float2* ws_row = reinterpret_cast<float2*>(workspace);
   float2* ws_col = ws_row + 2LL * tn * n_loc;
-  const int tiles = tm * tn;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  clip_loss_fwd_kernel<<<grid, GEMM_THREADS, FwdLayout::DYN_BYTES, s>>>(tmA, tmB, ws_row, ws_col, diag, n_loc, n_all, E,
-                                                                        row_offset, scale);
-  if ((rc = check_launch("clip_loss_fwd_kernel"))) return rc;
+  if (n_loc >= 512) {   // CTA pairs (256-row tiles)
+    if ((rc = launch_loss_kernel<true>(clip_loss_fwd_kernel<true>, FwdLayout<true>::DYN_BYTES, ((n_loc + 255) / 256) * tn, s,
+                                       tmA, tmB, ws_row, ws_col, diag, n_loc, n_all, E, row_offset, scale)))
+      return rc;
+  } else {
+    if ((rc = launch_loss_kernel<false>(clip_loss_fwd_kernel<false>, FwdLayout<false>::DYN_BYTES, tm * tn, s, tmA, tmB, ws_row,
+                                        ws_col, diag, n_loc, n_all, E, row_offset, scale)))
+      return rc;
+  }
   const int total = n_loc + n_all;
   clip_loss_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(ws_row, ws_col, n_loc, n_all, 2 * tn, tm, row_lse, col_max, col_sum);
   return check_launch("clip_loss_finalize_kernel");
@@ -442,17 +470,13 @@ extern "C" int ovk_clip_loss_grad_logits(const void* img_loc, const void* txt_al
   CUtensorMap tmA, tmB, tmG;
   int rc;
   if ((rc = make_tmap_2d_bf16(&tmA, img_loc, E, n_loc, E, GEMM_BK, GEMM_BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmB, txt_all, E, n_all, E, GEMM_BK, CL_BN))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, txt_all, E, n_all, E, GEMM_BK, n_loc >= 512 ? CL_BN / 2 : CL_BN))) return rc;
   if ((rc = make_tmap_2d_bf16(&tmG, G, n_all, n_loc, ldg, 64, GEMM_BM))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(clip_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GradLayout::DYN_BYTES);
-    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(clip_loss_grad): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  const int tiles = cl_tiles_m(n_loc) * cl_tiles_n(n_all);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  clip_loss_grad_kernel<<<grid, GEMM_THREADS, GradLayout::DYN_BYTES, s>>>(tmA, tmB, tmG, row_lse, col_lse, d_scale_partial,
-                                                                          n_loc, n_all, E, row_offset, scale, w_row, w_col);
-  return check_launch("clip_loss_grad_kernel");
+  if (n_loc >= 512)
+    return launch_loss_kernel<true>(clip_loss_grad_kernel<true>, GradLayout<true>::DYN_BYTES,
+                                    ((n_loc + 255) / 256) * cl_tiles_n(n_all), s, tmA, tmB, tmG, row_lse, col_lse,
+                                    d_scale_partial, n_loc, n_all, E, row_offset, scale, w_row, w_col);
+  return launch_loss_kernel<false>(clip_loss_grad_kernel<false>, GradLayout<false>::DYN_BYTES,
+                                   cl_tiles_m(n_loc) * cl_tiles_n(n_all), s, tmA, tmB, tmG, row_lse, col_lse, d_scale_partial,
+                                   n_loc, n_all, E, row_offset, scale, w_row, w_col);
 }
