@@ -251,5 +251,6 @@ def test_act_matches_exact_erf_gelu_pointwise(ops):
     y = ops.gemm(x.cuda(), eye.cuda(), act="gelu")
     ref = O.gelu(x.double(), "erf")
     err = (y.double().cpu() - ref).abs()
-    # bf16 output rounding (rel 2^-9) dominates; the approximation itself is <= 3e-5 absolute
-    assert (err <= 2.0 ** -8 * ref.abs() + 4e-5).all(), err.max()
+    # bf16 output rounding (rel 2^-9) dominates; the polynomial fit is <= 3e-5 absolute and the single-MUFU tanh.approx
+    # (relative error 2^-11) adds <= 2.5e-4 * |x|
+    assert (err <= 2.0 ** -8 * ref.abs() + 3e-4 * x.double().abs() + 4e-5).all(), err.max()
