@@ -28,15 +28,33 @@ constexpr int ATT_OFF_TAIL = ATT_OFF_XCHG + 512;   // remainder key row (128 B) 
 constexpr int ATT_OFF_BAR = ATT_OFF_TAIL + 384;
 constexpr int ATT_NUM_BARS = 14;
 constexpr int ATT_SMEM_BYTES = ATT_OFF_BAR + ATT_NUM_BARS * 8 + 16;
+// Head widths 64 < hd <= 80 (H/14: 80, So400m/14: 72): the extra RB = 16 dims ride along as a second, narrow operand
+// block: [128 rows x 32 B] tiles with 32-byte swizzle (TMA zero-fills dims >= hd), one more k-step in S = Q K^T and a
+// second N = 16 accumulator for P V.  These tiles sit after the hd = 64 layout (then only one CTA fits per SM).
+constexpr int ATT_BT = 128 * 32;                                   // 4 KB narrow tile
+constexpr int ATT_OFF_QB = (ATT_SMEM_BYTES + 1023) / 1024 * 1024;
+constexpr int ATT_OFF_KB = ATT_OFF_QB + ATT_BT;                    // x2
+constexpr int ATT_OFF_VB = ATT_OFF_KB + 2 * ATT_BT;                // x2
+constexpr int ATT_OFF_OB = ATT_OFF_VB + 2 * ATT_BT;                // output staging
+constexpr int ATT_SMEM_BYTES_RB = ATT_OFF_OB + ATT_BT;
+constexpr uint32_t ATT_TMEM_OB = 192;                              // 16 columns after O
+constexpr uint32_t UMMA_SW32 = 6;
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) { return umma_desc(saddr, 16, 256, UMMA_SW32); }
+// 16-byte chunk `chunk` (0..1) of row `row` in a [rows x 32 B] SWIZZLE_32B tile
+__device__ __forceinline__ uint32_t sw32_offset(uint32_t row, uint32_t chunk) {
+  return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
+}
 constexpr int ATT_MAX_TAIL = 1;     // remainder key / query row (L mod 128 == 1: cls + power-of-two grid) handled outside the tiles
 constexpr int ATT_TAIL_MAX_L = 1040;  // longest sequence the remainder-row kernel keeps scores for (16 KB of smem)     // remainder keys / query rows (L mod 128) handled outside the 128-wide tiles
 constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
 
+template <int RB>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
-                     const __grid_constant__ CUtensorMap tmTail, float* __restrict__ lse_out, int L, int Lm, int H,
+                     const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmQKVb,
+                     const __grid_constant__ CUtensorMap tmOb, float* __restrict__ lse_out, int L, int Lm, int H,
                      int nq, int total_items, float scale_log2) {
   // PERSISTENT: each CTA walks work items (query tile, head, image) with stride gridDim.x, keeping its TMEM allocation,
   // barriers and the K/V TMA ring alive across items, so the next item's Q/K/V loads run under the current item's
@@ -100,8 +118,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
         const int qt = item % nq, h = (item / nq) % H, b = item / (nq * H);
         mbar_wait(q_empty, (n & 1) ^ 1, 9);
-        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0));
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0) + (RB ? ATT_BT : 0));
         tma_load_4d(sQ, &tmQKV, q_full, 0, h, qt * ATT_BQ, b);
+        if (RB) tma_load_4d(smem + ATT_OFF_QB, &tmQKVb, q_full, 64, h, qt * ATT_BQ, b);
         if (ntail > 0) {  // remainder key row and its value row (1 x 128 B each, unswizzled)
           tma_load_4d(smem + ATT_OFF_TAIL, &tmTail, q_full, 0, H + h, Lm, b);
           tma_load_4d(smem + ATT_OFF_TAIL + 128 + (n & 1) * 128, &tmTail, q_full, 0, 2 * H + h, Lm, b);
@@ -110,11 +129,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           const int s = g & 1;
           const uint32_t ph = (g >> 1) & 1;
           mbar_wait(&k_empty[s], ph ^ 1, 10);
-          mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+          mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES + (RB ? ATT_BT : 0));
           tma_load_4d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], 0, H + h, j * ATT_BKV, b);
+          if (RB) tma_load_4d(smem + ATT_OFF_KB + s * ATT_BT, &tmQKVb, &k_full[s], 64, H + h, j * ATT_BKV, b);
           mbar_wait(&v_empty[s], ph ^ 1, 11);
-          mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+          mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES + (RB ? ATT_BT : 0));
           tma_load_4d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], 0, 2 * H + h, j * ATT_BKV, b);
+          if (RB) tma_load_4d(smem + ATT_OFF_VB + s * ATT_BT, &tmQKVb, &v_full[s], 64, 2 * H + h, j * ATT_BKV, b);
         }
       }
     }
@@ -142,6 +163,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
                          umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
           }
+          if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
+            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + ATT_OFF_QB)),
+                         umma_desc_sw32(smem_u32(smem + ATT_OFF_KB + s * ATT_BT)), idesc_s, 1);
           umma_commit(&k_empty[s]);
           umma_commit(s_full);
           if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
@@ -157,6 +181,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             const uint32_t bb = v_addr + kk * 16 * 128;
             umma_bf16_ss(tmem_base + ATT_TMEM_O, umma_desc_kmajor_sw128(a), umma_desc_mnmajor_sw128(bb, ATT_TILE_BYTES),
                          idesc_pv, (j | kk) != 0);
+          }
+          if (RB) {   // output dims 64 .. 64 + RB: N = 16 accumulator, V_b consumed MN-major from its 32-byte rows
+            constexpr uint32_t idesc_pvb = umma_idesc_bf16(ATT_BQ, 16, 0, 1);
+            const uint32_t vb_addr = smem_u32(smem + ATT_OFF_VB + s * ATT_BT);
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
+              umma_bf16_ss(tmem_base + ATT_TMEM_OB, umma_desc_kmajor_sw128(a), umma_desc_sw32(vb_addr + kk * 512), idesc_pvb,
+                           (j | kk) != 0);
+            }
           }
           umma_commit(&v_empty[s]);
           umma_commit(pv_done);
@@ -265,6 +298,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
             tmem_st_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
+            if (RB && half == 0) {
+              uint32_t ob[16];
+              tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_OB, ob);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * alpha);
+              tmem_st_x16(tmem_base + t_lane + ATT_TMEM_OB, ob);
+            }
             tmem_st_wait();
           }
         }
@@ -301,7 +342,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_wait(pv_done, (g - 1) & 1, 18);
       tc_fence_after();
       uint32_t o[32];
+      uint32_t ob[16];
       tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
+      if (RB && half == 0) tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_OB, ob);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(o_free);  // the accumulator may be overwritten by the next item's first P V
@@ -340,10 +383,21 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       if (half == 0 && lse_out != nullptr && q0 + r < L) {
         lse_out[(static_cast<long long>(b) * H + h) * L + q0 + r] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
       }
+      if (RB && half == 0) {
+        const uint32_t obs = smem_u32(smem + ATT_OFF_OB);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+          sts128(obs + sw32_offset(r, c),
+                 make_uint4(pack_bf16x2(__uint_as_float(ob[8 * c]) * inv_l, __uint_as_float(ob[8 * c + 1]) * inv_l),
+                            pack_bf16x2(__uint_as_float(ob[8 * c + 2]) * inv_l, __uint_as_float(ob[8 * c + 3]) * inv_l),
+                            pack_bf16x2(__uint_as_float(ob[8 * c + 4]) * inv_l, __uint_as_float(ob[8 * c + 5]) * inv_l),
+                            pack_bf16x2(__uint_as_float(ob[8 * c + 6]) * inv_l, __uint_as_float(ob[8 * c + 7]) * inv_l)));
+      }
       fence_proxy_async_smem();
       named_bar_sync(1, SMT);
       if (threadIdx.x == 0) {
         tma_store_4d(&tmO, sP, 0, h, q0, b);
+        if (RB) tma_store_4d(&tmOb, smem + ATT_OFF_OB, 64, h, q0, b);
         tma_store_commit();
       }
     }
@@ -447,42 +501,54 @@ using namespace ovk;
 extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
                                  void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention: empty problem");
-  if (hd != ATT_HD) return set_error(OVK_ERR_SHAPE, "attention: head dim %d not supported (this build: 64)", hd);
+  if (hd < 64 || hd > 80 || (hd % 8))
+    return set_error(OVK_ERR_SHAPE, "attention: head dim %d not supported (64, 72 or 80)", hd);
+  const bool ext = hd > ATT_HD;   // 64 < hd <= 80: extra 16-dim operand block (zero-filled past hd by TMA)
   if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention: B and H must be <= 65535");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tmQKV, tmO, tmTail;
+  CUtensorMap tmQKV, tmO, tmTail, tmQKVb, tmOb;
   int rc;
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * H), (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)3 * H * hd * 2, (uint64_t)L * 3 * H * hd * 2};
-    const uint32_t box[4] = {(uint32_t)hd, 1, ATT_BKV, 1};
+    const uint32_t box[4] = {ATT_HD, 1, ATT_BKV, 1};
     if ((rc = make_tmap_nd_bf16(&tmQKV, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    const uint32_t box1[4] = {(uint32_t)hd, 1, 1, 1};   // one head row (128 B), unswizzled: the remainder key / value
+    const uint32_t box1[4] = {ATT_HD, 1, 1, 1};   // one head row (128 B), unswizzled: the remainder key / value
     if ((rc = make_tmap_nd_bf16(&tmTail, qkv, 4, dims, strides, box1, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    const uint32_t boxb[4] = {16, 1, ATT_BKV, 1};  // dims 64..79 as [128 rows x 32 B] tiles
+    if ((rc = make_tmap_nd_bf16(&tmQKVb, qkv, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)H * hd * 2, (uint64_t)L * H * hd * 2};
-    const uint32_t box[4] = {(uint32_t)hd, 1, ATT_BQ, 1};
+    const uint32_t box[4] = {ATT_HD, 1, ATT_BQ, 1};
     if ((rc = make_tmap_nd_bf16(&tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    const uint32_t boxb[4] = {16, 1, ATT_BQ, 1};
+    if ((rc = make_tmap_nd_bf16(&tmOb, out, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES_RB);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  // a short remainder of query rows goes to the FMA-pipe tail kernel instead of a padded 128-row tile
+  // a short remainder of query rows goes to the FMA-pipe tail kernel instead of a padded 128-row tile (hd = 64 only)
   int tail = L % ATT_BQ;
-  if (L <= ATT_BQ || tail > ATT_MAX_TAIL || L > ATT_TAIL_MAX_L) tail = 0;
+  if (ext || L <= ATT_BQ || tail > ATT_MAX_TAIL || L > ATT_TAIL_MAX_L) tail = 0;
   const int l_main = L - tail;
   const int nq = (l_main + ATT_BQ - 1) / ATT_BQ;
   const long long items = static_cast<long long>(nq) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
-  const int grid = static_cast<int>(items < 2LL * num_sms() ? items : 2LL * num_sms());   // persistent, 2 CTAs per SM
-  attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, lse, L, l_main, H, nq,
-                                                                 static_cast<int>(items),
-                                                                 scale * 1.4426950408889634f);
+  const int per_sm = ext ? 1 : 2;   // the extended layout needs 137 KB of shared memory
+  const int grid = static_cast<int>(items < (long long)per_sm * num_sms() ? items : (long long)per_sm * num_sms());
+  if (ext)
+    attention_fwd_kernel<16><<<grid, ATT_THREADS, ATT_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+                                                                          static_cast<int>(items), scale * 1.4426950408889634f);
+  else
+    attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+                                                                      static_cast<int>(items), scale * 1.4426950408889634f);
   if ((rc = check_launch("attention_fwd_kernel"))) return rc;
   if (tail) {
     dim3 tgrid((tail * H + 3) / 4, B);

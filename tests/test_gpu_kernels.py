@@ -197,7 +197,7 @@ def test_error_paths_return_codes_not_crashes(ops):
     with pytest.raises(OvkError):
         ops.gemm(a.cpu(), w.cpu())
     with pytest.raises(OvkError):
-        ops.attention(torch.zeros(4, 3 * 48, dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 48)   # hd = 48 unsupported
+        ops.attention(torch.zeros(4, 3 * 48, dtype=torch.bfloat16, device="cuda"), 1, 4, 1, 48)   # hd < 64 unsupported
 
 
 # ------------------------------------------------------------------------------------------------ backward GEMMs
@@ -254,3 +254,14 @@ def test_act_matches_exact_erf_gelu_pointwise(ops):
     # bf16 output rounding (rel 2^-9) dominates; the polynomial fit is <= 3e-5 absolute and the single-MUFU tanh.approx
     # (relative error 2^-11) adds <= 2.5e-4 * |x|
     assert (err <= 2.0 ** -8 * ref.abs() + 3e-4 * x.double().abs() + 4e-5).all(), err.max()
+
+
+@pytest.mark.parametrize("hd", [72, 80])
+@pytest.mark.parametrize("B,L,H", [(2, 257, 2), (1, 101, 3), (1, 577, 1), (2, 128, 1), (1, 130, 2)])
+def test_attention_fwd_wide_heads(ops, hd, B, L, H):
+    """head widths of H/14 (80) and So400m/14 (72): the dims past 64 ride along as a 16-wide operand block."""
+    qkv = rnd(B * L, 3 * H * hd, seed=L + hd).bfloat16()
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, f"attention hd{hd} B{B} L{L} H{H}")
+    assert_close(lse, lse_ref, 1e-3, "attention lse")
