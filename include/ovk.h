@@ -125,7 +125,7 @@ int ovk_colsum_bf16(const void* x, long long ldx, int rows, int cols, float* out
  *   qkv : bf16 [B, L, 3, H, hd] (= in_proj output [B*L, 3*D], rows q|k|v as in in_proj_weight)
  *   out : bf16 [B, L, H*hd]
  *   lse : optional f32 [B, H, L], natural-log sum-exp of the scaled scores (saved for backward)
- * hd must be 64 in this build.
+ * hd: 64 (Ti/B/L towers), 72 (So400m/14) or 80 (H/14); the dims past 64 ride along as a 16-wide operand block.
  */
 int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, void* stream);
 /* Backward: dqkv (bf16, same [B, L, 3, H, hd] layout) from qkv, the forward output `out`, its gradient `dout`

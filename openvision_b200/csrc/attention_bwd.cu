@@ -29,14 +29,31 @@ constexpr int AB_OFF_X = AB_OFF_DS + 2 * AB_TILE;   // extra tile (DQ: O_i for D
 constexpr int AB_OFF_BAR = AB_OFF_X + AB_TILE;
 constexpr int AB_NUM_BARS = 10;
 constexpr int AB_SMEM_BYTES = AB_OFF_BAR + AB_NUM_BARS * 8 + 16;
+// head widths 64 < hd <= 80: the dims past 64 ride along as narrow [128 rows x 32 B] SWIZZLE_32B tiles (see attention.cu)
+constexpr int AB_BT = 128 * 32;
+constexpr int AB_OFF_ST0B = (AB_SMEM_BYTES + 1023) / 1024 * 1024;
+constexpr int AB_OFF_ST1B = AB_OFF_ST0B + AB_BT;
+constexpr int AB_OFF_SAB = AB_OFF_ST1B + AB_BT;       // x2
+constexpr int AB_OFF_SBB = AB_OFF_SAB + 2 * AB_BT;    // x2
+constexpr int AB_OFF_XB = AB_OFF_SBB + 2 * AB_BT;
+constexpr int AB_OFF_OUTB = AB_OFF_XB + AB_BT;        // x2 output staging
+constexpr int AB_SMEM_BYTES_RB = AB_OFF_OUTB + 2 * AB_BT;
+constexpr uint32_t AB_TM_ACC0B = 384, AB_TM_ACC1B = 400;
+constexpr uint32_t AB_SW32 = 6;
+__device__ __forceinline__ uint64_t ab_desc_sw32(uint32_t saddr) { return umma_desc(saddr, 16, 256, AB_SW32); }
+__device__ __forceinline__ uint32_t ab_sw32_offset(uint32_t row, uint32_t chunk) {
+  return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
+}
 constexpr int AB_TMEM_COLS = 512;
 constexpr uint32_t AB_TM_S = 0, AB_TM_DP = 128, AB_TM_ACC0 = 256, AB_TM_ACC1 = 320;
 enum { MODE_DQ = 0, MODE_DKV = 1 };
 
-template <int MODE>
+template <int MODE, int RB>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                      const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
+                     const __grid_constant__ CUtensorMap tmQKVb, const __grid_constant__ CUtensorMap tmOb,
+                     const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
                      const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -84,26 +101,43 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
       if (MODE == MODE_DQ) {
-        mbar_arrive_expect_tx(st_full, 3 * AB_TILE);
+        mbar_arrive_expect_tx(st_full, 3 * AB_TILE + (RB ? 3 * AB_BT : 0));
         tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, h, t0, b);          // Q_i
         tma_load_4d(smem + AB_OFF_ST1, &tmDO, st_full, 0, h, t0, b);           // dO_i
         tma_load_4d(smem + AB_OFF_X, &tmO, st_full, 0, h, t0, b);              // O_i
+        if (RB) {
+          tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, st_full, 64, h, t0, b);
+          tma_load_4d(smem + AB_OFF_ST1B, &tmDOb, st_full, 64, h, t0, b);
+          tma_load_4d(smem + AB_OFF_XB, &tmOb, st_full, 64, h, t0, b);
+        }
       } else {
-        mbar_arrive_expect_tx(st_full, 2 * AB_TILE);
+        mbar_arrive_expect_tx(st_full, 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
         tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, H + h, t0, b);      // K_j
         tma_load_4d(smem + AB_OFF_ST1, &tmQKV, st_full, 0, 2 * H + h, t0, b);  // V_j
+        if (RB) {
+          tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, st_full, 64, H + h, t0, b);
+          tma_load_4d(smem + AB_OFF_ST1B, &tmQKVb, st_full, 64, 2 * H + h, t0, b);
+        }
       }
       for (int it = 0; it < nt; ++it) {
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&se[s], ph ^ 1, 20);
-        mbar_arrive_expect_tx(&sf[s], 2 * AB_TILE);
+        mbar_arrive_expect_tx(&sf[s], 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
         if (MODE == MODE_DQ) {
           tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, H + h, it * AB_T, b);      // K_j
           tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmQKV, &sf[s], 0, 2 * H + h, it * AB_T, b);  // V_j
+          if (RB) {
+            tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, H + h, it * AB_T, b);
+            tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmQKVb, &sf[s], 64, 2 * H + h, it * AB_T, b);
+          }
         } else {
           tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, h, it * AB_T, b);          // Q_i
           tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmDO, &sf[s], 0, h, it * AB_T, b);           // dO_i
+          if (RB) {
+            tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, h, it * AB_T, b);
+            tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmDOb, &sf[s], 64, h, it * AB_T, b);
+          }
         }
       }
     }
@@ -126,6 +160,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
         const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
         const uint32_t v_addr = (MODE == MODE_DQ) ? sb : st1;
+        const uint32_t st0b = smem_u32(smem + AB_OFF_ST0B), st1b = smem_u32(smem + AB_OFF_ST1B);
+        const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
+        const uint32_t qb_addr = (MODE == MODE_DQ) ? st0b : sab;
+        const uint32_t dob_addr = (MODE == MODE_DQ) ? st1b : sbb;
+        const uint32_t kb_addr = (MODE == MODE_DQ) ? sab : st0b;
+        const uint32_t vb_addr = (MODE == MODE_DQ) ? sbb : st1b;
         mbar_wait(&sf[s], ph, 22);
         tc_fence_after();
         const uint32_t idesc_s = umma_idesc_bf16(AB_T, nkv, 0, 0);
@@ -133,10 +173,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         for (int k = 0; k < AB_HD / 16; ++k)   // S = Q K^T
           umma_bf16_ss(tmem_base + AB_TM_S, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
                        idesc_s, k != 0);
+        if (RB) umma_bf16_ss(tmem_base + AB_TM_S, ab_desc_sw32(qb_addr), ab_desc_sw32(kb_addr), idesc_s, 1);
 #pragma unroll
         for (int k = 0; k < AB_HD / 16; ++k)   // dP = dO V^T
           umma_bf16_ss(tmem_base + AB_TM_DP, umma_desc_kmajor_sw128(do_addr + k * 32), umma_desc_kmajor_sw128(v_addr + k * 32),
                        idesc_s, k != 0);
+        if (RB) umma_bf16_ss(tmem_base + AB_TM_DP, ab_desc_sw32(dob_addr), ab_desc_sw32(vb_addr), idesc_s, 1);
         umma_commit(s_full);
         mbar_wait(pds_ready, it & 1, 23);
         tc_fence_after();
@@ -146,6 +188,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           for (int kk = 0; kk < nkv / 16; ++kk)
             umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
                          umma_desc_mnmajor_sw128(k_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+          if (RB) {
+            constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 0, 1);
+            for (int kk = 0; kk < nkv / 16; ++kk)
+              umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                           ab_desc_sw32(kb_addr + kk * 512), idescb, (it | kk) != 0);
+          }
         } else {
           // dV += P^T dO_i, dK += dS^T Q_i : A = (P | dS)^T MN-major (M = keys: two 64-key panels), B MN-major (rows = queries)
           constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 1, 1);
@@ -155,6 +203,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           for (int kk = 0; kk < nq / 16; ++kk)
             umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
                          umma_desc_mnmajor_sw128(q_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+          if (RB) {
+            constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 1, 1);
+            for (int kk = 0; kk < nq / 16; ++kk)
+              umma_bf16_ss(tmem_base + AB_TM_ACC1B, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
+                           ab_desc_sw32(dob_addr + kk * 512), idescb, (it | kk) != 0);
+            for (int kk = 0; kk < nq / 16; ++kk)
+              umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
+                           ab_desc_sw32(qb_addr + kk * 512), idescb, (it | kk) != 0);
+          }
         }
         umma_commit(&se[s]);
         umma_commit(mma_done);
@@ -180,6 +237,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) d = fmaf(bf16_lo(aw[q]), bf16_lo(gw[q]), fmaf(bf16_hi(aw[q]), bf16_hi(gw[q]), d));
+      }
+      if (RB) {
+        const uint32_t ob_s = smem_u32(smem + AB_OFF_XB), dob_s = smem_u32(smem + AB_OFF_ST1B);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const uint4 a = lds128(ob_s + ab_sw32_offset(r, c));
+          const uint4 g = lds128(dob_s + ab_sw32_offset(r, c));
+          const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) d = fmaf(bf16_lo(aw[q]), bf16_lo(gw[q]), fmaf(bf16_hi(aw[q]), bf16_hi(gw[q]), d));
+        }
       }
       dlt = d;
       const int row = t0 + r;
@@ -264,14 +332,35 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                             pack_bf16x2(__uint_as_float(o[8 * q + 6]) * mul, __uint_as_float(o[8 * q + 7]) * mul)));
       }
     }
+    if (RB && (MODE == MODE_DKV || hsel == 0)) {
+      // narrow accumulators: DQ: dQ_b (hsel 0); DKV: dK_b (hsel 0, scaled), dV_b (hsel 1)
+      const float mulb = (MODE == MODE_DQ || hsel == 0) ? scale : 1.f;
+      const uint32_t srcb = (MODE == MODE_DQ || hsel == 0) ? AB_TM_ACC0B : AB_TM_ACC1B;
+      uint32_t ob[16];
+      tmem_ld_x16(tmem_base + t_lane + srcb, ob);
+      tmem_ld_wait();
+      const uint32_t dst = smem_u32(smem + AB_OFF_OUTB + hsel * AB_BT);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        sts128(dst + ab_sw32_offset(r, c),
+               make_uint4(pack_bf16x2(__uint_as_float(ob[8 * c]) * mulb, __uint_as_float(ob[8 * c + 1]) * mulb),
+                          pack_bf16x2(__uint_as_float(ob[8 * c + 2]) * mulb, __uint_as_float(ob[8 * c + 3]) * mulb),
+                          pack_bf16x2(__uint_as_float(ob[8 * c + 4]) * mulb, __uint_as_float(ob[8 * c + 5]) * mulb),
+                          pack_bf16x2(__uint_as_float(ob[8 * c + 6]) * mulb, __uint_as_float(ob[8 * c + 7]) * mulb)));
+    }
     fence_proxy_async_smem();
     named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
     if (threadIdx.x == 0) {
       if (MODE == MODE_DQ) {
         tma_store_4d(&tmDQKV, smem + AB_OFF_P, 0, h, t0, b);
+        if (RB) tma_store_4d(&tmDQKVb, smem + AB_OFF_OUTB, 64, h, t0, b);
       } else {
         tma_store_4d(&tmDQKV, smem + AB_OFF_P, 0, H + h, t0, b);
         tma_store_4d(&tmDQKV, smem + AB_OFF_P + AB_TILE, 0, 2 * H + h, t0, b);
+        if (RB) {
+          tma_store_4d(&tmDQKVb, smem + AB_OFF_OUTB, 64, H + h, t0, b);
+          tma_store_4d(&tmDQKVb, smem + AB_OFF_OUTB + AB_BT, 64, 2 * H + h, t0, b);
+        }
       }
       tma_store_commit();
       tma_store_wait_all<0>();
@@ -292,37 +381,59 @@ using namespace ovk;
 extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                  float* delta, int B, int L, int H, int hd, float scale, void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
-  if (hd != AB_HD) return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (this build: 64)", hd);
+  if (hd < 64 || hd > 80 || (hd % 8))
+    return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (64, 72 or 80)", hd);
+  const bool ext = hd > AB_HD;
   if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention_bwd: B and H must be <= 65535");
   if (!lse || !delta) return set_error(OVK_ERR_SHAPE, "attention_bwd: lse and delta buffers are required");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  CUtensorMap tmQKV, tmDQKV, tmO, tmDO;
+  CUtensorMap tmQKV, tmDQKV, tmO, tmDO, tmQKVb, tmDQKVb, tmOb, tmDOb;
   int rc;
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)(3 * H), (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)3 * H * hd * 2, (uint64_t)L * 3 * H * hd * 2};
-    const uint32_t box[4] = {(uint32_t)hd, 1, AB_T, 1};
+    const uint32_t box[4] = {AB_HD, 1, AB_T, 1};
+    const uint32_t boxb[4] = {16, 1, AB_T, 1};
     if ((rc = make_tmap_nd_bf16(&tmQKV, qkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_tmap_nd_bf16(&tmDQKV, dqkv, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmQKVb, qkv, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmDQKVb, dqkv, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)H * hd * 2, (uint64_t)L * H * hd * 2};
-    const uint32_t box[4] = {(uint32_t)hd, 1, AB_T, 1};
+    const uint32_t box[4] = {AB_HD, 1, AB_T, 1};
+    const uint32_t boxb[4] = {16, 1, AB_T, 1};
     if ((rc = make_tmap_nd_bf16(&tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_tmap_nd_bf16(&tmDO, dout, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmOb, out, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+    if ((rc = make_tmap_nd_bf16(&tmDOb, dout, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((L + AB_T - 1) / AB_T, H, B);
-  attention_bwd_kernel<MODE_DQ><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, lse, delta, L, H, scale);
-  if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
-  attention_bwd_kernel<MODE_DKV><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, lse, delta, L, H, scale);
+  if (ext) {
+    attention_bwd_kernel<MODE_DQ, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
+                                                                                 tmDQKVb, lse, delta, L, H, scale);
+    if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
+    attention_bwd_kernel<MODE_DKV, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
+                                                                                  tmDQKVb, lse, delta, L, H, scale);
+  } else {
+    attention_bwd_kernel<MODE_DQ, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
+                                                                             tmDQKVb, lse, delta, L, H, scale);
+    if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
+    attention_bwd_kernel<MODE_DKV, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
+                                                                              tmDQKVb, lse, delta, L, H, scale);
+  }
   return check_launch("attention_bwd_kernel<dKdV>");
 }

@@ -21,6 +21,10 @@ CONFIGS = {
                               pool_type="last", act_kwargs={"approximate": "tanh"})),
     "mini-stock": dict(embed_dim=64, vision=dict(image_size=56, patch_size=14, width=128, layers=2, head_width=64, **STOCK_FLAGS),
                        text=dict(context_length=8, vocab_size=64, width=64, heads=1, layers=2, pool_type="last")),
+    # H/14-style head width (80) at toy size: 2 heads x 80
+    "mini-h80": dict(embed_dim=64, vision=dict(image_size=56, patch_size=14, width=160, layers=2, head_width=80, **OPENVISION_FLAGS),
+                     text=dict(context_length=8, vocab_size=64, width=64, heads=1, layers=2, no_causal_mask=True,
+                               pool_type="last", act_kwargs={"approximate": "tanh"})),
     "Ti16-160": dict(embed_dim=192, vision=dict(image_size=160, patch_size=16, width=192, layers=12, head_width=64, **OPENVISION_FLAGS),
                      text=dict(context_length=80, vocab_size=32000, width=192, heads=3, layers=12, no_causal_mask=True,
                                pool_type="last", act_kwargs={"approximate": "tanh"})),

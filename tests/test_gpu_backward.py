@@ -59,6 +59,51 @@ def test_attention_bwd(ops, B, L, H):
         assert_grad(g[:, :, i], r[:, :, i], f"attention d{name} B{B} L{L} H{H}", 3e-2)
 
 
+@pytest.mark.parametrize("hd", [72, 80])
+@pytest.mark.parametrize("B,L,H", [(2, 257, 2), (1, 101, 3), (1, 577, 1), (2, 130, 1)])
+def test_attention_bwd_wide_heads(ops, hd, B, L, H):
+    qkv = rnd(B * L, 3 * H * hd, seed=L + hd).bfloat16()
+    dout = rnd(B * L, H * hd, seed=L + hd + 1).bfloat16()
+    qc = qkv.cuda()
+    out, lse = ops.attention(qc, B, L, H, hd, save_lse=True)
+    dqkv = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), -1)
+    (p @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd).backward(dout.float())
+    g = dqkv.float().cpu().view(B, L, 3, H, hd)
+    r = qf.grad.view(B, L, 3, H, hd)
+    for i, name in enumerate("qkv"):
+        assert_grad(g[:, :, i], r[:, :, i], f"attention hd{hd} d{name} B{B} L{L} H{H}", 3e-2)
+
+
+def test_h14_style_tower_forward_backward_vs_oracle():
+    """head width 80 (H/14, BASELINE configs[4]) end to end at toy size: embeddings and image / parameter gradients
+    against autograd of the CPU oracle (no golden fixture for this config: the oracle is pinned on the others)."""
+    cfg_name, batch = "mini-h80", 3
+    cfg = synth.CONFIGS[cfg_name]
+    sd = synth.make_state_dict(cfg_name, 0)
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train()
+    images = synth.make_images(cfg_name, batch, 0).cuda().requires_grad_(True)
+    gy = rnd(batch, cfg["embed_dim"], seed=3)
+    out = m.encode_image(images, normalize=True)
+    out.backward(gy.cuda())
+    sdf = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xf = synth.make_images(cfg_name, batch, 0).requires_grad_(True)
+    ref = O.l2_normalize(O.vision_transformer(xf, sdf, synth.vision_heads(cfg_name)))
+    ref.backward(gy)
+    got = out.detach().float().cpu()
+    assert (got - ref.detach()).abs().max() <= 2e-2
+    assert torch.nn.functional.cosine_similarity(got, ref.detach(), dim=-1).min() >= 0.9995
+    assert_grad(images.grad, xf.grad, "d images (hd 80)", 6e-2)
+    for name in ("visual.conv1.weight", "visual.transformer.resblocks.0.attn.in_proj_weight",
+                 "visual.transformer.resblocks.1.attn.out_proj.weight", "visual.transformer.resblocks.1.mlp.c_fc.weight"):
+        p = dict(m.named_parameters())[name]
+        assert_grad(p.grad, sdf[name].grad, name, 6e-2)
+
+
 def test_small_backward_kernels(ops):
     # colsum
     x = rnd(1000, 776, seed=0).bfloat16()

@@ -13,7 +13,7 @@ v.set_grad_checkpointing(ckpt)
 s = cfg["vision"]["image_size"]
 images = torch.randn(batch, 3, s, s, device="cuda")
 gy = torch.randn(batch, cfg["embed_dim"], device="cuda")
-flops = {"L14-224": 162.03e9, "B16-384": 110.97e9, "Ti16-160": 1.2e9}.get(cfg_name, 0) * batch
+flops = {"L14-224": 162.03e9, "B16-384": 110.97e9, "Ti16-160": 1.2e9, "H14-224": 334.59e9}.get(cfg_name, 0) * batch
 def ev(fn, iters=3):
     fn(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
