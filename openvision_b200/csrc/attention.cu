@@ -19,24 +19,29 @@ constexpr int ATT_HD = 64;
 constexpr int ATT_SM_WARPS = 8;    // softmax warps: warp w owns TMEM lane quadrant w % 4 and key columns [64*(w/4), +64)
 constexpr int ATT_THREADS = 32 * (ATT_SM_WARPS + 2);  // + warp 8 TMA producer, warp 9 MMA issuer / TMEM owner
 constexpr int ATT_TILE_BYTES = 128 * 128;  // [128 rows x 64 bf16]
-constexpr int ATT_OFF_Q = 0;
-constexpr int ATT_OFF_K = ATT_OFF_Q + ATT_TILE_BYTES;
-constexpr int ATT_OFF_V = ATT_OFF_K + 2 * ATT_TILE_BYTES;
-constexpr int ATT_OFF_P = ATT_OFF_V + 2 * ATT_TILE_BYTES;
-constexpr int ATT_OFF_XCHG = ATT_OFF_P + 2 * ATT_TILE_BYTES;   // bf16 [2][128]: per-row maxima of the two column halves
-constexpr int ATT_OFF_TAIL = ATT_OFF_XCHG + 512;   // remainder key row (128 B) + its value row, double-buffered (2 x 128 B)
-constexpr int ATT_OFF_BAR = ATT_OFF_TAIL + 384;
 constexpr int ATT_NUM_BARS = 14;
-constexpr int ATT_SMEM_BYTES = ATT_OFF_BAR + ATT_NUM_BARS * 8 + 16;
-// Head widths 64 < hd <= 80 (H/14: 80, So400m/14: 72): the extra RB = 16 dims ride along as a second, narrow operand
+constexpr int ATT_BT = 128 * 32;   // 4 KB narrow tile (head dims 64..79), SWIZZLE_32B
+// Shared-memory layout.  hd = 64 (RB = 0): K / V double-buffered, 113 KB -> two CTAs per SM.
+// Head widths 64 < hd <= 80 (RB = 16; H/14: 80, So400m/14: 72): the extra dims ride along as a second, narrow operand
 // block: [128 rows x 32 B] tiles with 32-byte swizzle (TMA zero-fills dims >= hd), one more k-step in S = Q K^T and a
-// second N = 16 accumulator for P V.  These tiles sit after the hd = 64 layout (then only one CTA fits per SM).
-constexpr int ATT_BT = 128 * 32;                                   // 4 KB narrow tile
-constexpr int ATT_OFF_QB = (ATT_SMEM_BYTES + 1023) / 1024 * 1024;
-constexpr int ATT_OFF_KB = ATT_OFF_QB + ATT_BT;                    // x2
-constexpr int ATT_OFF_VB = ATT_OFF_KB + 2 * ATT_BT;                // x2
-constexpr int ATT_OFF_OB = ATT_OFF_VB + 2 * ATT_BT;                // output staging
-constexpr int ATT_SMEM_BYTES_RB = ATT_OFF_OB + ATT_BT;
+// second N = 16 accumulator for P V; K / V are single-buffered there so that two CTAs still fit per SM (98 KB).
+template <int RB>
+struct AttL {
+  static constexpr int NS = RB ? 1 : 2;   // K / V ring depth
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + ATT_TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + NS * ATT_TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + NS * ATT_TILE_BYTES;
+  static constexpr int OFF_XCHG = OFF_P + 2 * ATT_TILE_BYTES;   // bf16 [2][128]: per-row maxima of the two column halves
+  static constexpr int OFF_TAIL = OFF_XCHG + 512;   // remainder key row (128 B) + its value row, double-buffered (2 x 128 B)
+  static constexpr int OFF_BAR = OFF_TAIL + 384;
+  static constexpr int BASE_BYTES = OFF_BAR + ATT_NUM_BARS * 8 + 16;
+  static constexpr int OFF_QB = (BASE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int OFF_KB = OFF_QB + ATT_BT;
+  static constexpr int OFF_VB = OFF_KB + NS * ATT_BT;
+  static constexpr int OFF_OB = OFF_VB + NS * ATT_BT;   // output staging
+  static constexpr int SMEM_BYTES = RB ? OFF_OB + ATT_BT : BASE_BYTES;
+};
 constexpr uint32_t ATT_TMEM_OB = 192;                              // 16 columns after O
 constexpr uint32_t UMMA_SW32 = 6;
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) { return umma_desc(saddr, 16, 256, UMMA_SW32); }
@@ -59,16 +64,18 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   // PERSISTENT: each CTA walks work items (query tile, head, image) with stride gridDim.x, keeping its TMEM allocation,
   // barriers and the K/V TMA ring alive across items, so the next item's Q/K/V loads run under the current item's
   // softmax.  Query rows [0, nq * 128) are handled here; a short remainder of rows goes to attention_tail_kernel.
+  using LL = AttL<RB>;
+  constexpr int NS = LL::NS;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  uint8_t* sQ = smem + ATT_OFF_Q;
-  uint8_t* sK = smem + ATT_OFF_K;
-  uint8_t* sV = smem + ATT_OFF_V;
-  uint8_t* sP = smem + ATT_OFF_P;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_OFF_BAR);
+  uint8_t* sQ = smem + LL::OFF_Q;
+  uint8_t* sK = smem + LL::OFF_K;
+  uint8_t* sV = smem + LL::OFF_V;
+  uint8_t* sP = smem + LL::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LL::OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;   // [2]
   uint64_t* v_full = bars + 3;   // [2]
@@ -79,7 +86,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* pv_done = bars + 11;
   uint64_t* q_empty = bars + 12;
   uint64_t* o_free = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ATT_OFF_BAR + ATT_NUM_BARS * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LL::OFF_BAR + ATT_NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -120,22 +127,22 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         mbar_wait(q_empty, (n & 1) ^ 1, 9);
         mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0) + (RB ? ATT_BT : 0));
         tma_load_4d(sQ, &tmQKV, q_full, 0, h, qt * ATT_BQ, b);
-        if (RB) tma_load_4d(smem + ATT_OFF_QB, &tmQKVb, q_full, 64, h, qt * ATT_BQ, b);
+        if (RB) tma_load_4d(smem + LL::OFF_QB, &tmQKVb, q_full, 64, h, qt * ATT_BQ, b);
         if (ntail > 0) {  // remainder key row and its value row (1 x 128 B each, unswizzled)
-          tma_load_4d(smem + ATT_OFF_TAIL, &tmTail, q_full, 0, H + h, Lm, b);
-          tma_load_4d(smem + ATT_OFF_TAIL + 128 + (n & 1) * 128, &tmTail, q_full, 0, 2 * H + h, Lm, b);
+          tma_load_4d(smem + LL::OFF_TAIL, &tmTail, q_full, 0, H + h, Lm, b);
+          tma_load_4d(smem + LL::OFF_TAIL + 128 + (n & 1) * 128, &tmTail, q_full, 0, 2 * H + h, Lm, b);
         }
         for (int j = 0; j < nkv; ++j, ++g) {
-          const int s = g & 1;
-          const uint32_t ph = (g >> 1) & 1;
+          const int s = g % NS;
+          const uint32_t ph = (g / NS) & 1;
           mbar_wait(&k_empty[s], ph ^ 1, 10);
           mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES + (RB ? ATT_BT : 0));
           tma_load_4d(sK + s * ATT_TILE_BYTES, &tmQKV, &k_full[s], 0, H + h, j * ATT_BKV, b);
-          if (RB) tma_load_4d(smem + ATT_OFF_KB + s * ATT_BT, &tmQKVb, &k_full[s], 64, H + h, j * ATT_BKV, b);
+          if (RB) tma_load_4d(smem + LL::OFF_KB + s * ATT_BT, &tmQKVb, &k_full[s], 64, H + h, j * ATT_BKV, b);
           mbar_wait(&v_empty[s], ph ^ 1, 11);
           mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES + (RB ? ATT_BT : 0));
           tma_load_4d(sV + s * ATT_TILE_BYTES, &tmQKV, &v_full[s], 0, 2 * H + h, j * ATT_BKV, b);
-          if (RB) tma_load_4d(smem + ATT_OFF_VB + s * ATT_BT, &tmQKVb, &v_full[s], 64, 2 * H + h, j * ATT_BKV, b);
+          if (RB) tma_load_4d(smem + LL::OFF_VB + s * ATT_BT, &tmQKVb, &v_full[s], 64, 2 * H + h, j * ATT_BKV, b);
         }
       }
     }
@@ -148,8 +155,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
         mbar_wait(q_full, n & 1, 12);
         for (int j = 0; j < nkv; ++j, ++g) {
-          const int s = g & 1;
-          const uint32_t ph = (g >> 1) & 1;
+          const int s = g % NS;
+          const uint32_t ph = (g / NS) & 1;
           const int valid = min(ATT_BKV, Lm - j * ATT_BKV);
           const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
           const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
@@ -164,8 +171,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                          umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
           }
           if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
-            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + ATT_OFF_QB)),
-                         umma_desc_sw32(smem_u32(smem + ATT_OFF_KB + s * ATT_BT)), idesc_s, 1);
+            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + LL::OFF_QB)),
+                         umma_desc_sw32(smem_u32(smem + LL::OFF_KB + s * ATT_BT)), idesc_s, 1);
           umma_commit(&k_empty[s]);
           umma_commit(s_full);
           if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
@@ -184,7 +191,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           }
           if (RB) {   // output dims 64 .. 64 + RB: N = 16 accumulator, V_b consumed MN-major from its 32-byte rows
             constexpr uint32_t idesc_pvb = umma_idesc_bf16(ATT_BQ, 16, 0, 1);
-            const uint32_t vb_addr = smem_u32(smem + ATT_OFF_VB + s * ATT_BT);
+            const uint32_t vb_addr = smem_u32(smem + LL::OFF_VB + s * ATT_BT);
             for (int kk = 0; kk < ksteps; ++kk) {
               const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
               umma_bf16_ss(tmem_base + ATT_TMEM_OB, umma_desc_kmajor_sw128(a), umma_desc_sw32(vb_addr + kk * 512), idesc_pvb,
@@ -208,7 +215,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int r = quad * 32 + lane;  // row in tile = TMEM lane
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t p_base = smem_u32(sP) + half * ATT_TILE_BYTES;
-    const uint32_t xchg = smem_u32(smem + ATT_OFF_XCHG);
+    const uint32_t xchg = smem_u32(smem + LL::OFF_XCHG);
     constexpr uint32_t SMT = 32 * ATT_SM_WARPS;
     int g = 0, n = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
@@ -225,7 +232,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       float s_tail = 0.f;
       if (ntail > 0) {
         mbar_wait(q_full, n & 1, 19);
-        const uint32_t kt = smem_u32(smem + ATT_OFF_TAIL);
+        const uint32_t kt = smem_u32(smem + LL::OFF_TAIL);
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -349,7 +356,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       tc_fence_before();
       mbar_arrive(o_free);  // the accumulator may be overwritten by the next item's first P V
       if (ntail > 0) {      // fold the remainder key in: one more online-softmax step, entirely in registers
-        const uint32_t vt = smem_u32(smem + ATT_OFF_TAIL + 128 + (n & 1) * 128) + 64 * half;
+        const uint32_t vt = smem_u32(smem + LL::OFF_TAIL + 128 + (n & 1) * 128) + 64 * half;
         const float m_fin = fmaxf(m_ref, s_tail);
         const float a = fast_exp2(m_ref - m_fin);
         const float pt = fast_exp2(s_tail - m_fin);
@@ -384,7 +391,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         lse_out[(static_cast<long long>(b) * H + h) * L + q0 + r] = (m_ref + log2f(l_tot)) * 0.69314718055994531f;
       }
       if (RB && half == 0) {
-        const uint32_t obs = smem_u32(smem + ATT_OFF_OB);
+        const uint32_t obs = smem_u32(smem + LL::OFF_OB);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           sts128(obs + sw32_offset(r, c),
@@ -397,7 +404,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       named_bar_sync(1, SMT);
       if (threadIdx.x == 0) {
         tma_store_4d(&tmO, sP, 0, h, q0, b);
-        if (RB) tma_store_4d(&tmOb, smem + ATT_OFF_OB, 64, h, q0, b);
+        if (RB) tma_store_4d(&tmOb, smem + LL::OFF_OB, 64, h, q0, b);
         tma_store_commit();
       }
     }
@@ -528,9 +535,9 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttL<0>::SMEM_BYTES);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_BYTES_RB);
+      e = cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttL<16>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -541,13 +548,13 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   const int nq = (l_main + ATT_BQ - 1) / ATT_BQ;
   const long long items = static_cast<long long>(nq) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
-  const int per_sm = ext ? 1 : 2;   // the extended layout needs 137 KB of shared memory
+  const int per_sm = 2;
   const int grid = static_cast<int>(items < (long long)per_sm * num_sms() ? items : (long long)per_sm * num_sms());
   if (ext)
-    attention_fwd_kernel<16><<<grid, ATT_THREADS, ATT_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+    attention_fwd_kernel<16><<<grid, ATT_THREADS, AttL<16>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
                                                                           static_cast<int>(items), scale * 1.4426950408889634f);
   else
-    attention_fwd_kernel<0><<<grid, ATT_THREADS, ATT_SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+    attention_fwd_kernel<0><<<grid, ATT_THREADS, AttL<0>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
                                                                       static_cast<int>(items), scale * 1.4426950408889634f);
   if ((rc = check_launch("attention_fwd_kernel"))) return rc;
   if (tail) {

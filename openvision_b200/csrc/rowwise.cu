@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
                                                             float* __restrict__ rstd_out, int rows, int D, float eps) {
   // one warp owns LN_RPW consecutive rows and issues all their loads before touching any of them (more bytes in
   // flight per SM: the kernel is pure HBM streaming)
-  constexpr int RPW = 2;
+  constexpr int RPW = MAXV >= 8 ? 1 : 2;   // wide rows (D > 1024) already keep 8 vectors per lane in flight
   const int warps_per_block = blockDim.x >> 5;
   const int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
@@ -380,7 +380,7 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   if ((D % 8) || (ldx % 8) || (ldy % 8)) return set_error(OVK_ERR_ALIGN, "layernorm: D, ldx, ldy must be multiples of 8");
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int rpb = 8 * 2;  // 8 warps x 2 rows
+  const int rpb = 8 * (D > 1024 ? 1 : 2);  // 8 warps x rows per warp (layernorm_fwd_kernel::RPW)
   const int grid = (rows + rpb - 1) / rpb;
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yp = reinterpret_cast<__nv_bfloat16*>(y);
