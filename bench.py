@@ -409,6 +409,85 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Extra workloads (BASELINE.json configs[2] / configs[4]; not the headline line): image tower fwd+bwd (+ contrastive
+    loss fwd+bwd against synthetic text embeddings) per step; with N > 1 ranks the loss runs its NCCL exchange and the
+    tower gradients are all-reduced (plain NCCL, flattened per dtype) inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    import openvision_b200 as ovb
+    from openvision_b200 import ops
+    from oracle import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    name = {"b16_384_train": "B16-384", "h14_train": "H14-224", "l14_train": "L14-224"}[args.workload]
+    cfg = synth.CONFIGS[name]
+    batch = args.batch if args.batch != 1024 or name != "B16-384" else 512
+    torch.manual_seed(0)
+    tower = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"]).cuda().train()
+    tower.set_grad_checkpointing(args.checkpoint)
+    side = cfg["vision"]["image_size"]
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    images = torch.randn(batch, 3, side, side, device="cuda", generator=g)
+    txt = torch.nn.functional.normalize(torch.randn(batch, cfg["embed_dim"], device="cuda", generator=g), dim=-1)
+    log_scale = torch.tensor(2.6592, device="cuda", requires_grad=True)
+    crit = ovb.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, rank=rank, world_size=world)
+    params = [p for p in tower.parameters() if p.requires_grad]
+
+    def step():
+        for p in params:
+            p.grad = None
+        feats = tower(images)
+        feats = ovb.model._normalize(feats)
+        loss = crit(feats, txt, log_scale.exp())
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return loss
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    n0 = ops.launch_count
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.reset_peak_memory_stats()
+    s.record()
+    for _ in range(args.steps):
+        loss = step()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    if rank == 0:
+        fl = {"B16-384": 110.97e9, "H14-224": 334.59e9, "L14-224": 162.03e9}[name]
+        per = ms / args.steps
+        line = {"metric": "image_tower_plus_clip_loss_train_step", "value": world * batch / per * 1e3, "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"OpenVision ViT-{name} image tower fwd+bwd + CLIP loss fwd+bwd"
+                                       f"{' + NCCL gradient all-reduce' if world > 1 else ''}",
+                           "batch_per_gpu": batch, "global_batch": batch * world, "activation_checkpointing": args.checkpoint,
+                           "text_features": "synthetic unit vectors (text tower not on this path)"},
+                "model_tflops_algorithmic": 3 * fl * batch / per / 1e9, "loss": float(loss.detach()),
+                "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30,
+                "gpu_launches": ops.launch_count - n0}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,9 +497,14 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step (BASELINE config: 1024)")
     ap.add_argument("--loss-batch", type=int, default=32768, help="global batch of the contrastive-loss leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="l14_fwd", choices=["l14_fwd", "b16_384_train", "h14_train", "l14_train"],
+                    help="l14_fwd = the headline benchmark (default); *_train = extra fwd+bwd(+loss) workloads")
+    ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per block (train workloads)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "l14_fwd":
+        run_train(args)
     else:
         run_ours(args)
 
