@@ -101,29 +101,38 @@ class _FusedClipLoss(torch.autograd.Function):
         n_all = txt_all.shape[0]
         w = loss_weights(float(grad_out), n, n_all, world_size, local_loss, gather_with_grad)
         d_scale = torch.zeros(1, dtype=torch.float32, device=img.device)
+        # The text-gradient partial dT = s G^T I_r is produced FIRST so that its reduce-scatter over NVLink (async NCCL)
+        # runs under the image-gradient GEMM dI = s G T.
+        def reduce_scatter_async(d_txt_part):
+            d_txt = torch.empty((n, d_txt_part.shape[1]), dtype=torch.float32, device=img.device)
+            return d_txt, dist.reduce_scatter_tensor(d_txt, d_txt_part, async_op=True)
+
+        work = None
         if world_size > 1 and local_loss and not gather_with_grad:
             # loss.py:52-61: no gradient through the gathered copies -> dI from the row terms only, dT from the column
             # terms only (not the gradient of the global objective; kept for surface parity)
-            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, w, 0.0, d_scale)
-            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)
             G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, 0.0, w, d_scale)
             d_txt_part = ops.gemm_tn(G, img, alpha=scale, out_dtype=torch.float32)
+            d_txt, work = reduce_scatter_async(d_txt_part)
+            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, w, 0.0, d_scale)
+            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)
         else:
             G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, w, w, d_scale)
-            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)            # dI = s G T
             d_txt_part = ops.gemm_tn(G, img, alpha=scale, out_dtype=torch.float32)           # dT = s G^T I
+            if world_size > 1:
+                d_txt, work = reduce_scatter_async(d_txt_part)
+            else:
+                d_txt = d_txt_part
+            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)            # dI = s G T
         del G
         if world_size > 1:
-            d_txt = torch.empty((n, d_txt_part.shape[1]), dtype=torch.float32, device=img.device)
-            dist.reduce_scatter_tensor(d_txt, d_txt_part)
+            work.wait()
             if not local_loss:
                 # every rank differentiates the GLOBAL objective w.r.t. the (replicated) temperature: sum the row-block
                 # shares (loss.py:111-113 computes the full N x N matrix on every rank instead)
                 dist.all_reduce(d_scale)
                 if gather_with_grad:
                     d_scale = d_scale / world_size
-        else:
-            d_txt = d_txt_part
         return d_img.to(dt_i), d_txt.to(dt_t), d_scale.reshape(()).to(dt_s), None, None, None, None
 
 
