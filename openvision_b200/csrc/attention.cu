@@ -261,8 +261,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_S + 64 * half + c, sv);
             tmem_ld_wait();
             if (c + 32 <= valid) {
+              float m4[4] = {mx, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+              for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(sv[i]));
+              mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
             } else if (c < valid) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = (c + i < valid) ? fmaxf(mx, __uint_as_float(sv[i])) : mx;
@@ -324,18 +326,34 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             uint32_t sv[32];
             tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_S + 64 * half + c, sv);
             tmem_ld_wait();
+            if (c + 32 <= valid) {   // full chunk (the common case): no per-element masking
+              float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int cc = 0; cc < 32; cc += 8) {
-              if (c + cc < nblk) {
+              for (int cc = 0; cc < 32; cc += 8) {
                 float pv[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float e = fast_exp2(fmaf(__uint_as_float(sv[cc + i]), scale_log2, -m_ref));
-                  pv[i] = (c + cc + i < valid) ? e : 0.f;
-                  rowsum += pv[i];
+                  pv[i] = fast_exp2(fmaf(__uint_as_float(sv[cc + i]), scale_log2, -m_ref));
+                  rs4[i & 3] += pv[i];
                 }
                 sts128(p_base + sw128_offset(r, (c + cc) >> 3),
                        make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
+              }
+              rowsum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < 32; cc += 8) {
+                if (c + cc < nblk) {
+                  float pv[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float e = fast_exp2(fmaf(__uint_as_float(sv[cc + i]), scale_log2, -m_ref));
+                    pv[i] = (c + cc + i < valid) ? e : 0.f;
+                    rowsum += pv[i];
+                  }
+                  sts128(p_base + sw128_offset(r, (c + cc) >> 3),
+                         make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
+                }
               }
             }
           }
