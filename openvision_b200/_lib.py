@@ -37,6 +37,10 @@ _PROTOTYPES = {
                               c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_gemm_bf16_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_gemm_bf16_ln": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_longlong, c_void_p,
+                                 c_longlong, c_void_p, c_int, c_void_p]),
+    "ovk_row_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),
     "ovk_gemm_bf16_nn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_gemm_bf16_tn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,

@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from typing import Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -334,10 +336,60 @@ def _block_packed(blk):
         w2=_w_bf16(pj, "w", pj.weight), c2=_v_f32(pj, "b", pj.bias) if pj.bias is not None else None)
 
 
-def _block_forward(x2, p, blk, B, L, inplace, save):
+def _ln_fold_enabled(D: int) -> bool:
+    """LayerNorm is folded into the QKV / fc1 GEMMs when the width fits the statistics epilogue (include/ovk.h,
+    ovk_gemm_bf16_ln); OVK_LN_FOLD=0 selects the stand-alone LayerNorm kernels (A/B measurements)."""
+    return D > 128 and D % 64 == 0 and os.environ.get("OVK_LN_FOLD", "1") != "0"
+
+
+def _ln_folded(owner, key, w, b, gamma, beta):
+    """(W . gamma as bf16 [N,K], c = rowsum of that, d = W beta + b), cached on the versions of all four parameters:
+    ln(x) W^T + b = rstd (x (W.gamma)^T - mu c) + d."""
+    cache = owner.__dict__.setdefault("_ovk_cache", {})
+    tag = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device) for t in (w, b, gamma, beta))
+    hit = cache.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    with torch.no_grad():
+        wf = w.detach().float()
+        wg = (wf * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        c = wg.float().sum(dim=1).contiguous()
+        d = wf @ beta.detach().float()
+        if b is not None:
+            d = d + b.detach().float()
+        d = d.contiguous()
+    cache[key] = (tag, (wg, c, d))
+    return wg, c, d
+
+
+def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
+    """-> (y, saved tensors or None, row statistics of y or None).  `stats` are the partial (sum, sum sq) of the rows of
+    x2 when the producer of x2 already had them (the previous block's last GEMM)."""
     H = blk.attn.num_heads
     hd = blk.attn.embed_dim // H
     act = blk._act_kind()
+    M, D = x2.shape
+    if _ln_fold_enabled(D) and blk.ln_1.eps > 0:
+        a_, fc = blk.attn, blk.mlp.c_fc
+        wq, cq, dq = _ln_folded(a_, "in_ln", a_.in_proj_weight, a_.in_proj_bias, blk.ln_1.weight, blk.ln_1.bias)
+        w1, cc1, dd1 = _ln_folded(fc, "w_ln", fc.weight, fc.bias, blk.ln_2.weight, blk.ln_2.bias)
+        if stats is None:
+            stats = ops.row_stats(x2)
+        parts = (D + 127) // 128
+        qkv = ops.gemm_ln(x2, wq, bias=dq, colsum=cq, row_stats=stats, eps=blk.ln_1.eps)
+        if save:
+            a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+        else:
+            a = ops.attention(qkv, B, L, H, hd)
+        st_mid = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
+        x_mid = ops.gemm_ln(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None, stats_out=st_mid)
+        u = torch.empty((M, w1.shape[0]), dtype=torch.bfloat16, device=x2.device) if save else None
+        f = ops.gemm_ln(x_mid, w1, bias=dd1, colsum=cc1, row_stats=st_mid, eps=blk.ln_2.eps, act=act, preact_out=u)
+        st_y = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
+        y = ops.gemm_ln(f, p["w2"], bias=p["c2"], residual=x_mid, out=None if save else x_mid, stats_out=st_y)
+        if save:   # LayerNorm statistics are recomputed in backward together with h1 / h2
+            return y, (x2, None, None, qkv, a, lse, x_mid, None, None, u, f), st_y
+        return y, None, st_y
     if save:
         h, mean1, rstd1 = ops.layernorm(x2, p["g1"], p["b1"], blk.ln_1.eps, save_stats=True)
     else:
@@ -353,23 +405,26 @@ def _block_forward(x2, p, blk, B, L, inplace, save):
         u = torch.empty((x2.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x2.device)
         f = ops.gemm(h, p["w1"], bias=p["c1"], act=act, preact_out=u)
         y = ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid)
-        return y, (x2, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f)
+        return y, (x2, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f), None
     h = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, out=h)
     f = ops.gemm(h, p["w1"], bias=p["c1"], act=act)
-    return ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid, out=x_mid), None
+    return ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid, out=x_mid), None, None
 
 
 class _Block(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, blk, B, L, *params):
+    def forward(ctx, x2, stats, blk, B, L, *params):
         p = _block_packed(blk)
-        y, saved = _block_forward(x2, p, blk, B, L, inplace=False, save=True)
+        y, saved, st_y = _block_forward(x2, p, blk, B, L, inplace=False, save=True, stats=stats)
         ctx.save_for_backward(*saved)
         ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params = blk, B, L, p, params
-        return y
+        if st_y is None:
+            return y, None
+        ctx.mark_non_differentiable(st_y)
+        return y, st_y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dstats=None):
         x_in, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f = ctx.saved_tensors
         blk, B, L, p, params = ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params
         (ln1_w, ln1_b, in_w, in_b, out_w, out_b, ln2_w, ln2_b, fc_w, fc_b, pj_w, pj_b) = params
@@ -377,13 +432,16 @@ class _Block(torch.autograd.Function):
         hd = blk.attn.embed_dim // H
         act = blk._act_kind()
         dy = _c(dy)
-        need_w = any(ctx.needs_input_grad[4:])
+        need_w = any(ctx.needs_input_grad[5:])
         # ---- MLP branch
         du = ops.gemm_nn(dy, p["w2"], preact=u, act=act)                                    # (dY W2) . act'(u)
         g_pj_w = ops.gemm_tn(dy, f, out_dtype=_grad_dtype(pj_w)) if need_w else None
         g_pj_b = ops.colsum(dy) if need_w and pj_b is not None else None
         del f, u
-        h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps) if need_w else None      # recomputed, not stored
+        if mean2 is None:   # LayerNorm was folded into the forward GEMMs: statistics come with the recomputed h2
+            h2, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True)
+        else:
+            h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps) if need_w else None   # recomputed, not stored
         dh = ops.gemm_nn(du, p["w1"])
         g_fc_w = ops.gemm_tn(du, h2, out_dtype=_grad_dtype(fc_w)) if need_w else None
         g_fc_b = ops.colsum(du) if need_w and fc_b is not None else None
@@ -396,7 +454,10 @@ class _Block(torch.autograd.Function):
         g_out_b = ops.colsum(dxm) if need_w and out_b is not None else None
         dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, hd)
         del da
-        h1 = ops.layernorm(x_in, p["g1"], p["b1"], blk.ln_1.eps) if need_w else None
+        if mean1 is None:
+            h1, mean1, rstd1 = ops.layernorm(x_in, p["g1"], p["b1"], blk.ln_1.eps, save_stats=True)
+        else:
+            h1 = ops.layernorm(x_in, p["g1"], p["b1"], blk.ln_1.eps) if need_w else None
         dh1 = ops.gemm_nn(dqkv, p["wqkv"])
         g_in_w = ops.gemm_tn(dqkv, h1, out_dtype=_grad_dtype(in_w)) if need_w else None
         g_in_b = ops.colsum(dqkv) if need_w and in_b is not None else None
@@ -407,14 +468,16 @@ class _Block(torch.autograd.Function):
                  _like_param(g_out_w, out_w), _like_param(g_out_b, out_b), _like_param(dg2, ln2_w),
                  _like_param(db2, ln2_b), _like_param(g_fc_w, fc_w), _like_param(g_fc_b, fc_b),
                  _like_param(g_pj_w, pj_w), _like_param(g_pj_b, pj_b))
-        return (dx, None, None, None) + grads
+        return (dx, None, None, None, None) + grads
 
 
-def block_fn(x2, blk, B, L, inplace):
-    """One ResidualAttentionBlock on a bf16 [B*L, D] residual stream: 7 kernels forward
-    (LN, QKV GEMM, attention, out-proj GEMM+residual, LN, fc1 GEMM+GELU, fc2 GEMM+residual)."""
+def block_fn(x2, blk, B, L, inplace, stats=None):
+    """One ResidualAttentionBlock on a bf16 [B*L, D] residual stream -> (y, row statistics of y or None).
+    5 kernels forward with LayerNorm folded into the GEMMs (QKV GEMM, attention, out-proj GEMM+residual, fc1 GEMM+GELU,
+    fc2 GEMM+residual; +1 row-statistics kernel in the first block), 7 with the stand-alone LayerNorm kernels.
+    `stats`: the statistics the previous block returned for x2, if any."""
     params = _block_params(blk)
     if _needs_grad(x2, *params):
-        return _Block.apply(x2, blk, B, L, *params)
-    y, _ = _block_forward(x2, _block_packed(blk), blk, B, L, inplace=inplace, save=False)
-    return y
+        return _Block.apply(x2, stats, blk, B, L, *params)
+    y, _, st_y = _block_forward(x2, _block_packed(blk), blk, B, L, inplace=inplace, save=False, stats=stats)
+    return y, st_y

@@ -275,16 +275,26 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_x32(tmem_base + t_lane + AB_TM_DP + col, dv);
         tmem_ld_wait();
         uint32_t pp[16], dd[16];
+        if (col + 32 <= valid_kv) {   // full chunk (the common case): no per-element masking
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
-          float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
-          p0 = (col + 2 * j < valid_kv) ? p0 : 0.f;
-          p1 = (col + 2 * j + 1 < valid_kv) ? p1 : 0.f;
-          const float d0 = (col + 2 * j < valid_kv) ? p0 * (__uint_as_float(dv[2 * j]) - dlt) : 0.f;
-          const float d1 = (col + 2 * j + 1 < valid_kv) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dlt) : 0.f;
-          pp[j] = pack_bf16x2(p0, p1);
-          dd[j] = pack_bf16x2(d0, d1);
+          for (int j = 0; j < 16; ++j) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
+            pp[j] = pack_bf16x2(p0, p1);
+            dd[j] = pack_bf16x2(p0 * (__uint_as_float(dv[2 * j]) - dlt), p1 * (__uint_as_float(dv[2 * j + 1]) - dlt));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
+            float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
+            p0 = (col + 2 * j < valid_kv) ? p0 : 0.f;
+            p1 = (col + 2 * j + 1 < valid_kv) ? p1 : 0.f;
+            const float d0 = (col + 2 * j < valid_kv) ? p0 * (__uint_as_float(dv[2 * j]) - dlt) : 0.f;
+            const float d1 = (col + 2 * j + 1 < valid_kv) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dlt) : 0.f;
+            pp[j] = pack_bf16x2(p0, p1);
+            dd[j] = pack_bf16x2(d0, d1);
+          }
         }
         const uint32_t chunk0 = c >> 3;  // 16-byte chunk inside the 64-column atom
 #pragma unroll

@@ -17,12 +17,19 @@ struct GemmEpi {
   float alpha;
   int flags;          // OVK_EPI_BIAS | OVK_EPI_RESIDUAL | act id | OVK_EPI_SAVE_PREACT
   ActCoef act;
+  // LayerNorm folded into the GEMM (FUSE kernels): y = rstd_i (acc - mu_i c_n) + d_n with B = W . gamma, c = rowsum(B),
+  // d = W beta + bias, (mu, rstd) from per-row (sum x, sum x^2) produced by the epilogue of the GEMM that wrote x.
+  const float* colsum;       // f32[N] or null
+  const float* row_stats_in; // f32[stats_parts_in][M][2] partial (sum, sum sq) of the A rows, or null
+  float* row_stats_out;      // f32[ceil(N/128)][M][2] partial (sum, sum sq) of the output rows, or null
+  int stats_parts_in;
+  float inv_k, ln_eps;
 };
 
 // EPI_LINEAR: C = alpha*acc + bias (+ R)                   R  = residual tile [M,N] bf16 (tmR), may alias C
 // EPI_ACT   : C = act(acc + bias), optionally D = acc+bias  D  = saved pre-activation (tmD) for the backward pass
 // EPI_DACT  : C = alpha*acc * act'(R)                       R  = saved pre-activation
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR, bool FUSE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -64,16 +71,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const GemmTileInfo ti = sched.tile(t, BN);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // bias tile -> smem (double-buffered by tile parity; the 256-thread barrier publishes it)
-      const uint32_t bias_s = bias_base + (it & 1) * (BN * 4);
+      // per-column epilogue vectors -> smem.  Lean kernels: the bias tile, double-buffered by tile parity (one barrier
+      // publishes it).  FUSE kernels: (d, c) pairs, single-buffered (a barrier on either side of the write).
+      const uint32_t bias_s = bias_base + (FUSE ? 0 : (it & 1) * (BN * 4));
+      if constexpr (FUSE) named_bar_sync(3, GEMM_EPI_THREADS);
       {
         const int j = threadIdx.x - 32 * GEMM_CTRL_WARPS;
         if (j < BN) {
           const int n = ti.n0 + j;
-          sts_f32(bias_s + j * 4, (has_bias && n < N) ? ep.bias[n] : 0.f);
+          const float bv = (has_bias && n < N) ? ep.bias[n] : 0.f;
+          if constexpr (FUSE) sts_f32x2(bias_s + j * 8, bv, (ep.colsum != nullptr && n < N) ? ep.colsum[n] : 0.f);
+          else sts_f32(bias_s + j * 4, bv);
         }
       }
       named_bar_sync(3, GEMM_EPI_THREADS);
+      // FUSE: this row's LayerNorm statistics -> multiplier of the accumulator and of the column sums
+      float a_mul = alpha, c_mul = 0.f, st1 = 0.f, st2 = 0.f;
+      if constexpr (FUSE) {
+        if (ep.row_stats_in != nullptr) {
+          const int row_s = ti.m0 + et;
+          float mu = 0.f, rstd = 0.f;
+          if (row_s < M) {
+            // partial sums (one slot per 128 source columns) combined in a fixed order: deterministic
+            const float2* sp = reinterpret_cast<const float2*>(ep.row_stats_in) + row_s;
+            float s1 = 0.f, s2 = 0.f;
+            for (int q = 0; q < ep.stats_parts_in; ++q) {
+              const float2 st = sp[static_cast<long long>(q) * M];
+              s1 += st.x;
+              s2 += st.y;
+            }
+            mu = s1 * ep.inv_k;
+            rstd = rsqrtf(fmaxf(s2 * ep.inv_k - mu * mu, 0.f) + ep.ln_eps);
+          }
+          a_mul = rstd;
+          c_mul = -mu * rstd;
+        }
+      }
       mbar_wait(&cx.tmem_full[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BN + grp * GROUP_COLS;
@@ -107,13 +140,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!live) continue;
         float x[CW];
+        if constexpr (FUSE) {
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) {
-          const float4 b = lds_f32x4(bias_s + (col_in_tile + 4 * j) * 4);
-          x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), alpha, b.x);
-          x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b.y);
-          x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b.z);
-          x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b.w);
+          for (int j = 0; j < CW / 2; ++j) {
+            const float4 b = lds_f32x4(bias_s + (col_in_tile + 2 * j) * 8);   // (d, c, d, c)
+            x[2 * j + 0] = fmaf(__uint_as_float(v[2 * j + 0]), a_mul, fmaf(c_mul, b.y, b.x));
+            x[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), a_mul, fmaf(c_mul, b.w, b.z));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 b = lds_f32x4(bias_s + (col_in_tile + 4 * j) * 4);
+            x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), alpha, b.x);
+            x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b.y);
+            x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b.z);
+            x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b.w);
+          }
         }
         if constexpr (EPI == EPI_ACT) {
           if (save_pre) {  // pre-activation out first (same staging buffer), then the activation
@@ -161,10 +203,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sts128(sbuf + sw128_offset(et, j), make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
                                                           __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3])));
         } else {
+          uint32_t w[CW / 2];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(sbuf + sw128_offset(et, j), make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                                          pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7])));
+          for (int j = 0; j < CW / 2; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+          if constexpr (FUSE) {
+            // row statistics of the tensor being written (for the NEXT LayerNorm), taken from the ROUNDED values so
+            // that they are exactly the statistics of what a later LayerNorm kernel would read back
+            if (ep.row_stats_out != nullptr) {
+              float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < CW / 2; ++j) {
+                const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+                p1[(2 * j) & 3] += lo;
+                p1[(2 * j + 1) & 3] += hi;
+                p2[(2 * j) & 3] = fmaf(lo, lo, p2[(2 * j) & 3]);
+                p2[(2 * j + 1) & 3] = fmaf(hi, hi, p2[(2 * j + 1) & 3]);
+              }
+              st1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+              st2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(sbuf + sw128_offset(et, j), make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, GEMM_GROUP_THREADS);
@@ -172,6 +232,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (reduce_out) tma_reduce_add_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
           else tma_store_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
           tma_store_commit();
+        }
+      }
+      if constexpr (FUSE) {
+        // one slot per (row, 128 output columns) = per epilogue group of a 256-wide tile: plain stores, no atomics
+        if (ep.row_stats_out != nullptr && ti.m0 + et < M && ti.n0 + grp * GROUP_COLS < N) {
+          const long long slot = (ti.n0 + grp * GROUP_COLS) >> 7;
+          reinterpret_cast<float2*>(ep.row_stats_out)[slot * M + ti.m0 + et] = make_float2(st1, st2);
         }
       }
     }
@@ -201,7 +268,7 @@ static bool pair_mode_enabled() {
   return v == 1;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR, bool FUSE = false>
 static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4, PAIR>;
   CUtensorMap tmA, tmB, tmC, tmR, tmD;
@@ -219,7 +286,7 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   tmD = tmC;
   if (g.R && (rc = make_tmap_2d_bf16(&tmR, g.R, g.N, g.M, g.ldr, 64, GEMM_BM))) return rc;
   if (g.D && (rc = make_tmap_2d_bf16(&tmD, g.D, g.N, g.M, g.ldd, 64, GEMM_BM))) return rc;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32, PAIR>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32, PAIR, FUSE>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
@@ -265,12 +332,12 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   return check_launch("gemm_bf16_kernel");
 }
 
-template <bool A_MN, bool B_MN, int EPI, bool OUT_F32>
+template <bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool FUSE = false>
 static int launch_gemm_bn(const GemmArgs& g, cudaStream_t s) {
-  if (g.N <= 128) return launch_gemm_t<128, A_MN, B_MN, EPI, OUT_F32, false>(g, s);
+  if (g.N <= 128) return launch_gemm_t<128, A_MN, B_MN, EPI, OUT_F32, false, FUSE>(g, s);
   // CTA pairs (256-row tiles) once there are enough rows to fill them; small problems stay on single CTAs
-  if (pair_mode_enabled() && g.M >= 512) return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, true>(g, s);
-  return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, false>(g, s);
+  if (pair_mode_enabled() && g.M >= 512) return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, true, FUSE>(g, s);
+  return launch_gemm_t<256, A_MN, B_MN, EPI, OUT_F32, false, FUSE>(g, s);
 }
 
 static int check_common(const GemmArgs& g, const char* who) {
@@ -349,4 +416,41 @@ extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, lon
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (c_is_f32) return launch_gemm_bn<true, true, EPI_LINEAR, true>(g, s);
   return launch_gemm_bn<true, true, EPI_LINEAR, false>(g, s);
+}
+
+
+extern "C" int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                int M, int N, int K, const float* bias, const float* colsum, const float* row_stats_in,
+                                int stats_parts_in, float ln_eps, const void* residual, long long ldr, void* preact, long long ldp,
+                                float* row_stats_out, int flags, void* stream) {
+  GemmArgs g{A, lda, false, B, ldb, false, C, ldc, false, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  const int act = flags & OVK_EPI_ACT_MASK;
+  if ((flags & OVK_EPI_RESIDUAL) && residual == nullptr) return set_error(OVK_ERR_SHAPE, "gemm_ln: residual flag without pointer");
+  if ((flags & OVK_EPI_BIAS) && bias == nullptr) return set_error(OVK_ERR_SHAPE, "gemm_ln: bias flag without pointer");
+  if ((flags & OVK_EPI_SAVE_PREACT) && (preact == nullptr || act == 0))
+    return set_error(OVK_ERR_SHAPE, "gemm_ln: SAVE_PREACT needs an activation and an output pointer");
+  if (act && (flags & OVK_EPI_RESIDUAL)) return set_error(OVK_ERR_SHAPE, "gemm_ln: activation + residual in one epilogue is not supported");
+  if ((row_stats_in == nullptr) != (colsum == nullptr))
+    return set_error(OVK_ERR_SHAPE, "gemm_ln: row_stats_in and colsum come together (LayerNorm folded into the GEMM)");
+  if (row_stats_in != nullptr && stats_parts_in < 1) return set_error(OVK_ERR_SHAPE, "gemm_ln: stats_parts_in must be >= 1");
+  if (row_stats_out != nullptr && ((N % 64) || N <= 128))
+    return set_error(OVK_ERR_SHAPE, "gemm_ln: row statistics output needs N %% 64 == 0 and N > 128");
+  if (row_stats_out != nullptr && act) return set_error(OVK_ERR_SHAPE, "gemm_ln: row statistics output is for the linear epilogue");
+  g.ep.bias = bias;
+  g.ep.alpha = 1.f;
+  g.ep.flags = flags;
+  g.ep.act = act_coef(act);
+  g.ep.colsum = colsum;
+  g.ep.row_stats_in = row_stats_in;
+  g.ep.row_stats_out = row_stats_out;
+  g.ep.stats_parts_in = stats_parts_in;
+  g.ep.inv_k = 1.f / static_cast<float>(K);
+  g.ep.ln_eps = ln_eps;
+  if (flags & OVK_EPI_RESIDUAL) g.R = residual, g.ldr = ldr;
+  if (flags & OVK_EPI_SAVE_PREACT) g.D = preact, g.ldd = ldp;
+  int rc = check_common(g, "gemm_ln");
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (act) return launch_gemm_bn<false, false, EPI_ACT, false, true>(g, s);
+  return launch_gemm_bn<false, false, EPI_LINEAR, false, true>(g, s);
 }

@@ -105,6 +105,32 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row statistics
+// (sum x, sum x^2) per row: the LayerNorm statistics in the form the LN-folding GEMM epilogue consumes
+// (ovk_gemm_bf16_ln).  Inside the tower they come for free from the epilogue of the GEMM that writes x; this kernel
+// seeds the first block.  One warp per row.
+__global__ void __launch_bounds__(256) row_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                        float* __restrict__ stats, int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+  float s1 = 0.f, s2 = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    unpack8(xr[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1 += f[j];
+      s2 = fmaf(f[j], f[j], s2);
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) *reinterpret_cast<float2*>(stats + 2 * static_cast<long long>(row)) = make_float2(s1, s2);
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm bwd
 // g = dy*gamma ; dx = rstd * (g - mean(g) - xhat * mean(g*xhat)) (+ dres) ; dgamma = sum_rows dy*xhat ; dbeta = sum_rows dy.
 // Two streaming kernels instead of one register-heavy one (which ran at a single block per SM):
@@ -389,6 +415,14 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   else if (D <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   return check_launch("layernorm_fwd_kernel");
+}
+
+extern "C" int ovk_row_stats(const void* x, long long ldx, float* stats, int rows, int D, void* stream) {
+  if (rows <= 0 || D <= 0) return set_error(OVK_ERR_SHAPE, "row_stats: empty input");
+  if ((D % 8) || (ldx % 8)) return set_error(OVK_ERR_ALIGN, "row_stats: D and ldx must be multiples of 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  row_stats_kernel<<<(rows + 7) / 8, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, stats, rows, D);
+  return check_launch("row_stats_kernel");
 }
 
 extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const float* gamma,

@@ -110,6 +110,67 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+            row_stats: Optional[torch.Tensor] = None, eps: float = 1e-6, residual: Optional[torch.Tensor] = None,
+            act: Optional[str] = None, out: Optional[torch.Tensor] = None, preact_out: Optional[torch.Tensor] = None,
+            stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GEMM with LayerNorm folded in and / or row statistics out (kernel: gemm_bf16_kernel<..., FUSE>):
+       out = act(rstd * (a @ w^T - mu * colsum) + bias) (+ residual); (mu, rstd) come from row_stats [P,M,2], partial
+       (sum, sum sq) of the rows of a.  stats_out [ceil(N/128),M,2] fp32 receives the same statistics of the output rows."""
+    _require(a, torch.bfloat16, "gemm_ln.a", 2)
+    _require(w, torch.bfloat16, "gemm_ln.w", 2)
+    M, K = a.shape
+    N, K2 = w.shape
+    if K2 != K:
+        raise OvkError(f"gemm_ln: inner dimensions differ ({K} vs {K2})")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    flags = _ACT[act]
+    if bias is not None:
+        _require(bias, torch.float32, "gemm_ln.bias", 1)
+        flags |= EPI_BIAS
+    if (row_stats is None) != (colsum is None):
+        raise OvkError("gemm_ln: row_stats and colsum come together")
+    parts = 0
+    if row_stats is not None:
+        _require(row_stats, torch.float32, "gemm_ln.row_stats", 3)
+        _require(colsum, torch.float32, "gemm_ln.colsum", 1)
+        if tuple(row_stats.shape[1:]) != (M, 2) or not row_stats.is_contiguous() or colsum.numel() != N:
+            raise OvkError("gemm_ln: row_stats must be contiguous [P, M, 2] and colsum [N]")
+        parts = row_stats.shape[0]
+    ldr = 0
+    if residual is not None:
+        _require(residual, torch.bfloat16, "gemm_ln.residual", 2)
+        flags |= EPI_RESIDUAL
+        ldr = residual.stride(0)
+    ldp = 0
+    if preact_out is not None:
+        _require(preact_out, torch.bfloat16, "gemm_ln.preact_out", 2)
+        flags |= EPI_SAVE_PREACT
+        ldp = preact_out.stride(0)
+    if stats_out is not None:
+        _require(stats_out, torch.float32, "gemm_ln.stats_out", 3)
+        if tuple(stats_out.shape) != ((N + 127) // 128, M, 2) or not stats_out.is_contiguous():
+            raise OvkError("gemm_ln: stats_out must be contiguous [ceil(N/128), M, 2]")
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_ln", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+                  _p(colsum), _p(row_stats), parts, float(eps), _p(residual), ldr, _p(preact_out), ldp, _p(stats_out), flags,
+                  _stream())
+    _count()
+    return out
+
+
+def row_stats(x: torch.Tensor) -> torch.Tensor:
+    """(sum, sum of squares) per row of x bf16 [rows, D] -> fp32 [1, rows, 2] (one partial slot). Kernel: row_stats_kernel."""
+    _require(x, torch.bfloat16, "row_stats.x", 2)
+    rows, D = x.shape
+    st = torch.empty((1, rows, 2), dtype=torch.float32, device=x.device)
+    with _timed("layernorm", 2.0 * rows * D):
+        _lib.call("ovk_row_stats", _p(x), x.stride(0), _p(st), rows, D, _stream())
+    _count()
+    return st
+
+
 def gemm_nn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torch.bfloat16,
             preact: Optional[torch.Tensor] = None, act: Optional[str] = None,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:

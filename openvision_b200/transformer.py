@@ -256,10 +256,11 @@ class ResidualAttentionBlock(nn.Module):
     def attention(self, q_x, k_x=None, v_x=None, attn_mask=None):
         return self.attn(q_x, k_x, v_x, need_weights=False, attn_mask=attn_mask)[0]
 
-    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, inplace: bool) -> torch.Tensor:
-        """Fast path on a bf16 [B*L, D] residual stream. When `inplace`, x2 is updated in place (it is ours)."""
+    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, inplace: bool, stats: Optional[torch.Tensor] = None):
+        """Fast path on a bf16 [B*L, D] residual stream -> (y, row statistics of y or None). When `inplace`, x2 is
+        updated in place (it is ours). `stats` are the LayerNorm statistics of x2 handed over by the previous block."""
         from .autograd import block_fn
-        return block_fn(x2, self, B, L, inplace)
+        return block_fn(x2, self, B, L, inplace, stats)
 
     def forward(self, q_x: torch.Tensor, k_x=None, v_x=None, attn_mask=None):
         if k_x is not None or v_x is not None:
@@ -269,7 +270,7 @@ class ResidualAttentionBlock(nn.Module):
                            "OpenVision text towers use no_causal_mask=True")
         B, L, D = q_x.shape
         if self._fusable():
-            y = self.forward_tokens(_as_bf16_2d(q_x), B, L, inplace=False)
+            y, _ = self.forward_tokens(_as_bf16_2d(q_x), B, L, inplace=False)
             return y.reshape(B, L, D).to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
         # module-by-module path (hooks on nn.GELU, LayerScale): every submodule still runs on libovk kernels
         if isinstance(self.ls_1, nn.Identity) and isinstance(self.ls_2, nn.Identity):
@@ -319,16 +320,17 @@ class Transformer(nn.Module):
 
     def forward_tokens(self, x2: torch.Tensor, B: int, L: int, owned: bool) -> torch.Tensor:
         """bf16 [B*L, D] -> bf16 [B*L, D]; `owned` says whether x2 may be overwritten."""
+        stats = None   # LayerNorm statistics of x2, produced by the epilogue of the GEMM that wrote it
         for r in self.resblocks:
             if r._fusable():
                 if self.grad_checkpointing and torch.is_grad_enabled() and x2.requires_grad:
-                    x2 = checkpoint(r.forward_tokens, x2, B, L, False, use_reentrant=False)
+                    x2, stats = checkpoint(r.forward_tokens, x2, B, L, False, stats, use_reentrant=False)
                 else:
-                    x2 = r.forward_tokens(x2, B, L, inplace=owned and not torch.is_grad_enabled())
+                    x2, stats = r.forward_tokens(x2, B, L, inplace=owned and not torch.is_grad_enabled(), stats=stats)
                 owned = True
             else:
                 x2 = _as_bf16_2d(r(x2.reshape(B, L, -1)))
-                owned = True
+                owned, stats = True, None
         return x2
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None):

@@ -265,3 +265,70 @@ def test_attention_fwd_wide_heads(ops, hd, B, L, H):
     ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
     assert_close(out, ref, 2e-2, f"attention hd{hd} B{B} L{L} H{H}")
     assert_close(lse, lse_ref, 1e-3, "attention lse")
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm folded into GEMMs
+LN_GEMM_CASES = [
+    # M, D (LayerNorm width = K of the consumer), N, act, pair of notes
+    (808, 192, 576, None), (808, 192, 768, "gelu"),          # Ti/16: 1.5 statistics slots, row tail
+    (1024, 1024, 3072, None), (1024, 1024, 4096, "gelu"),    # L/14 QKV and fc1 (CTA pairs)
+    (300, 1280, 1280, "gelu_tanh"), (130, 1152, 384, None),  # H/14 and So400m widths, single-CTA tiles
+]
+
+
+@pytest.mark.parametrize("M,D,N,act", LN_GEMM_CASES)
+def test_gemm_ln_fold_matches_layernorm_then_linear(ops, M, D, N, act):
+    """Producer GEMM (+bias +residual) emits the row statistics of what it writes; the consumer GEMM reads the
+    un-normalised rows and applies ln(x) W^T + b through rstd (x (W.gamma)^T - mu c) + d.  Checked against the oracle's
+    LayerNorm (oc/transformer.py:24-30) followed by F.linear (+ activation)."""
+    eps = 1e-6
+    # producer: x = a w0^T + b0 + r, with a per-row offset and scale so that mean and variance differ row to row
+    a = rnd(M, 256, seed=1, scale=0.5).bfloat16()
+    w0 = rnd(D, 256, seed=2, scale=0.1).bfloat16()
+    b0 = rnd(D, seed=3)
+    r = (rnd(M, D, seed=4) * (0.25 + 4 * torch.rand(M, 1, generator=torch.Generator().manual_seed(5)))
+         + 3 * rnd(M, 1, seed=6)).bfloat16()
+    parts = (D + 127) // 128
+    st = torch.full((parts, M, 2), float("nan"), device="cuda")
+    x = ops.gemm_ln(a.cuda(), w0.cuda(), bias=b0.cuda(), residual=r.cuda(), stats_out=st)
+    x_ref = a.float() @ w0.float().t() + b0 + r.float()
+    assert_close(x, x_ref, 1e-2, "producer output")
+    xs = x.float()
+    s = st.sum(0)
+    assert_close(s[:, 0], xs.sum(1), 2e-5 * math.sqrt(D), "row sums")        # of the ROUNDED values it wrote
+    assert_close(s[:, 1], (xs * xs).sum(1), 1e-5, "row sums of squares")
+    st1 = ops.row_stats(x)
+    assert tuple(st1.shape) == (1, M, 2)
+    assert_close(st1[0, :, 0], xs.sum(1), 2e-5 * math.sqrt(D), "row_stats sums")
+    assert_close(st1[0, :, 1], (xs * xs).sum(1), 1e-5, "row_stats sums of squares")
+    # consumer
+    gamma = 1 + 0.2 * rnd(D, seed=7)
+    beta = 0.1 * rnd(D, seed=8)
+    w = rnd(N, D, seed=9, scale=0.05)
+    b = rnd(N, seed=10)
+    wg = (w * gamma[None, :]).bfloat16()
+    c = wg.float().sum(1)
+    d = w @ beta + b
+    pre = torch.empty((M, N), dtype=torch.bfloat16, device="cuda") if act else None
+    for stats in (st, st1):
+        y = ops.gemm_ln(x, wg.cuda(), bias=d.cuda(), colsum=c.cuda(), row_stats=stats, eps=eps, act=act, preact_out=pre)
+        h = O.layer_norm(xs.cpu(), gamma, beta, eps)
+        ref = h @ w.t() + b
+        if act:
+            assert_close(pre, ref, 1e-2, "saved pre-activation")
+            ref = O.gelu(ref, {"gelu": "erf", "gelu_tanh": "tanh"}[act])
+        assert_close(y, ref, 1e-2, f"ln-folded gemm {M}x{N}x{D}")
+    # deterministic: same bits on a second run (plain stores in fixed slots, no atomics)
+    st2 = torch.empty_like(st)
+    x2 = ops.gemm_ln(a.cuda(), w0.cuda(), bias=b0.cuda(), residual=r.cuda(), stats_out=st2)
+    assert torch.equal(x2, x) and torch.equal(st2, st)
+
+
+def test_gemm_ln_rejects_bad_arguments(ops):
+    a = torch.zeros(128, 256, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(128, 256, dtype=torch.bfloat16, device="cuda")
+    from openvision_b200._lib import OvkError
+    with pytest.raises(OvkError):   # statistics need N > 128
+        ops.gemm_ln(a, w, stats_out=torch.zeros(1, 128, 2, device="cuda"))
+    with pytest.raises(OvkError):   # colsum without row statistics
+        ops.gemm_ln(a, w, colsum=torch.zeros(128, device="cuda"))
