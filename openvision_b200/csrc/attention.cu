@@ -32,9 +32,14 @@ struct AttL {
   static constexpr int OFF_K = OFF_Q + ATT_TILE_BYTES;
   static constexpr int OFF_V = OFF_K + NS * ATT_TILE_BYTES;
   static constexpr int OFF_P = OFF_V + NS * ATT_TILE_BYTES;
-  static constexpr int OFF_XCHG = OFF_P + 2 * ATT_TILE_BYTES;   // bf16 [2][128]: per-row maxima of the two column halves
-  static constexpr int OFF_TAIL = OFF_XCHG + 512;   // remainder key row (128 B) + its value row, double-buffered (2 x 128 B)
-  static constexpr int OFF_BAR = OFF_TAIL + 384;
+  // remainder token (L = 128 k + 1): its key row (128 B), its value row (double-buffered, 2 x 128 B), its query row
+  // (128 B, B operand of the S_t^T MMA), the probabilities of the remainder query row (bf16 [128], B operand of the
+  // O_t^T MMA; the MMA over-reads up to 128 B past it, into the scratch / barrier bytes) and two 16-byte scratch vectors
+  static constexpr int OFF_TAIL = OFF_P + 2 * ATT_TILE_BYTES;
+  static constexpr int OFF_QR = OFF_TAIL + 384;
+  static constexpr int OFF_PT = OFF_QR + 128;
+  static constexpr int OFF_XT = OFF_PT + 256;
+  static constexpr int OFF_BAR = OFF_XT + 128;
   static constexpr int BASE_BYTES = OFF_BAR + ATT_NUM_BARS * 8 + 16;
   static constexpr int OFF_QB = (BASE_BYTES + 1023) / 1024 * 1024;
   static constexpr int OFF_KB = OFF_QB + ATT_BT;
@@ -51,7 +56,10 @@ __device__ __forceinline__ uint32_t sw32_offset(uint32_t row, uint32_t chunk) {
 }
 constexpr int ATT_MAX_TAIL = 1;     // remainder key / query row (L mod 128 == 1: cls + power-of-two grid) handled outside the tiles
 constexpr int ATT_TAIL_MAX_L = 1040;  // longest sequence the remainder-row kernel keeps scores for (16 KB of smem)     // remainder keys / query rows (L mod 128) handled outside the 128-wide tiles
-constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)
+constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)  O_b: [192,208)  O_t^T: [208,224)  S_t^T: [224,240)  X: [240,242)
+constexpr uint32_t ATT_TMEM_OT = 208;   // remainder query row: O_t^T (lane = head dim, column 0)
+constexpr uint32_t ATT_TMEM_ST = 224;   // remainder query row: S_t^T (lane = key of the block, column 0)
+constexpr uint32_t ATT_TMEM_X = 240;    // half-row maxima exchanged between the two threads of a row
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
 
@@ -59,8 +67,9 @@ template <int RB>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                      const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmQKVb,
-                     const __grid_constant__ CUtensorMap tmOb, float* __restrict__ lse_out, int L, int Lm, int H,
-                     int nq, int total_items, float scale_log2) {
+                     const __grid_constant__ CUtensorMap tmOb, float* __restrict__ lse_out,
+                     __nv_bfloat16* __restrict__ out, int tail_row_fused, int L, int Lm, int H, int nq, int total_items,
+                     float scale_log2) {
   // PERSISTENT: each CTA walks work items (query tile, head, image) with stride gridDim.x, keeping its TMEM allocation,
   // barriers and the K/V TMA ring alive across items, so the next item's Q/K/V loads run under the current item's
   // softmax.  Query rows [0, nq * 128) are handled here; a short remainder of rows goes to attention_tail_kernel.
@@ -93,6 +102,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   // keys [0, Lm) go through the tensor-core blocks; the (few) keys [Lm, L) are folded in on the FMA pipe (see below)
   const int nkv = (Lm + ATT_BKV - 1) / ATT_BKV;
   const int ntail = L - Lm;
+  // The remainder QUERY row (row Lm) rides along with the last query tile of its head (hd = 64 only): its scores come
+  // out of one more small MMA per key block in TRANSPOSED form, S_t^T = K_j q_t^T (M = 128 keys, N = 16 of which one
+  // column is real), so each softmax thread of column-half 0 holds the score of one key; the probabilities go back as
+  // a 256-byte vector and O_t^T = V_j^T p_t^T (M = head dims, N = 16) accumulates in 16 more TMEM columns.
+  const bool tail_q = RB == 0 && ntail > 0 && tail_row_fused != 0;
 
   if (warp == ATT_SM_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -125,12 +139,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
         const int qt = item % nq, h = (item / nq) % H, b = item / (nq * H);
         mbar_wait(q_empty, (n & 1) ^ 1, 9);
-        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0) + (RB ? ATT_BT : 0));
+        const bool titem = tail_q && qt == nq - 1;
+        mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES + (ntail > 0 ? 256 : 0) + (titem ? 128 : 0) + (RB ? ATT_BT : 0));
         tma_load_4d(sQ, &tmQKV, q_full, 0, h, qt * ATT_BQ, b);
         if (RB) tma_load_4d(smem + LL::OFF_QB, &tmQKVb, q_full, 64, h, qt * ATT_BQ, b);
         if (ntail > 0) {  // remainder key row and its value row (1 x 128 B each, unswizzled)
           tma_load_4d(smem + LL::OFF_TAIL, &tmTail, q_full, 0, H + h, Lm, b);
           tma_load_4d(smem + LL::OFF_TAIL + 128 + (n & 1) * 128, &tmTail, q_full, 0, 2 * H + h, Lm, b);
+          if (titem) tma_load_4d(smem + LL::OFF_QR, &tmTail, q_full, 0, h, Lm, b);
         }
         for (int j = 0; j < nkv; ++j, ++g) {
           const int s = g % NS;
@@ -153,6 +169,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t p_addr = smem_u32(sP);
       int n = 0, g = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        const bool titem = tail_q && item % nq == nq - 1;
         mbar_wait(q_full, n & 1, 12);
         for (int j = 0; j < nkv; ++j, ++g) {
           const int s = g % NS;
@@ -173,6 +190,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
             umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + LL::OFF_QB)),
                          umma_desc_sw32(smem_u32(smem + LL::OFF_KB + s * ATT_BT)), idesc_s, 1);
+          if (titem) {   // S_t^T = K_j q_t^T
+            constexpr uint32_t idesc_st = umma_idesc_bf16(128, 16, 0, 0);
+            const uint32_t qr_addr = smem_u32(smem + LL::OFF_QR);
+#pragma unroll
+            for (int k = 0; k < ATT_HD / 16; ++k)
+              umma_bf16_ss(tmem_base + ATT_TMEM_ST, umma_desc_kmajor_sw128(k_addr + k * 32), umma_desc_row0(qr_addr + k * 32),
+                           idesc_st, k != 0);
+          }
           umma_commit(&k_empty[s]);
           umma_commit(s_full);
           if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
@@ -198,6 +223,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                            (j | kk) != 0);
             }
           }
+          if (titem) {   // O_t^T += V_j^T p_t^T  (A = V MN-major: M runs over head dims; rows 64..127 are padding)
+            constexpr uint32_t idesc_ot = umma_idesc_bf16(128, 16, 1, 0);
+            const uint32_t pt_addr = smem_u32(smem + LL::OFF_PT);
+            for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+              umma_bf16_ss(tmem_base + ATT_TMEM_OT, umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_TILE_BYTES),
+                           umma_desc_row0(pt_addr + kk * 32), idesc_ot, (j | kk) != 0);
+          }
           umma_commit(&v_empty[s]);
           umma_commit(pv_done);
         }
@@ -215,7 +247,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int r = quad * 32 + lane;  // row in tile = TMEM lane
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t p_base = smem_u32(sP) + half * ATT_TILE_BYTES;
-    const uint32_t xchg = smem_u32(smem + LL::OFF_XCHG);
+    const uint32_t xt = smem_u32(smem + LL::OFF_XT);   // [0,16): warp maxima, [16,32): warp sums of the remainder row
     constexpr uint32_t SMT = 32 * ATT_SM_WARPS;
     int g = 0, n = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
@@ -230,6 +262,9 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // here on the FMA pipe while the first S MMA runs, and folded into the output in the epilogue — instead of a
       // whole extra TMA -> MMA -> softmax -> MMA round for a 1-column block.
       float s_tail = 0.f;
+      // remainder query row (handled by the threads of column-half 0): reference, partial sum, score against the remainder key
+      const bool titem = tail_q && qt == nq - 1 && half == 0;
+      float m_t = -INFINITY, l_t = 0.f, s_tt = 0.f;
       if (ntail > 0) {
         mbar_wait(q_full, n & 1, 19);
         const uint32_t kt = smem_u32(smem + LL::OFF_TAIL);
@@ -244,6 +279,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           d = fmaf(bf16_lo(qv.w), bf16_lo(kv.w), d); d = fmaf(bf16_hi(qv.w), bf16_hi(kv.w), d);
         }
         s_tail = d * scale_log2;
+        if (titem && quad < 2) {   // q_t . k_t, two dims per lane
+          uint32_t qa, ka;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa) : "r"(smem_u32(smem + LL::OFF_QR) + 4 * lane));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ka) : "r"(kt + 4 * lane));
+          float e = fmaf(bf16_lo(qa), bf16_lo(ka), bf16_hi(qa) * bf16_hi(ka));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+          s_tt = e * scale_log2;
+        }
         mbar_arrive(q_empty);
       }
       for (int j = 0; j < nkv; ++j, ++g) {
@@ -271,22 +315,30 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
           }
         }
-        // exchange the half-row maxima (rounded UP to bf16: any reference >= the true maximum - 2^8 is valid, and both
-        // halves must derive the SAME reference)
-        {
-          float mt = mx * scale_log2;
-          uint32_t bits = __float_as_uint(mt);
-          uint32_t up = (bits + ((mt >= 0.f) ? 0xFFFFu : 0u)) & 0xFFFF0000u;   // toward +inf for either sign
-          if (mt == -INFINITY) up = 0xFF800000u;
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(xchg + (half * 128 + r) * 2), "h"(static_cast<unsigned short>(up >> 16)) : "memory");
+        float st_raw = 0.f;
+        if (titem) {   // this thread's key (row r of the block) against the remainder query row
+          uint32_t u;
+          tmem_ld_x1(tmem_base + t_lane + ATT_TMEM_ST, u);
+          tmem_ld_wait();
+          st_raw = __uint_as_float(u) * scale_log2;
+          float wm = st_raw;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+          if (lane == 0) sts_f32(xt + quad * 4, wm);
         }
+        // exchange the half-row maxima through two spare TMEM columns of the row's lane (both threads of a row must
+        // derive the SAME reference; any reference >= the true maximum - 2^8 is valid)
+        tmem_st_x1(tmem_base + t_lane + ATT_TMEM_X + half, __float_as_uint(mx * scale_log2));
+        tmem_st_wait();
+        tc_fence_before();
         named_bar_sync(2, SMT);
+        tc_fence_after();
         float m_tile;
         {
-          unsigned short a, bb;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(a) : "r"(xchg + r * 2));
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(bb) : "r"(xchg + (128 + r) * 2));
-          m_tile = fmaxf(__uint_as_float(static_cast<uint32_t>(a) << 16), __uint_as_float(static_cast<uint32_t>(bb) << 16));
+          uint32_t a, bb;
+          tmem_ld_x2(tmem_base + t_lane + ATT_TMEM_X, a, bb);
+          tmem_ld_wait();
+          m_tile = fmaxf(__uint_as_float(a), __uint_as_float(bb));
         }
         // P buffer and the O accumulator are owned by PV(j-1) until it completes
         if (j > 0) {
@@ -317,6 +369,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             }
             tmem_st_wait();
           }
+        }
+        if (titem) {   // online-softmax step of the remainder query row over this block's 128 keys (one per thread)
+          const float4 w4 = lds_f32x4(xt);
+          const float mt = fmaxf(fmaxf(w4.x, w4.y), fmaxf(w4.z, w4.w));
+          if (j == 0) {
+            m_t = mt;
+          } else if (mt > m_t + 8.f) {   // uniform over the 128 threads
+            const float alpha = fast_exp2(m_t - mt);
+            m_t = mt;
+            l_t *= alpha;
+            if (quad < 2) {              // O_t^T lives in lanes 0..63 (head dims), column 0
+              uint32_t o1;
+              tmem_ld_x1(tmem_base + t_lane + ATT_TMEM_OT, o1);
+              tmem_ld_wait();
+              tmem_st_x1(tmem_base + t_lane + ATT_TMEM_OT, __float_as_uint(__uint_as_float(o1) * alpha));
+              tmem_st_wait();
+            }
+          }
+          const float p = fast_exp2(st_raw - m_t);
+          l_t += p;
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(smem + LL::OFF_PT) + 2 * r),
+                       "h"(static_cast<unsigned short>(pack_bf16x2(p, 0.f) & 0xFFFFu)) : "memory");
         }
         // pass 2: P = 2^(S*scale - m_ref) -> bf16 -> swizzled smem (this half's 64-column atom); row sum in fp32
         float rowsum = 0.f;
@@ -370,9 +444,16 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       uint32_t ob[16];
       tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_O + 32 * half, o);
       if (RB && half == 0) tmem_ld_x16(tmem_base + t_lane + ATT_TMEM_OB, ob);
+      uint32_t ot = 0;
+      if (titem && quad < 2) tmem_ld_x1(tmem_base + t_lane + ATT_TMEM_OT, ot);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(o_free);  // the accumulator may be overwritten by the next item's first P V
+      if (titem) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) l_t += __shfl_xor_sync(0xffffffffu, l_t, o);
+        if (lane == 0) sts_f32(xt + 16 + quad * 4, l_t);
+      }
       if (ntail > 0) {      // fold the remainder key in: one more online-softmax step, entirely in registers
         const uint32_t vt = smem_u32(smem + LL::OFF_TAIL + 128 + (n & 1) * 128) + 64 * half;
         const float m_fin = fmaxf(m_ref, s_tail);
@@ -397,6 +478,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       named_bar_sync(2, SMT);
       const float l_tot = lds_f32(lx + r * 4) + lds_f32(lx + (128 + r) * 4);
       const float inv_l = 1.f / l_tot;
+      if (titem && quad < 2) {   // remainder query row: fold its remainder key in, normalise, store head dim r
+        const float4 w4 = lds_f32x4(xt + 16);
+        const float m_fin = fmaxf(m_t, s_tt);
+        const float a = fast_exp2(m_t - m_fin);
+        const float pt = fast_exp2(s_tt - m_fin);
+        const float l_all = fmaf((w4.x + w4.y) + (w4.z + w4.w), a, pt);
+        unsigned short vb;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(vb) : "r"(smem_u32(smem + LL::OFF_TAIL + 128 + (n & 1) * 128) + 2 * r));
+        const float v = __uint_as_float(static_cast<uint32_t>(vb) << 16);
+        const float o = fmaf(__uint_as_float(ot), a, pt * v) / l_all;
+        const float o_hi = __shfl_down_sync(0xffffffffu, o, 1);
+        const long long row = static_cast<long long>(b) * L + Lm;
+        if ((lane & 1) == 0)
+          *reinterpret_cast<uint32_t*>(out + (row * H + h) * ATT_HD + r) = pack_bf16x2(o, o_hi);
+        if (r == 0 && lse_out != nullptr)
+          lse_out[(static_cast<long long>(b) * H + h) * L + Lm] = (m_fin + log2f(l_all)) * 0.69314718055994531f;
+      }
       // staging in the first P atom (every MMA that read P has completed: pv_done)
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -566,16 +664,21 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   const int nq = (l_main + ATT_BQ - 1) / ATT_BQ;
   const long long items = static_cast<long long>(nq) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
+  // the remainder query row rides inside the main kernel (OVK_ATT_TAIL_KERNEL=1 selects the stand-alone FMA-pipe kernel)
+  static const bool tail_kernel = [] { const char* e = getenv("OVK_ATT_TAIL_KERNEL"); return e != nullptr && e[0] == '1'; }();
+  const int fused_tail = (tail > 0 && !tail_kernel) ? 1 : 0;
   const int per_sm = 2;
   const int grid = static_cast<int>(items < (long long)per_sm * num_sms() ? items : (long long)per_sm * num_sms());
   if (ext)
-    attention_fwd_kernel<16><<<grid, ATT_THREADS, AttL<16>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+    attention_fwd_kernel<16><<<grid, ATT_THREADS, AttL<16>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse,
+                                                                          reinterpret_cast<__nv_bfloat16*>(out), 0, L, l_main, H, nq,
                                                                           static_cast<int>(items), scale * 1.4426950408889634f);
   else
-    attention_fwd_kernel<0><<<grid, ATT_THREADS, AttL<0>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse, L, l_main, H, nq,
+    attention_fwd_kernel<0><<<grid, ATT_THREADS, AttL<0>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse,
+                                                                      reinterpret_cast<__nv_bfloat16*>(out), fused_tail, L, l_main, H, nq,
                                                                       static_cast<int>(items), scale * 1.4426950408889634f);
   if ((rc = check_launch("attention_fwd_kernel"))) return rc;
-  if (tail) {
+  if (tail && !fused_tail) {
     dim3 tgrid((tail * H + 3) / 4, B);
     attention_tail_kernel<<<tgrid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                 reinterpret_cast<__nv_bfloat16*>(out), lse, L, H, l_main, tail,

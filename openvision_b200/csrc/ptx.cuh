@@ -292,6 +292,17 @@ __device__ __forceinline__ float fast_rcp(float x) {
 __device__ __forceinline__ void tmem_ld_x1(uint32_t taddr, uint32_t& r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+// K-major operand without swizzle whose ONLY meaningful row is row 0, stored as plain contiguous bytes at `saddr`
+// (16-byte aligned): core matrices (8 rows x 16 B) are addressed with a 16-byte stride in both directions, so row 0's
+// k-chunks are consecutive and every other row of the (padding) operand is a shifted view of the same bytes.  Lets a
+// single vector be the B operand of a small-N MMA without owning a 1024-byte aligned tile.
+__device__ __forceinline__ uint64_t umma_desc_row0(uint32_t saddr) { return umma_desc(saddr, 16, 16, 0); }
 }  // namespace ovk
 
 // ---------------------------------------------------------------- CTA pairs (cta_group::2) and clusters

@@ -332,3 +332,24 @@ def test_gemm_ln_rejects_bad_arguments(ops):
         ops.gemm_ln(a, w, stats_out=torch.zeros(1, 128, 2, device="cuda"))
     with pytest.raises(OvkError):   # colsum without row statistics
         ops.gemm_ln(a, w, colsum=torch.zeros(128, device="cuda"))
+
+
+@pytest.mark.parametrize("L", [129, 257, 385, 513])
+@pytest.mark.parametrize("grow", [False, True])
+def test_attention_remainder_row_rides_in_main_kernel(ops, L, grow):
+    """L = 128 k + 1 (cls + power-of-two grid): the last query row and the last key are handled outside the 128-wide
+    tiles (transposed small-N MMA / FMA fold).  `grow` makes later key blocks score far higher against the last query
+    than earlier ones, which forces the rescale of its running output.  Row L-1 is checked on its own."""
+    B, H, hd = 3, 5, 64
+    qkv = rnd(B * L, 3 * H * hd, seed=100 + L).bfloat16().view(B, L, 3, H, hd).clone()
+    if grow:
+        ramp = torch.linspace(0.0, 6.0, L).view(1, L, 1, 1)
+        qkv[:, :, 1] = (qkv[:, :, 1].float() + ramp * qkv[:, L - 1:L, 0].float().sign()).bfloat16()   # keys align with the last query
+    qkv = qkv.view(B * L, 3 * H * hd)
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, f"attention L{L}")
+    last = out.view(B, L, H * hd)[:, L - 1]
+    assert_close(last, ref.view(B, L, H * hd)[:, L - 1], 2e-2, f"attention L{L}: remainder query row")
+    assert_close(lse, lse_ref, 1e-3, "attention lse")
+    assert_close(lse[:, :, L - 1], lse_ref[:, :, L - 1], 1e-3, "attention lse of the remainder row")
