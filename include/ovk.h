@@ -66,21 +66,28 @@ int ovk_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
 int ovk_gemm_bf16_ex(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
                      int K, const float* bias, const void* residual, long long ldr, void* preact, long long ldp,
                      int flags, void* stream);
-/* LayerNorm folded into the projection that consumes it (transformer.py:254-265: attn(ln_1(x)), mlp(ln_2(x))):
- *   ln(x) W^T + b = rstd_i * (x (W.gamma)^T - mu_i * c) + d,   c = rowsum(W.gamma),  d = W beta + b
- * so the GEMM reads the un-normalised residual stream x directly and no normalised copy is ever written.
- *   B         : bf16 [N, K] = W . gamma (column-scaled weight)         colsum : f32[N] = c        bias : f32[N] = d
- *   row_stats_in  : f32 [stats_parts_in][M][2] = partial (sum_k x, sum_k x^2) per row of A, summed in slot order
- *                   (K = the LayerNorm width); mu and rstd are derived from them with ln_eps
- *   row_stats_out : optional f32 [ceil(N/128)][M][2]: the same statistics of the OUTPUT rows as written (bf16-rounded),
- *                   one slot per 128 output columns, plain stores (deterministic; needs N % 64 == 0, N > 128, linear
- *                   epilogue) - this is how out_proj / c_proj (+ residual) hand the next LayerNorm its statistics.
- * With row_stats_in == colsum == NULL it is ovk_gemm_bf16_ex plus row_stats_out.  ovk_row_stats (one slot) seeds the
- * first block. */
+/* LayerNorm folded into the projection that consumes it (transformer.py:254-265: attn(ln_1(x)), mlp(ln_2(x));
+ * LayerNorm itself: transformer.py:15-30):
+ *   ln(x) W^T + b = rstd_i * (x Wc^T) + d,   Wc[n][k] = W[n][k] gamma[k] - mean_k(W[n][.] gamma[.]),   d = W beta + b
+ * sum_k Wc[n][k] = 0 makes the product blind to the row mean, so the GEMM reads the un-normalised residual stream x
+ * directly, no normalised copy is ever written, and the epilogue only scales each row by its rstd.
+ *   ovk_pack_ln_linear : W [N,K] (f32 or bf16), gamma / beta f32[K], bias f32[N] or NULL -> Wc bf16 [N,K], d f32[N].
+ *                        After rounding, a few entries per row are moved to the adjacent bf16 value so that the rounded
+ *                        row still sums to ~0 (see csrc/ln_pack.cu).
+ *   ovk_gemm_bf16_ln   : C = act(rstd_i * (A B^T) + bias) (+ residual);  B = Wc, bias = d.
+ *     row_stats_in  : f32 [stats_parts_in][M][2] = partial (sum_k x, sum_k x^2) per row of A, summed in slot order
+ *                     (K = the LayerNorm width, stats_parts_in <= 64); rstd is derived from them with ln_eps.
+ *                     NULL: plain GEMM (rstd = 1).
+ *     row_stats_out : optional f32 [ceil(N/128)][M][2]: the same statistics of the OUTPUT rows, one slot per 128 output
+ *                     columns, plain stores (deterministic; needs N % 64 == 0, N > 128, linear epilogue) - this is how
+ *                     out_proj / c_proj (+ residual) hand the next LayerNorm its statistics.
+ *   ovk_row_stats      : the statistics (one slot) of a tensor that no GEMM of ours produced (first block). */
+int ovk_pack_ln_linear(const void* W, int w_is_f32, long long ldw, const float* gamma, const float* beta,
+                       const float* bias, void* Wc, long long ldwc, float* d, int N, int K, void* stream);
 int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
-                     int K, const float* bias, const float* colsum, const float* row_stats_in, int stats_parts_in,
-                     float ln_eps, const void* residual, long long ldr, void* preact, long long ldp,
-                     float* row_stats_out, int flags, void* stream);
+                     int K, const float* bias, const float* row_stats_in, int stats_parts_in, float ln_eps,
+                     const void* residual, long long ldr, void* preact, long long ldp, float* row_stats_out, int flags,
+                     void* stream);
 int ovk_row_stats(const void* x, long long ldx, float* stats, int rows, int D, void* stream);
 /* Backward GEMMs (what autograd derives from F.linear): operands are read in place, nothing is transposed in memory.
  *   ovk_gemm_bf16_nn : C[M,N] = alpha * A[M,K] * B[K,N]      (B row-major [K,N])   dX = dY * W

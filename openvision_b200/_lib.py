@@ -38,8 +38,10 @@ _PROTOTYPES = {
     "ovk_gemm_bf16_ex": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_gemm_bf16_ln": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
-                                 c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_longlong, c_void_p,
-                                 c_longlong, c_void_p, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_int, c_float, c_void_p, c_longlong, c_void_p, c_longlong,
+                                 c_void_p, c_int, c_void_p]),
+    "ovk_pack_ln_linear": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                   c_void_p, c_int, c_int, c_void_p]),
     "ovk_row_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),
     "ovk_gemm_bf16_nn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),

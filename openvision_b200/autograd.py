@@ -339,27 +339,24 @@ def _block_packed(blk):
 def _ln_fold_enabled(D: int) -> bool:
     """LayerNorm is folded into the QKV / fc1 GEMMs when the width fits the statistics epilogue (include/ovk.h,
     ovk_gemm_bf16_ln); OVK_LN_FOLD=0 selects the stand-alone LayerNorm kernels (A/B measurements)."""
-    return D > 128 and D % 64 == 0 and os.environ.get("OVK_LN_FOLD", "1") != "0"
+    return 128 < D <= 8192 and D % 64 == 0 and os.environ.get("OVK_LN_FOLD", "1") != "0"
 
 
-def _ln_folded(owner, key, w, b, gamma, beta):
-    """(W . gamma as bf16 [N,K], c = rowsum of that, d = W beta + b), cached on the versions of all four parameters:
-    ln(x) W^T + b = rstd (x (W.gamma)^T - mu c) + d."""
+def _ln_folded(owner, key, w, b, ln, gamma_f32, beta_f32, b_f32):
+    """(Wc bf16 [N,K], d fp32 [N]) from ops.pack_ln_linear, cached on the versions of the parameters involved:
+    ln(x) W^T + b = rstd (x Wc^T) + d with Wc = W.gamma, rows centred to zero sum."""
     cache = owner.__dict__.setdefault("_ovk_cache", {})
-    tag = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device) for t in (w, b, gamma, beta))
+    tag = tuple(None if t is None else (t.data_ptr(), t._version, t.dtype, t.device) for t in (w, b, ln.weight, ln.bias))
     hit = cache.get(key)
     if hit is not None and hit[0] == tag:
         return hit[1]
     with torch.no_grad():
-        wf = w.detach().float()
-        wg = (wf * gamma.detach().float()[None, :]).to(torch.bfloat16).contiguous()
-        c = wg.float().sum(dim=1).contiguous()
-        d = wf @ beta.detach().float()
-        if b is not None:
-            d = d + b.detach().float()
-        d = d.contiguous()
-    cache[key] = (tag, (wg, c, d))
-    return wg, c, d
+        wd = w.detach()
+        if wd.dtype not in (torch.float32, torch.bfloat16):
+            wd = wd.float()
+        packed = ops.pack_ln_linear(wd.contiguous(), gamma_f32, beta_f32, b_f32)
+    cache[key] = (tag, packed)
+    return packed
 
 
 def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
@@ -371,12 +368,12 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
     M, D = x2.shape
     if _ln_fold_enabled(D) and blk.ln_1.eps > 0:
         a_, fc = blk.attn, blk.mlp.c_fc
-        wq, cq, dq = _ln_folded(a_, "in_ln", a_.in_proj_weight, a_.in_proj_bias, blk.ln_1.weight, blk.ln_1.bias)
-        w1, cc1, dd1 = _ln_folded(fc, "w_ln", fc.weight, fc.bias, blk.ln_2.weight, blk.ln_2.bias)
+        wq, dq = _ln_folded(a_, "in_ln", a_.in_proj_weight, a_.in_proj_bias, blk.ln_1, p["g1"], p["b1"], p["bqkv"])
+        w1, dd1 = _ln_folded(fc, "w_ln", fc.weight, fc.bias, blk.ln_2, p["g2"], p["b2"], p["c1"])
         if stats is None:
             stats = ops.row_stats(x2)
         parts = (D + 127) // 128
-        qkv = ops.gemm_ln(x2, wq, bias=dq, colsum=cq, row_stats=stats, eps=blk.ln_1.eps)
+        qkv = ops.gemm_ln(x2, wq, bias=dq, row_stats=stats, eps=blk.ln_1.eps)
         if save:
             a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
         else:
@@ -384,7 +381,7 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
         st_mid = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
         x_mid = ops.gemm_ln(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None, stats_out=st_mid)
         u = torch.empty((M, w1.shape[0]), dtype=torch.bfloat16, device=x2.device) if save else None
-        f = ops.gemm_ln(x_mid, w1, bias=dd1, colsum=cc1, row_stats=st_mid, eps=blk.ln_2.eps, act=act, preact_out=u)
+        f = ops.gemm_ln(x_mid, w1, bias=dd1, row_stats=st_mid, eps=blk.ln_2.eps, act=act, preact_out=u)
         st_y = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
         y = ops.gemm_ln(f, p["w2"], bias=p["c2"], residual=x_mid, out=None if save else x_mid, stats_out=st_y)
         if save:   # LayerNorm statistics are recomputed in backward together with h1 / h2

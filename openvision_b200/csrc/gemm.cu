@@ -12,14 +12,16 @@ namespace ovk {
 
 enum { EPI_LINEAR = 0, EPI_ACT = 1, EPI_DACT = 2 };
 
+constexpr int GEMM_MAX_STAT_PARTS = 64;   // partial-sum slots (one per 128 columns of the LayerNorm width)
+
 struct GemmEpi {
   const float* bias;  // f32[N] or null
   float alpha;
   int flags;          // OVK_EPI_BIAS | OVK_EPI_RESIDUAL | act id | OVK_EPI_SAVE_PREACT
   ActCoef act;
-  // LayerNorm folded into the GEMM (FUSE kernels): y = rstd_i (acc - mu_i c_n) + d_n with B = W . gamma, c = rowsum(B),
-  // d = W beta + bias, (mu, rstd) from per-row (sum x, sum x^2) produced by the epilogue of the GEMM that wrote x.
-  const float* colsum;       // f32[N] or null
+  // LayerNorm folded into the GEMM (FUSE kernels): y = rstd_i * acc + d_n with B = the row-centred W . gamma
+  // (ovk_pack_ln_linear: sum_k B[n][k] = 0, which is what removes the mean), d = W beta + bias, and rstd from the per-row
+  // (sum x, sum x^2) produced by the epilogue of the GEMM that wrote x.
   const float* row_stats_in; // f32[stats_parts_in][M][2] partial (sum, sum sq) of the A rows, or null
   float* row_stats_out;      // f32[ceil(N/128)][M][2] partial (sum, sum sq) of the output rows, or null
   int stats_parts_in;
@@ -35,7 +37,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const __grid_constant__ CUtensorMap tmD, const GemmEpi ep, int M, int N, int K, int splits) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4, PAIR>;
+  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4 + (FUSE ? GEMM_BM * 4 : 0), PAIR>;
   GemmCtx<BN, L> cx(smem_raw);
   const uint32_t tmem_base = gemm_prologue(cx, &tmA, &tmB, &tmC, &tmR);
   const int warp = threadIdx.x >> 5;
@@ -44,6 +46,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) gemm_producer<BN, A_MN, B_MN>(cx, &tmA, &tmB, M, N, K, splits);
   } else if (warp == 1) {
     if (elect_one()) gemm_mma_issuer<BN, A_MN, B_MN>(cx, tmem_base, M, N, K, splits);
+  } else if (FUSE && warp == 3) {
+    // ------------------------------------------------------------ row-scale producer (LayerNorm folded into the GEMM)
+    // rstd of the 128 rows of the NEXT tile from the partial (sum, sum sq) slots, one tile ahead of the epilogue, so the
+    // global-load latency never sits on the epilogue's critical path.  Slots are combined in slot order (deterministic).
+    if (ep.row_stats_in != nullptr) {
+      const uint32_t lane = lane_id();
+      const uint32_t rs_base = smem_u32(cx.epi_scratch()) + 2 * BN * 4;
+      GemmSched sched(M, N, BN, K, splits, PAIR, cx.rank);
+      int it = 0;
+      for (int t = cx.first; t < sched.total; t += cx.stride, ++it) {
+        const GemmTileInfo ti = sched.tile(t, BN);
+        float rstd[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = ti.m0 + static_cast<int>(lane) + 32 * i;
+          float s1 = 0.f, s2 = 0.f;
+          if (row < M) {
+            const float2* src = reinterpret_cast<const float2*>(ep.row_stats_in) + row;
+            for (int q = 0; q < ep.stats_parts_in; ++q) {
+              const float2 v = __ldg(src + static_cast<long long>(q) * M);
+              s1 += v.x;
+              s2 += v.y;
+            }
+          }
+          const float mu = s1 * ep.inv_k;
+          rstd[i] = rsqrtf(fmaxf(s2 * ep.inv_k - mu * mu, 0.f) + ep.ln_eps);   // rows >= M: finite, never stored
+        }
+        mbar_wait(&cx.rs[1], (it & 1) ^ 1, 6);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts_f32(rs_base + (lane + 32 * i) * 4, rstd[i]);
+        mbar_arrive(&cx.rs[0]);
+      }
+    }
   } else if (warp >= GEMM_CTRL_WARPS) {
     // ------------------------------------------------------------ epilogue: TMEM -> regs -> smem -> TMA store
     constexpr int CW = OUT_F32 ? 32 : 64;         // columns per staged chunk (one 128-byte row)
@@ -71,40 +106,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const GemmTileInfo ti = sched.tile(t, BN);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      // per-column epilogue vectors -> smem.  Lean kernels: the bias tile, double-buffered by tile parity (one barrier
-      // publishes it).  FUSE kernels: (d, c) pairs, single-buffered (a barrier on either side of the write).
-      const uint32_t bias_s = bias_base + (FUSE ? 0 : (it & 1) * (BN * 4));
-      if constexpr (FUSE) named_bar_sync(3, GEMM_EPI_THREADS);
+      // per-column bias tile -> smem, double-buffered by tile parity (one barrier publishes it)
+      const uint32_t bias_s = bias_base + (it & 1) * (BN * 4);
       {
         const int j = threadIdx.x - 32 * GEMM_CTRL_WARPS;
         if (j < BN) {
           const int n = ti.n0 + j;
-          const float bv = (has_bias && n < N) ? ep.bias[n] : 0.f;
-          if constexpr (FUSE) sts_f32x2(bias_s + j * 8, bv, (ep.colsum != nullptr && n < N) ? ep.colsum[n] : 0.f);
-          else sts_f32(bias_s + j * 4, bv);
+          sts_f32(bias_s + j * 4, (has_bias && n < N) ? ep.bias[n] : 0.f);
         }
       }
       named_bar_sync(3, GEMM_EPI_THREADS);
-      // FUSE: this row's LayerNorm statistics -> multiplier of the accumulator and of the column sums
-      float a_mul = alpha, c_mul = 0.f, st1 = 0.f, st2 = 0.f;
+      float a_mul = alpha, st1 = 0.f, st2 = 0.f;
       if constexpr (FUSE) {
-        if (ep.row_stats_in != nullptr) {
-          const int row_s = ti.m0 + et;
-          float mu = 0.f, rstd = 0.f;
-          if (row_s < M) {
-            // partial sums (one slot per 128 source columns) combined in a fixed order: deterministic
-            const float2* sp = reinterpret_cast<const float2*>(ep.row_stats_in) + row_s;
-            float s1 = 0.f, s2 = 0.f;
-            for (int q = 0; q < ep.stats_parts_in; ++q) {
-              const float2 st = sp[static_cast<long long>(q) * M];
-              s1 += st.x;
-              s2 += st.y;
-            }
-            mu = s1 * ep.inv_k;
-            rstd = rsqrtf(fmaxf(s2 * ep.inv_k - mu * mu, 0.f) + ep.ln_eps);
-          }
-          a_mul = rstd;
-          c_mul = -mu * rstd;
+        if (ep.row_stats_in != nullptr) {   // this row's rstd, prepared by warp 3
+          mbar_wait(&cx.rs[0], it & 1, 7);
+          a_mul = lds_f32(bias_base + 2 * BN * 4 + et * 4);
+          mbar_arrive(&cx.rs[1]);
         }
       }
       mbar_wait(&cx.tmem_full[acc], acc_phase, 4);
@@ -140,22 +157,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (!live) continue;
         float x[CW];
-        if constexpr (FUSE) {
 #pragma unroll
-          for (int j = 0; j < CW / 2; ++j) {
-            const float4 b = lds_f32x4(bias_s + (col_in_tile + 2 * j) * 8);   // (d, c, d, c)
-            x[2 * j + 0] = fmaf(__uint_as_float(v[2 * j + 0]), a_mul, fmaf(c_mul, b.y, b.x));
-            x[2 * j + 1] = fmaf(__uint_as_float(v[2 * j + 1]), a_mul, fmaf(c_mul, b.w, b.z));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            const float4 b = lds_f32x4(bias_s + (col_in_tile + 4 * j) * 4);
-            x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), alpha, b.x);
-            x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), alpha, b.y);
-            x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), alpha, b.z);
-            x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), alpha, b.w);
-          }
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 b = lds_f32x4(bias_s + (col_in_tile + 4 * j) * 4);
+          x[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), a_mul, b.x);
+          x[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a_mul, b.y);
+          x[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a_mul, b.z);
+          x[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a_mul, b.w);
         }
         if constexpr (EPI == EPI_ACT) {
           if (save_pre) {  // pre-activation out first (same staging buffer), then the activation
@@ -203,26 +211,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             sts128(sbuf + sw128_offset(et, j), make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
                                                           __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3])));
         } else {
-          uint32_t w[CW / 2];
-#pragma unroll
-          for (int j = 0; j < CW / 2; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
           if constexpr (FUSE) {
-            // row statistics of the tensor being written (for the NEXT LayerNorm), taken from the ROUNDED values so
-            // that they are exactly the statistics of what a later LayerNorm kernel would read back
+            // row statistics of the tensor being written (for the NEXT LayerNorm); taken before the bf16 rounding, which
+            // moves the mean and the variance by ~1e-5 relative
             if (ep.row_stats_out != nullptr) {
               float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j) {
-                const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
-                p1[(2 * j) & 3] += lo;
-                p1[(2 * j + 1) & 3] += hi;
-                p2[(2 * j) & 3] = fmaf(lo, lo, p2[(2 * j) & 3]);
-                p2[(2 * j + 1) & 3] = fmaf(hi, hi, p2[(2 * j + 1) & 3]);
+              for (int j = 0; j < CW; ++j) {
+                p1[j & 3] += x[j];
+                p2[j & 3] = fmaf(x[j], x[j], p2[j & 3]);
               }
               st1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
               st2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
             }
           }
+          uint32_t w[CW / 2];
+#pragma unroll
+          for (int j = 0; j < CW / 2; ++j) w[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) sts128(sbuf + sw128_offset(et, j), make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]));
         }
@@ -270,7 +275,7 @@ static bool pair_mode_enabled() {
 
 template <int BN, bool A_MN, bool B_MN, int EPI, bool OUT_F32, bool PAIR, bool FUSE = false>
 static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
-  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4, PAIR>;
+  using L = GemmSmemLayout<BN, 2 * GEMM_BM * 128, 2 * BN * 4 + (FUSE ? GEMM_BM * 4 : 0), PAIR>;
   CUtensorMap tmA, tmB, tmC, tmR, tmD;
   int rc;
   if (A_MN) rc = make_tmap_2d_bf16(&tmA, g.A, g.M, g.K, g.lda, 64, 64);
@@ -420,8 +425,8 @@ extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, lon
 
 
 extern "C" int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
-                                int M, int N, int K, const float* bias, const float* colsum, const float* row_stats_in,
-                                int stats_parts_in, float ln_eps, const void* residual, long long ldr, void* preact, long long ldp,
+                                int M, int N, int K, const float* bias, const float* row_stats_in, int stats_parts_in,
+                                float ln_eps, const void* residual, long long ldr, void* preact, long long ldp,
                                 float* row_stats_out, int flags, void* stream) {
   GemmArgs g{A, lda, false, B, ldb, false, C, ldc, false, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
   const int act = flags & OVK_EPI_ACT_MASK;
@@ -430,9 +435,8 @@ extern "C" int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, lon
   if ((flags & OVK_EPI_SAVE_PREACT) && (preact == nullptr || act == 0))
     return set_error(OVK_ERR_SHAPE, "gemm_ln: SAVE_PREACT needs an activation and an output pointer");
   if (act && (flags & OVK_EPI_RESIDUAL)) return set_error(OVK_ERR_SHAPE, "gemm_ln: activation + residual in one epilogue is not supported");
-  if ((row_stats_in == nullptr) != (colsum == nullptr))
-    return set_error(OVK_ERR_SHAPE, "gemm_ln: row_stats_in and colsum come together (LayerNorm folded into the GEMM)");
-  if (row_stats_in != nullptr && stats_parts_in < 1) return set_error(OVK_ERR_SHAPE, "gemm_ln: stats_parts_in must be >= 1");
+  if (row_stats_in != nullptr && (stats_parts_in < 1 || stats_parts_in > GEMM_MAX_STAT_PARTS))
+    return set_error(OVK_ERR_SHAPE, "gemm_ln: stats_parts_in must be in [1, %d]", GEMM_MAX_STAT_PARTS);
   if (row_stats_out != nullptr && ((N % 64) || N <= 128))
     return set_error(OVK_ERR_SHAPE, "gemm_ln: row statistics output needs N %% 64 == 0 and N > 128");
   if (row_stats_out != nullptr && act) return set_error(OVK_ERR_SHAPE, "gemm_ln: row statistics output is for the linear epilogue");
@@ -440,7 +444,6 @@ extern "C" int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, lon
   g.ep.alpha = 1.f;
   g.ep.flags = flags;
   g.ep.act = act_coef(act);
-  g.ep.colsum = colsum;
   g.ep.row_stats_in = row_stats_in;
   g.ep.row_stats_out = row_stats_out;
   g.ep.stats_parts_in = stats_parts_in;

@@ -44,8 +44,8 @@ struct GemmSmemLayout {
   static constexpr int C_STAGE_BYTES = GEMM_BM * 128;
   static constexpr int OFF_EPI = OFF_C + C_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + EPI_BYTES;
-  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], aux[2]  + tmem base slot
-  static constexpr int NUM_BARS = 2 * STAGES + 6;
+  // barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], aux[2], row-scale full / empty  + tmem base slot
+  static constexpr int NUM_BARS = 2 * STAGES + 8;
   static constexpr int OFF_TMEM_SLOT = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM_SLOT + 16;
   static constexpr int DYN_BYTES = TOTAL;  // the dynamic smem window starts 1024-byte aligned (checked in GemmCtx)
@@ -94,6 +94,7 @@ struct GemmCtx {
   uint64_t* tmem_full;
   uint64_t* tmem_empty;
   uint64_t* aux;  // two spare barriers for the epilogue groups (residual / auxiliary tile loads)
+  uint64_t* rs;   // [0] full / [1] empty of the per-row scale vector (LayerNorm-folding GEMMs, filled by warp 3)
   uint32_t* tmem_slot;
   int rank;           // CTA rank inside the pair (0 when !PAIR)
   int first, stride;  // first work item and stride of this CTA (pair)
@@ -110,6 +111,7 @@ struct GemmCtx {
     tmem_full = bars + 2 * L::STAGES;
     tmem_empty = bars + 2 * L::STAGES + 2;
     aux = bars + 2 * L::STAGES + 4;
+    rs = bars + 2 * L::STAGES + 6;
     tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM_SLOT);
     if (L::kPair) {
       rank = static_cast<int>(cluster_ctarank());
@@ -152,6 +154,7 @@ __device__ __forceinline__ uint32_t gemm_prologue(const GemmCtx<BN, L>& cx, cons
       mbar_init(&cx.tmem_full[i], 1);
       mbar_init(&cx.tmem_empty[i], L::kPair ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);
       mbar_init(&cx.aux[i], 1);
+      mbar_init(&cx.rs[i], i == 0 ? 32 : GEMM_EPI_WARPS * 32);
     }
     fence_mbar_init();
   }

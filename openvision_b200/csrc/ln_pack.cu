@@ -1,0 +1,106 @@
+// Weight packing for LayerNorm folded into the projection that consumes it (transformer.py:254-265: attn(ln_1(x)),
+// mlp(ln_2(x)); LayerNorm: transformer.py:15-30).
+//
+//   ln(x) W^T + b = rstd * ((x - mu) (W.gamma)^T) + (W beta + b)
+//                 = rstd * (x Wc^T) + d        with  Wc[n][k] = W[n][k] gamma[k] - mean_k(W[n][.] gamma[.]),  d = W beta + b
+//
+// because sum_k Wc[n][k] = 0 makes x Wc^T blind to the row mean of x: the GEMM reads the un-normalised residual stream,
+// the mean never has to be subtracted, and the epilogue only scales by the row's rstd (ovk_gemm_bf16_ln).
+//
+// Wc is stored in bf16, and rounding breaks sum_k Wc = 0 by r_n ~ 2^-9 |w| sqrt(K), which would leak mu * rstd * r_n
+// into the output.  After round-to-nearest the kernel therefore walks each row once more and moves a few entries to the
+// ADJACENT bf16 value in the direction that cancels the residual (only entries whose rounding error already pointed
+// that way by more than a quarter ulp, so no entry ends up further than 3/4 ulp from its exact value), until
+// |sum_k Wc_bf16| is below half an ulp of the entries.  The leak drops to ~1e-4 * |mu| / sigma of the output scale.
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace ovk {
+
+template <typename TW>
+__device__ __forceinline__ float ldw(const TW* p);
+template <>
+__device__ __forceinline__ float ldw<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float ldw<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t b) { return __uint_as_float(b << 16); }
+
+// one warp per weight row
+template <typename TW>
+__global__ void __launch_bounds__(128) ln_pack_kernel(const TW* __restrict__ W, long long ldw_, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      __nv_bfloat16* __restrict__ Wc, long long ldwc, float* __restrict__ d,
+                                                      int N, int K) {
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  const TW* w = W + static_cast<long long>(n) * ldw_;
+  unsigned short* q = reinterpret_cast<unsigned short*>(Wc + static_cast<long long>(n) * ldwc);
+  // pass 1: row mean of W.gamma and d = W beta + b
+  float sg = 0.f, sb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = ldw<TW>(w + k);
+    sg = fmaf(wv, gamma[k], sg);
+    sb = fmaf(wv, beta[k], sb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sg += __shfl_xor_sync(0xffffffffu, sg, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  const float mean = sg / static_cast<float>(K);
+  if (lane == 0) d[n] = sb + (bias != nullptr ? bias[n] : 0.f);
+  // pass 2: round to nearest, residual of the rounded row
+  float r = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float v = fmaf(ldw<TW>(w + k), gamma[k], -mean);
+    const unsigned short b = static_cast<unsigned short>(pack_bf16x2(v, 0.f) & 0xFFFFu);
+    q[k] = b;
+    r += bf16_bits_to_float(b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  __syncwarp();
+  // pass 3 (lane 0, serial): cancel the residual with one-ulp moves
+  if (lane == 0) {
+    for (int k = 0; k < K && r != 0.f; ++k) {
+      const uint32_t b = q[k];
+      if ((b & 0x7FFFu) == 0 || (b & 0x7F80u) == 0x7F80u) continue;   // zero, inf / nan: leave alone
+      const float qv = bf16_bits_to_float(b);
+      // the adjacent value in the direction that reduces r: down (towards -inf) if r > 0, up if r < 0
+      const bool down = r > 0.f;
+      const bool shrink = (qv > 0.f) == down;                          // magnitude decreases
+      const uint32_t nb = shrink ? b - 1 : b + 1;
+      if ((nb & 0x7F80u) == 0x7F80u) continue;
+      const float nv = bf16_bits_to_float(nb);
+      const float delta = nv - qv;                                     // sign opposite to r
+      if (fabsf(delta) >= 2.f * fabsf(r)) continue;                    // the move would overshoot
+      const float v = fmaf(ldw<TW>(w + k), gamma[k], -mean);
+      const float e = v - qv;                                          // rounding error of this entry
+      if (e * delta < 0.25f * delta * delta) continue;                 // only entries already off in that direction
+      q[k] = static_cast<unsigned short>(nb);
+      r += delta;
+    }
+  }
+}
+
+}  // namespace ovk
+
+using namespace ovk;
+
+extern "C" int ovk_pack_ln_linear(const void* W, int w_is_f32, long long ldw, const float* gamma, const float* beta,
+                                  const float* bias, void* Wc, long long ldwc, float* d, int N, int K, void* stream) {
+  if (N <= 0 || K <= 0) return set_error(OVK_ERR_SHAPE, "pack_ln_linear: empty weight");
+  if (W == nullptr || gamma == nullptr || beta == nullptr || Wc == nullptr || d == nullptr)
+    return set_error(OVK_ERR_SHAPE, "pack_ln_linear: null pointer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (N + 3) / 4;
+  if (w_is_f32)
+    ln_pack_kernel<float><<<grid, 128, 0, s>>>(reinterpret_cast<const float*>(W), ldw, gamma, beta, bias,
+                                               reinterpret_cast<__nv_bfloat16*>(Wc), ldwc, d, N, K);
+  else
+    ln_pack_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(W), ldw, gamma, beta, bias,
+                                                       reinterpret_cast<__nv_bfloat16*>(Wc), ldwc, d, N, K);
+  return check_launch("ln_pack_kernel");
+}

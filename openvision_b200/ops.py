@@ -110,13 +110,13 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
     return out
 
 
-def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
             row_stats: Optional[torch.Tensor] = None, eps: float = 1e-6, residual: Optional[torch.Tensor] = None,
             act: Optional[str] = None, out: Optional[torch.Tensor] = None, preact_out: Optional[torch.Tensor] = None,
             stats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """GEMM with LayerNorm folded in and / or row statistics out (kernel: gemm_bf16_kernel<..., FUSE>):
-       out = act(rstd * (a @ w^T - mu * colsum) + bias) (+ residual); (mu, rstd) come from row_stats [P,M,2], partial
-       (sum, sum sq) of the rows of a.  stats_out [ceil(N/128),M,2] fp32 receives the same statistics of the output rows."""
+       out = act(rstd * (a @ w^T) + bias) (+ residual), w and bias from pack_ln_linear, rstd from row_stats [P,M,2], the
+       partial (sum, sum sq) of the rows of a.  stats_out [ceil(N/128),M,2] fp32 receives the statistics of the output."""
     _require(a, torch.bfloat16, "gemm_ln.a", 2)
     _require(w, torch.bfloat16, "gemm_ln.w", 2)
     M, K = a.shape
@@ -129,14 +129,11 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     if bias is not None:
         _require(bias, torch.float32, "gemm_ln.bias", 1)
         flags |= EPI_BIAS
-    if (row_stats is None) != (colsum is None):
-        raise OvkError("gemm_ln: row_stats and colsum come together")
     parts = 0
     if row_stats is not None:
         _require(row_stats, torch.float32, "gemm_ln.row_stats", 3)
-        _require(colsum, torch.float32, "gemm_ln.colsum", 1)
-        if tuple(row_stats.shape[1:]) != (M, 2) or not row_stats.is_contiguous() or colsum.numel() != N:
-            raise OvkError("gemm_ln: row_stats must be contiguous [P, M, 2] and colsum [N]")
+        if tuple(row_stats.shape[1:]) != (M, 2) or not row_stats.is_contiguous():
+            raise OvkError("gemm_ln: row_stats must be contiguous [P, M, 2]")
         parts = row_stats.shape[0]
     ldr = 0
     if residual is not None:
@@ -154,10 +151,31 @@ def gemm_ln(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
             raise OvkError("gemm_ln: stats_out must be contiguous [ceil(N/128), M, 2]")
     with _timed("gemm", 2.0 * M * N * K):
         _lib.call("ovk_gemm_bf16_ln", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
-                  _p(colsum), _p(row_stats), parts, float(eps), _p(residual), ldr, _p(preact_out), ldp, _p(stats_out), flags,
+                  _p(row_stats), parts, float(eps), _p(residual), ldr, _p(preact_out), ldp, _p(stats_out), flags,
                   _stream())
     _count()
     return out
+
+
+def pack_ln_linear(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor] = None):
+    """(Wc bf16 [N,K], d fp32 [N]) with ln(x) w^T + bias = rstd * (x Wc^T) + d: Wc = w.gamma with every row centred to zero
+    sum (also after bf16 rounding), d = w beta + bias.  Kernel: ln_pack_kernel."""
+    if w.dtype not in (torch.float32, torch.bfloat16) or w.dim() != 2 or not w.is_cuda or w.stride(1) != 1:
+        raise OvkError("pack_ln_linear: w must be a CUDA fp32 / bf16 matrix with unit inner stride")
+    N, K = w.shape
+    _require(gamma, torch.float32, "pack_ln_linear.gamma", 1)
+    _require(beta, torch.float32, "pack_ln_linear.beta", 1)
+    if bias is not None:
+        _require(bias, torch.float32, "pack_ln_linear.bias", 1)
+    if gamma.numel() != K or beta.numel() != K or (bias is not None and bias.numel() != N):
+        raise OvkError("pack_ln_linear: gamma / beta must have K entries, bias N")
+    wc = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
+    d = torch.empty((N,), dtype=torch.float32, device=w.device)
+    with _timed("pack", 4.0 * N * K):
+        _lib.call("ovk_pack_ln_linear", _p(w), 1 if w.dtype == torch.float32 else 0, w.stride(0), _p(gamma), _p(beta),
+                  _p(bias), _p(wc), wc.stride(0), _p(d), N, K, _stream())
+    _count()
+    return wc, d
 
 
 def row_stats(x: torch.Tensor) -> torch.Tensor:

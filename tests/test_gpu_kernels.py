@@ -279,7 +279,7 @@ LN_GEMM_CASES = [
 @pytest.mark.parametrize("M,D,N,act", LN_GEMM_CASES)
 def test_gemm_ln_fold_matches_layernorm_then_linear(ops, M, D, N, act):
     """Producer GEMM (+bias +residual) emits the row statistics of what it writes; the consumer GEMM reads the
-    un-normalised rows and applies ln(x) W^T + b through rstd (x (W.gamma)^T - mu c) + d.  Checked against the oracle's
+    un-normalised rows and applies ln(x) W^T + b through rstd (x Wc^T) + d with row-centred Wc.  Checked against the oracle's
     LayerNorm (oc/transformer.py:24-30) followed by F.linear (+ activation)."""
     eps = 1e-6
     # producer: x = a w0^T + b0 + r, with a per-row offset and scale so that mean and variance differ row to row
@@ -295,8 +295,8 @@ def test_gemm_ln_fold_matches_layernorm_then_linear(ops, M, D, N, act):
     assert_close(x, x_ref, 1e-2, "producer output")
     xs = x.float()
     s = st.sum(0)
-    assert_close(s[:, 0], xs.sum(1), 2e-5 * math.sqrt(D), "row sums")        # of the ROUNDED values it wrote
-    assert_close(s[:, 1], (xs * xs).sum(1), 1e-5, "row sums of squares")
+    assert_close(s[:, 0], x_ref.sum(1), 1e-4, "row sums")                    # of the values before bf16 rounding
+    assert_close(s[:, 1], (x_ref * x_ref).sum(1), 1e-4, "row sums of squares")
     st1 = ops.row_stats(x)
     assert tuple(st1.shape) == (1, M, 2)
     assert_close(st1[0, :, 0], xs.sum(1), 2e-5 * math.sqrt(D), "row_stats sums")
@@ -306,12 +306,17 @@ def test_gemm_ln_fold_matches_layernorm_then_linear(ops, M, D, N, act):
     beta = 0.1 * rnd(D, seed=8)
     w = rnd(N, D, seed=9, scale=0.05)
     b = rnd(N, seed=10)
-    wg = (w * gamma[None, :]).bfloat16()
-    c = wg.float().sum(1)
-    d = w @ beta + b
+    wc, d = ops.pack_ln_linear(w.cuda(), gamma.cuda(), beta.cuda(), b.cuda())
+    wg = w * gamma[None, :]
+    wc_ref = wg - wg.mean(1, keepdim=True)
+    assert_close(d, w @ beta + b, 1e-5, "packed bias")
+    ulp = torch.maximum(wc_ref.abs(), torch.tensor(1e-30)).log2().floor().exp2() * 2.0 ** -7
+    assert ((wc.float().cpu() - wc_ref).abs() <= 0.76 * ulp + 1e-9).all(), "packed weights stay within 3/4 ulp"
+    rowsum = wc.float().sum(1).abs().cpu()
+    assert (rowsum <= wc_ref.abs().amax(1) * 2.0 ** -8).all(), "rounded rows still sum to ~0 (below half an ulp of the largest entry)"
     pre = torch.empty((M, N), dtype=torch.bfloat16, device="cuda") if act else None
     for stats in (st, st1):
-        y = ops.gemm_ln(x, wg.cuda(), bias=d.cuda(), colsum=c.cuda(), row_stats=stats, eps=eps, act=act, preact_out=pre)
+        y = ops.gemm_ln(x, wc, bias=d, row_stats=stats, eps=eps, act=act, preact_out=pre)
         h = O.layer_norm(xs.cpu(), gamma, beta, eps)
         ref = h @ w.t() + b
         if act:
@@ -330,8 +335,8 @@ def test_gemm_ln_rejects_bad_arguments(ops):
     from openvision_b200._lib import OvkError
     with pytest.raises(OvkError):   # statistics need N > 128
         ops.gemm_ln(a, w, stats_out=torch.zeros(1, 128, 2, device="cuda"))
-    with pytest.raises(OvkError):   # colsum without row statistics
-        ops.gemm_ln(a, w, colsum=torch.zeros(128, device="cuda"))
+    with pytest.raises(OvkError):   # more partial-sum slots than the epilogue holds
+        ops.gemm_ln(a, w, row_stats=torch.zeros(65, 128, 2, device="cuda"))
 
 
 @pytest.mark.parametrize("L", [129, 257, 385, 513])

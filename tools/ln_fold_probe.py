@@ -15,7 +15,6 @@ wo = (torch.randn(D, D, device=dev, generator=g) * 0.02).bfloat16()
 w1 = (torch.randn(4 * D, D, device=dev, generator=g) * 0.02).bfloat16()
 w2 = (torch.randn(D, 4 * D, device=dev, generator=g) * 0.02).bfloat16()
 bq, bo, b1, b2 = (torch.zeros(n, device=dev) for n in (3 * D, D, 4 * D, D))
-cq, c1 = torch.ones(3 * D, device=dev), torch.ones(4 * D, device=dev)
 st = ops.row_stats(x)
 st8 = torch.empty(8, M, 2, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -39,13 +38,13 @@ qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
 y = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
 u = torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)
 timeit("qkv plain", lambda: ops.gemm(x, wq, bias=bq, out=qkv), 2.0 * M * D * 3 * D)
-timeit("qkv ln-fold (1 slot)", lambda: ops.gemm_ln(x, wq, bias=bq, colsum=cq, row_stats=st, out=qkv), 2.0 * M * D * 3 * D)
-timeit("qkv ln-fold (8 slots)", lambda: ops.gemm_ln(x, wq, bias=bq, colsum=cq, row_stats=st8, out=qkv), 2.0 * M * D * 3 * D)
+timeit("qkv ln-fold (1 slot)", lambda: ops.gemm_ln(x, wq, bias=bq, row_stats=st, out=qkv), 2.0 * M * D * 3 * D)
+timeit("qkv ln-fold (8 slots)", lambda: ops.gemm_ln(x, wq, bias=bq, row_stats=st8, out=qkv), 2.0 * M * D * 3 * D)
 timeit("qkv FUSE kernel, no fold", lambda: ops.gemm_ln(x, wq, bias=bq, out=qkv), 2.0 * M * D * 3 * D)
 timeit("out+res plain", lambda: ops.gemm(x, wo, bias=bo, residual=y, out=y), 2.0 * M * D * D)
 timeit("out+res stats", lambda: ops.gemm_ln(x, wo, bias=bo, residual=y, out=y, stats_out=st8), 2.0 * M * D * D)
 timeit("fc1 gelu plain", lambda: ops.gemm(x, w1, bias=b1, act="gelu", out=u), 2.0 * M * D * 4 * D)
-timeit("fc1 gelu ln-fold", lambda: ops.gemm_ln(x, w1, bias=b1, colsum=c1, row_stats=st8, act="gelu", out=u), 2.0 * M * D * 4 * D)
+timeit("fc1 gelu ln-fold", lambda: ops.gemm_ln(x, w1, bias=b1, row_stats=st8, act="gelu", out=u), 2.0 * M * D * 4 * D)
 timeit("fc2+res plain", lambda: ops.gemm(f, w2, bias=b2, residual=y, out=y), 2.0 * M * D * 4 * D)
 timeit("fc2+res stats", lambda: ops.gemm_ln(f, w2, bias=b2, residual=y, out=y, stats_out=st8), 2.0 * M * D * 4 * D)
 timeit("layernorm", lambda: ops.layernorm(x, gam, bet, 1e-6, out=y), 0.0)
