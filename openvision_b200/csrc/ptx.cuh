@@ -59,11 +59,32 @@ static __device__ __noinline__ void hang_trap(int code) {
          blockIdx.z, threadIdx.x, code);
   __trap();
 }
+// try_wait with a suspend-time hint (ns): the thread may sleep in hardware until the phase completes or the hint expires,
+// instead of coming back to the issue port every ~100 cycles.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+// Waiting warps share issue ports with the warps doing the work, so the poll loop is kept to a handful of instructions:
+// the hang guard counts polls (each poll sleeps up to OVK_WAIT_HINT_NS in hardware) instead of reading the clock.
+#ifndef OVK_WAIT_HINT_NS
+#define OVK_WAIT_HINT_NS 2000u
+#endif
+#ifndef OVK_HANG_GUARD_POLLS
+#define OVK_HANG_GUARD_POLLS (1u << 23)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > OVK_HANG_GUARD_CYCLES) hang_trap(code);
+  uint32_t polls = 0;
+  while (!mbar_try_wait_hint(bar, parity, OVK_WAIT_HINT_NS)) {
+    if (++polls > OVK_HANG_GUARD_POLLS) hang_trap(code);
   }
 }
 
