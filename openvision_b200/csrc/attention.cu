@@ -60,6 +60,7 @@ constexpr int ATT_TMEM_COLS = 256;  // S: [0,128)  O: [128,192)  O_b: [192,208) 
 constexpr uint32_t ATT_TMEM_OT = 208;   // remainder query row: O_t^T (lane = head dim, column 0)
 constexpr uint32_t ATT_TMEM_ST = 224;   // remainder query row: S_t^T (lane = key of the block, column 0)
 constexpr uint32_t ATT_TMEM_X = 240;    // half-row maxima exchanged between the two threads of a row
+constexpr uint32_t ATT_TMEM_SK = 192;   // scores of the tile's rows against the remainder key (column 0; hd = 64 only)
 constexpr uint32_t ATT_TMEM_S = 0;
 constexpr uint32_t ATT_TMEM_O = 128;
 
@@ -113,7 +114,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     tma_prefetch_desc(&tmO);
     tma_prefetch_desc(&tmTail);
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1 + (L > Lm ? 32 * ATT_SM_WARPS : 0));  // MMA commit (+ the softmax threads' read of Q for remainder keys)
+    mbar_init(q_empty, 1 + (tail_q ? 2 : 0));  // MMA commit (+ two softmax warps' read of the remainder query / key rows)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -168,41 +169,58 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
       int n = 0, g = 0;
+      // Issue order per item: S(0) | S(1) P V(0) | S(2) P V(1) | ... | P V(last).  S(j+1) goes out BEFORE P V(j): both
+      // wait for the same event (the softmax warps are done with S(j)), and the softmax warps need S(j+1) first —
+      // P V(j) only has to be finished before they overwrite P again.
+      auto issue_s = [&](int j, int gg, bool titem) {
+        const int s = gg % NS;
+        const int valid = min(ATT_BKV, Lm - j * ATT_BKV);
+        const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
+        const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+        mbar_wait(&k_full[s], (gg / NS) & 1, 13);
+        tc_fence_after();
+        const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, nblk, 0, 0);
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) {
+          umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
+                       umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
+        }
+        if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
+          umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + LL::OFF_QB)),
+                       umma_desc_sw32(smem_u32(smem + LL::OFF_KB + s * ATT_BT)), idesc_s, 1);
+        if (RB == 0 && ntail > 0 && j == 0) {   // scores against the remainder key: s_k = Q k_t^T (N = 16, column 0 is real)
+          constexpr uint32_t idesc_sk = umma_idesc_bf16(128, 16, 0, 0);
+          const uint32_t kt_addr = smem_u32(smem + LL::OFF_TAIL);
+#pragma unroll
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + ATT_TMEM_SK, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_row0(kt_addr + k * 32),
+                         idesc_sk, k != 0);
+        }
+        if (titem) {   // S_t^T = K_j q_t^T
+          constexpr uint32_t idesc_st = umma_idesc_bf16(128, 16, 0, 0);
+          const uint32_t qr_addr = smem_u32(smem + LL::OFF_QR);
+#pragma unroll
+          for (int k = 0; k < ATT_HD / 16; ++k)
+            umma_bf16_ss(tmem_base + ATT_TMEM_ST, umma_desc_kmajor_sw128(k_addr + k * 32), umma_desc_row0(qr_addr + k * 32),
+                         idesc_st, k != 0);
+        }
+        umma_commit(&k_empty[s]);
+        umma_commit(s_full);
+        if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
+      };
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
         const bool titem = tail_q && item % nq == nq - 1;
         mbar_wait(q_full, n & 1, 12);
+        issue_s(0, g, titem);   // the S columns are free: p_ready of the previous item's last block was waited on below
         for (int j = 0; j < nkv; ++j, ++g) {
           const int s = g % NS;
           const uint32_t ph = (g / NS) & 1;
           const int valid = min(ATT_BKV, Lm - j * ATT_BKV);
-          const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
-          const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+          const int nblk = (valid + 15) & ~15;
           const uint32_t v_addr = smem_u32(sV + s * ATT_TILE_BYTES);
-          // S = Q K_j^T   (the S columns are free: p_ready of the previous block was waited on below)
-          mbar_wait(&k_full[s], ph, 13);
-          tc_fence_after();
-          const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, nblk, 0, 0);
-#pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k) {
-            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
-                         umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
-          }
-          if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
-            umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + LL::OFF_QB)),
-                         umma_desc_sw32(smem_u32(smem + LL::OFF_KB + s * ATT_BT)), idesc_s, 1);
-          if (titem) {   // S_t^T = K_j q_t^T
-            constexpr uint32_t idesc_st = umma_idesc_bf16(128, 16, 0, 0);
-            const uint32_t qr_addr = smem_u32(smem + LL::OFF_QR);
-#pragma unroll
-            for (int k = 0; k < ATT_HD / 16; ++k)
-              umma_bf16_ss(tmem_base + ATT_TMEM_ST, umma_desc_kmajor_sw128(k_addr + k * 32), umma_desc_row0(qr_addr + k * 32),
-                           idesc_st, k != 0);
-          }
-          umma_commit(&k_empty[s]);
-          umma_commit(s_full);
-          if (j == nkv - 1) umma_commit(q_empty);  // Q tile no longer needed: the producer may fetch the next item's
+          mbar_wait(p_ready, g & 1, 14);    // softmax(j) done: S may be overwritten, P(j) is in shared memory
+          if (j + 1 < nkv) issue_s(j + 1, g + 1, titem);
           // O += P V_j   (P: K-major [128 x nblk] in two 64-column swizzle atoms; V: MN-major [nblk x 64])
-          mbar_wait(p_ready, g & 1, 14);
           mbar_wait(&v_full[s], ph, 15);
           if (j == 0) mbar_wait(o_free, (n & 1) ^ 1, 8);  // previous item's epilogue has read the O accumulator
           tc_fence_after();
@@ -258,43 +276,37 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       named_bar_sync(1, SMT);
       float m_ref = -INFINITY;  // exponent reference (log2 domain, already scaled), identical in both halves of a row
       float l = 0.f;            // this half's running sum of 2^(s - m_ref)
-      // Remainder keys [Lm, L) (e.g. the 257th token): their scores are a 64-long dot product per query row, computed
-      // here on the FMA pipe while the first S MMA runs, and folded into the output in the epilogue — instead of a
-      // whole extra TMA -> MMA -> softmax -> MMA round for a 1-column block.
+      // Remainder key (the 257th token): its scores against the tile's rows come out of a small N = 16 MMA issued with
+      // S(0) (one TMEM word per thread), and it is folded into the output in the epilogue — instead of a whole extra
+      // TMA -> MMA -> softmax -> MMA round for a 1-column block.
       float s_tail = 0.f;
       // remainder query row (handled by the threads of column-half 0): reference, partial sum, score against the remainder key
       const bool titem = tail_q && qt == nq - 1 && half == 0;
       float m_t = -INFINITY, l_t = 0.f, s_tt = 0.f;
-      if (ntail > 0) {
+      if (tail_q && half == 0 && quad < 2) {   // q_t . k_t, two dims per lane (the warps that finish the remainder row)
         mbar_wait(q_full, n & 1, 19);
-        const uint32_t kt = smem_u32(smem + LL::OFF_TAIL);
-        float d = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 qv = lds128(smem_u32(sQ) + sw128_offset(r, c));
-          const uint4 kv = lds128(kt + c * 16);
-          d = fmaf(bf16_lo(qv.x), bf16_lo(kv.x), d); d = fmaf(bf16_hi(qv.x), bf16_hi(kv.x), d);
-          d = fmaf(bf16_lo(qv.y), bf16_lo(kv.y), d); d = fmaf(bf16_hi(qv.y), bf16_hi(kv.y), d);
-          d = fmaf(bf16_lo(qv.z), bf16_lo(kv.z), d); d = fmaf(bf16_hi(qv.z), bf16_hi(kv.z), d);
-          d = fmaf(bf16_lo(qv.w), bf16_lo(kv.w), d); d = fmaf(bf16_hi(qv.w), bf16_hi(kv.w), d);
-        }
-        s_tail = d * scale_log2;
-        if (titem && quad < 2) {   // q_t . k_t, two dims per lane
+        if (titem) {
           uint32_t qa, ka;
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(qa) : "r"(smem_u32(smem + LL::OFF_QR) + 4 * lane));
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ka) : "r"(kt + 4 * lane));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ka) : "r"(smem_u32(smem + LL::OFF_TAIL) + 4 * lane));
           float e = fmaf(bf16_lo(qa), bf16_lo(ka), bf16_hi(qa) * bf16_hi(ka));
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
           s_tt = e * scale_log2;
         }
-        mbar_arrive(q_empty);
+        if (lane == 0) mbar_arrive(q_empty);
       }
       for (int j = 0; j < nkv; ++j, ++g) {
         const int valid = min(ATT_BKV, Lm - j * ATT_BKV) - 64 * half;   // valid columns of this half (may be <= 0)
         const int nblk = ((min(ATT_BKV, Lm - j * ATT_BKV) + 15) & ~15) - 64 * half;
         mbar_wait(s_full, g & 1, 16);
         tc_fence_after();
+        if (RB == 0 && ntail > 0 && j == 0) {   // this row against the remainder key (out of the small s_k MMA)
+          uint32_t u;
+          tmem_ld_x1(tmem_base + t_lane + ATT_TMEM_SK, u);
+          tmem_ld_wait();
+          s_tail = __uint_as_float(u) * scale_log2;
+        }
         // pass 1: half-row maximum (two 32-column TMEM loads; the scores are re-read in pass 2 to stay within the
         // 96-register budget that two resident CTAs of 320 threads allow)
         float mx = -INFINITY;
