@@ -365,7 +365,18 @@ def run_ours(args):
     e2e_value = world * batch * args.steps / (e2e_ms / 1e3)
 
     ksum = rec.summary()
-    loss_line = bench_loss(torch, ovb, args.loss_batch, 768, world, rank, max(3, args.steps), max(3, args.warmup), peaks)
+    if args.profile_range:
+        # one forward step + a short loss leg between cudaProfilerStart / Stop: `ncu --profile-from-start off` sees exactly
+        # these launches, whatever the warm-up and step counts were (numbers printed by a run under ncu are not bench values)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        loss_line = bench_loss(torch, ovb, args.loss_batch, 768, world, rank, 1, 1, peaks)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+    else:
+        loss_line = bench_loss(torch, ovb, args.loss_batch, 768, world, rank, max(3, args.steps), max(3, args.warmup), peaks)
 
     if rank == 0:
         gm = ksum.get("gemm", dict(launches=0, total_ms=0.0, total_work=0.0))
@@ -497,6 +508,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step (BASELINE config: 1024)")
     ap.add_argument("--loss-batch", type=int, default=32768, help="global batch of the contrastive-loss leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket one forward step + a short loss leg with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--workload", default="l14_fwd", choices=["l14_fwd", "b16_384_train", "h14_train", "l14_train"],
                     help="l14_fwd = the headline benchmark (default); *_train = extra fwd+bwd(+loss) workloads")
     ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per block (train workloads)")

@@ -8,13 +8,13 @@ echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | 
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke_${TAG}.log
 echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
 echo "== ncu launch list"
-NCU_CMD="python bench.py --steps 1 --warmup 3 --batch 1024 --no-cpu-baseline --loss-batch 8192"
+NCU_CMD="python bench.py --steps 1 --warmup 3 --batch 1024 --no-cpu-baseline --loss-batch 8192 --profile-range"
 timeout 600 $NCU_CMD > gpurun_out/plain_${TAG}.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 530 -c 190 --csv --log-file gpurun_out/launches_${TAG}.csv $NCU_CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $NCU_CMD > gpurun_out/ncu_launches_${TAG}.log 2>&1
 echo "ncu launches rc=$?"
 echo "== ncu full (top kernel)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 100 -c 4 -o gpurun_out/prof_gemm_${TAG} $NCU_CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16 -s 1 -c 5 -o gpurun_out/prof_gemm_${TAG} $NCU_CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"attention_fwd|clip_loss_fwd|clip_loss_grad" -s 30 -c 3 -o gpurun_out/prof_attn_loss_${TAG} $NCU_CMD > gpurun_out/ncu_full2_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attention_fwd|clip_loss_fwd|clip_loss_grad|layernorm|row_stats" -s 1 -c 8 -o gpurun_out/prof_attn_loss_${TAG} $NCU_CMD > gpurun_out/ncu_full2_${TAG}.log 2>&1
 echo "ncu full (attention/loss) rc=$?"
 ls -la gpurun_out | tail -20
