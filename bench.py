@@ -248,6 +248,65 @@ def bench_loss(torch, ovb, n_global, embed, world, rank, steps, warmup, peaks):
             "achieved_tflops_per_gpu": tf, "frac_of_measured_sustained": tf / peaks["tf_sustained"]}
 
 
+def torch_eager_throughput(torch, cfg, sample_batch: int, iters: int = 3):
+    """Comparison point of SURVEY.md §8(d): what the reference's modules ARE on a GPU — stock torch.nn building blocks
+    (nn.Conv2d patch embed, nn.LayerNorm, nn.MultiheadAttention, nn.Linear, nn.GELU; transformer.py:210-265,609-651) run
+    eagerly in bf16 (cuBLAS / cuDNN / ATen kernels) on the same box.  None of this repo's kernels or modules is involved;
+    reported next to `value` as a baseline, never used by the product path."""
+    nn, F = torch.nn, torch.nn.functional
+    v = cfg["vision"]
+    D, P, size, layers = v["width"], v["patch_size"], v["image_size"], v["layers"]
+    H, E = D // v["head_width"], cfg["embed_dim"]
+    n_tok = (size // P) ** 2
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ln_1, self.ln_2 = nn.LayerNorm(D, eps=1e-6), nn.LayerNorm(D, eps=1e-6)
+            self.attn = nn.MultiheadAttention(D, H, batch_first=True)
+            self.c_fc, self.c_proj, self.gelu = nn.Linear(D, 4 * D), nn.Linear(4 * D, D), nn.GELU()
+
+        def forward(self, x):
+            h = self.ln_1(x)
+            x = x + self.attn(h, h, h, need_weights=False)[0]
+            return x + self.c_proj(self.gelu(self.c_fc(self.ln_2(x))))
+
+    class Tower(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, D, P, P, bias=False)
+            self.cls = nn.Parameter(torch.randn(D) * D ** -0.5)
+            self.pos = nn.Parameter(torch.randn(n_tok + 1, D) * D ** -0.5)
+            self.blocks = nn.ModuleList([Block() for _ in range(layers)])
+            self.ln_post = nn.LayerNorm(D, eps=1e-6)
+            self.proj = nn.Parameter(torch.randn(D, E) * D ** -0.5)
+
+        def forward(self, img):
+            x = self.conv1(img).flatten(2).transpose(1, 2)
+            x = torch.cat([self.cls.expand(x.shape[0], 1, -1).to(x.dtype), x], 1) + self.pos.to(x.dtype)
+            for b in self.blocks:
+                x = b(x)
+            return F.normalize(self.ln_post(x[:, 1:].mean(1)) @ self.proj, dim=-1)
+
+    torch.manual_seed(0)
+    tower = Tower().cuda().to(torch.bfloat16).eval()
+    img = torch.randn(sample_batch, 3, size, size, device="cuda").to(torch.bfloat16)
+    with torch.no_grad():
+        for _ in range(2):
+            tower(img)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            tower(img)
+        e.record()
+        torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    del tower, img
+    torch.cuda.empty_cache()
+    return sample_batch / ms * 1e3
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -388,8 +447,12 @@ def run_ours(args):
                              ("achieved_tflops" if kind in ("gemm", "attention") else "achieved_gbs"):
                                  per if kind in ("gemm", "attention") else per * 1e3}
         cpu_val, cpu_cores, cpu_times = (None, None, None)
+        eager_val = None
         if not args.no_cpu_baseline:
             cpu_val, cpu_cores, cpu_times = cpu_port_throughput(8, 3, 1)
+            del images_dev, bufs[:]
+            torch.cuda.empty_cache()
+            eager_val = torch_eager_throughput(torch, cfg, 256)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -412,6 +475,9 @@ def run_ours(args):
                     "api": "CLIP.encode_image(images, normalize=True); every step's fp32 NCHW batch comes from pinned host memory "
                            "(H2D of batch i+1 double-buffered under the encode of batch i), embeddings read back to the host"},
             "gpu_launches": launches, "clocks": clocks,
+            "torch_eager_gpu": {"value": eager_val, "unit": UNIT, "sample": "256-image batches, bf16, stock torch.nn modules "
+                                "(Conv2d / LayerNorm / MultiheadAttention / Linear / GELU) run eagerly on the same GPU: what the "
+                                "reference's PyTorch path is on a B200 (SURVEY.md 8(d) comparison point); baseline only"},
         }
         if loss_line is not None:
             line["clip_loss"] = loss_line
