@@ -633,6 +633,8 @@ attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 
 using namespace ovk;
 
+int ovk_attention_fwd2_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
+
 extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
                                  void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention: empty problem");
@@ -641,6 +643,16 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   const bool ext = hd > ATT_HD;   // 64 < hd <= 80: extra 16-dim operand block (zero-filled past hd by TMA)
   if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention: B and H must be <= 65535");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // head width 64 and an even number of 128-row query tiles (L = 257: two): the pair kernel of attention2.cu, which fetches
+  // K / V once for two query tiles.  With an odd tile count one of its two softmax groups would idle for a whole item, and
+  // this file's kernel (one tile per CTA, two CTAs per SM) is faster.  OVK_ATT_V1=1 forces this file's kernel (A/B runs).
+  const char* att_env = getenv("OVK_ATT_V1");   // read per call so that tools/ab_probe.py can alternate the two kernels
+  const bool force_v1 = att_env != nullptr && att_env[0] == '1';
+  {
+    const int t2 = (L > ATT_BQ && L % ATT_BQ == 1) ? 1 : 0;
+    const int nq2 = (L - t2 + ATT_BQ - 1) / ATT_BQ;
+    if (!ext && !force_v1 && L <= 4096 && nq2 % 2 == 0) return ovk_attention_fwd2_launch(qkv, out, lse, B, L, H, scale, s);
+  }
   CUtensorMap tmQKV, tmO, tmTail, tmQKVb, tmOb;
   int rc;
   {
