@@ -489,7 +489,8 @@ def run_ours(args):
 def run_train(args):
     """Extra workloads (BASELINE.json configs[2] / configs[4]; not the headline line): image tower fwd+bwd (+ contrastive
     loss fwd+bwd against synthetic text embeddings) per step; with N > 1 ranks the loss runs its NCCL exchange and the
-    tower gradients are all-reduced (plain NCCL, flattened per dtype) inside the timed region."""
+    tower gradients are all-reduced (plain NCCL on the optimizer's flat gradient buffers) and the AdamW step of the training
+    recipe (openvision_b200.optim.FlatAdamW) runs, all inside the timed region."""
     import torch
     import torch.distributed as dist
 
@@ -515,18 +516,22 @@ def run_train(args):
     txt = torch.nn.functional.normalize(torch.randn(batch, cfg["embed_dim"], device="cuda", generator=g), dim=-1)
     log_scale = torch.tensor(2.6592, device="cuda", requires_grad=True)
     crit = ovb.ClipLoss(local_loss=world > 1, gather_with_grad=world > 1, rank=rank, world_size=world)
-    params = [p for p in tower.parameters() if p.requires_grad]
+    named = list(tower.named_parameters()) + [("logit_scale", log_scale)]
+    # optimizer of the training recipe on flat buffers (build_optax.py:188-278): p.data / p.grad become views of them
+    opt = ovb.FlatAdamW(named, lr=1e-4, b1=0.9, b2=0.95, weight_decay=0.2, grad_clip_norm=1.0)
+    step_no = [0]
 
     def step():
-        for p in params:
-            p.grad = None
+        opt.zero_grad()
         feats = tower(images)
         feats = ovb.model._normalize(feats)
         loss = crit(feats, txt, log_scale.exp())
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
+            for buf in opt.grad_buffers():     # DP gradient sum over NVLink (one NCCL call per flat buffer)
+                dist.all_reduce(buf)
+        step_no[0] += 1
+        opt.step(lr_mult=ovb.cosine_schedule(step_no[0], 10000, 100), grad_scale=1.0 / world)
         return loss
 
     for _ in range(max(1, args.warmup)):
@@ -554,7 +559,8 @@ def run_train(args):
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"OpenVision ViT-{name} image tower fwd+bwd + CLIP loss fwd+bwd"
-                                       f"{' + NCCL gradient all-reduce' if world > 1 else ''}",
+                                       f"{' + NCCL gradient all-reduce' if world > 1 else ''} + AdamW step "
+                                       "(bf16 first moment, global-norm clipping, cosine schedule)",
                            "batch_per_gpu": batch, "global_batch": batch * world, "activation_checkpointing": args.checkpoint,
                            "text_features": "synthetic unit vectors (text tower not on this path)"},
                 "model_tflops_algorithmic": 3 * fl * batch / per / 1e9, "loss": float(loss.detach()),

@@ -200,6 +200,17 @@ int ovk_clip_loss_grad_logits(const void* a_loc, const void* b_all, int n_loc, i
                               float scale, const float* row_lse, const float* col_lse, float w_row, float w_col,
                               void* G, long long ldg, float* d_scale_partial, void* stream);
 
+/* Optimizer step of the training recipe (src/optim/build_optax.py:188-278: clip_by_global_norm -> scale_by_adam(b1, b2,
+ * mu_dtype=bf16) -> add_decayed_weights -> scale(lr) -> schedule -> -1; configs/openvision.py:265-289) on flat buffers:
+ *   g' = g * gscale [* max_norm / max(||g'||, max_norm) when gnorm_sq != NULL: device scalar sum g^2 over the whole model]
+ *   mu = b1 mu + (1-b1) g' (bf16 storage), nu = b2 nu + (1-b2) g'^2 (f32),
+ *   p -= lr * ((mu / (1-b1^step)) / (sqrt(nu / (1-b2^step)) + eps) + wd * p);   step counts from 1.
+ * ovk_sumsq ACCUMULATES sum x^2 into *out (zero it first). */
+int ovk_sumsq(const void* x, int is_bf16, long long n, float* out, void* stream);
+int ovk_adamw_step(void* p, int p_is_bf16, const void* g, int g_is_bf16, void* mu, float* nu, long long n, float lr,
+                   float b1, float b2, float eps, float wd, int step, float gscale, const float* gnorm_sq, float max_norm,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

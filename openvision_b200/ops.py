@@ -517,3 +517,38 @@ def act_bwd(x: torch.Tensor, dy: torch.Tensor, act: str) -> torch.Tensor:
     _lib.call("ovk_act_bwd", _p(x), _p(dy), _p(dx), x.numel(), _ACT[act], _stream())
     _count()
     return dx
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# optimizer step on flat buffers (src/optim/build_optax.py:188-278)
+# ----------------------------------------------------------------------------------------------------------------
+def sumsq(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out (fp32 scalar tensor, ACCUMULATED) += sum x^2 over a flat fp32 / bf16 buffer. Kernel: sumsq_kernel."""
+    if x.dtype not in (torch.float32, torch.bfloat16) or not x.is_cuda or not x.is_contiguous():
+        raise OvkError("sumsq: x must be a contiguous CUDA fp32 / bf16 tensor")
+    _require(out, torch.float32, "sumsq.out")
+    with _timed("optimizer", float(x.numel())):
+        _lib.call("ovk_sumsq", _p(x), 1 if x.dtype == torch.bfloat16 else 0, x.numel(), _p(out), _stream())
+    _count()
+    return out
+
+
+def adamw_step(p: torch.Tensor, g: torch.Tensor, mu: torch.Tensor, nu: torch.Tensor, lr: float, b1: float, b2: float,
+               eps: float, wd: float, step: int, gscale: float = 1.0, gnorm_sq: Optional[torch.Tensor] = None,
+               max_norm: float = 0.0) -> None:
+    """In-place scale_by_adam (bf16 first moment) + decoupled weight decay + lr on flat buffers. Kernel: adamw_kernel."""
+    for t, name in ((p, "p"), (g, "g")):
+        if t.dtype not in (torch.float32, torch.bfloat16) or not t.is_cuda or not t.is_contiguous():
+            raise OvkError(f"adamw_step: {name} must be a contiguous CUDA fp32 / bf16 tensor")
+    _require(mu, torch.bfloat16, "adamw_step.mu")
+    _require(nu, torch.float32, "adamw_step.nu")
+    n = p.numel()
+    if g.numel() != n or mu.numel() != n or nu.numel() != n:
+        raise OvkError("adamw_step: p, g, mu, nu must have the same number of elements")
+    if gnorm_sq is not None:
+        _require(gnorm_sq, torch.float32, "adamw_step.gnorm_sq")
+    with _timed("optimizer", float(n)):
+        _lib.call("ovk_adamw_step", _p(p), 1 if p.dtype == torch.bfloat16 else 0, _p(g), 1 if g.dtype == torch.bfloat16 else 0,
+                  _p(mu), _p(nu), n, float(lr), float(b1), float(b2), float(eps), float(wd), int(step), float(gscale),
+                  _p(gnorm_sq), float(max_norm), _stream())
+    _count()
