@@ -6,7 +6,7 @@ Public surface mirrors /root/reference/src/convert_upload/open_clip/{model,trans
 All compute goes through libovk.so (include/ovk.h); there is no CPU / ATen fallback.
 """
 from ._lib import OvkError, load as load_library  # noqa: F401
-from .loss import ClipLoss, gather_features  # noqa: F401
+from .loss import ClipLoss, DualCaptionClipLoss, gather_features  # noqa: F401
 from .optim import FlatAdamW, cosine_schedule  # noqa: F401
 from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, TextTransformer, convert_weights_to_lp,  # noqa: F401
                     get_cast_dtype, get_input_dtype)

@@ -177,3 +177,19 @@ class ClipLoss(nn.Module):
         total_loss = _FusedClipLoss.apply(image_features, text_features, logit_scale, self.local_loss,
                                           self.gather_with_grad, self.rank, self.world_size)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+class DualCaptionClipLoss(ClipLoss):
+    """Dual-caption contrastive loss of the training recipe (JAX side: src/losses/common.py:120-189, the functional `local_loss`
+    branch used by main_clip.py:446-465): every image is scored against TWO caption sets,
+        L = mean_ranks mean_i ( 0.5 (l_img->txt1 + l_txt1->img) + 0.5 (l_img->txt2 + l_txt2->img) ) / 2
+          = ( ClipLoss(I, T1) + ClipLoss(I, T2) ) / 2 ,
+    each term being the per-rank local-row loss (labels i + rank * n_loc), i.e. this module's `local_loss=True` mode; the
+    `pmean` over devices is the mean of the per-rank losses that data-parallel training takes anyway.  Two passes of the fused
+    kernels; the image-feature gradient is the sum of the two passes' (autograd adds them)."""
+
+    def forward(self, image_features, text_features_1, text_features_2, logit_scale, output_dict=False):
+        l1 = super().forward(image_features, text_features_1, logit_scale)
+        l2 = super().forward(image_features, text_features_2, logit_scale)
+        total = 0.5 * (l1 + l2)
+        return {"contrastive_loss": total} if output_dict else total

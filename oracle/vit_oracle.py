@@ -186,6 +186,16 @@ def clip_loss(img: Tensor, txt: Tensor, logit_scale: Tensor) -> Tensor:
     return 0.5 * (row.mean() + col.mean())
 
 
+def dual_caption_loss(img: Tensor, txt1: Tensor, txt2: Tensor, logit_scale: Tensor) -> Tensor:
+    """src/losses/common.py:139-171 on one device (rank 0 of 1): log-softmax of img . txt_k^T * t along the rows for both
+    directions and both caption sets, diagonal picked, local_loss_k = 0.5 (l_img_k + l_txt_k), mean((loss_1 + loss_2) / 2)."""
+    def one(txt):
+        zi = torch.log_softmax(logit_scale * img @ txt.t(), dim=1)
+        zt = torch.log_softmax(logit_scale * txt @ img.t(), dim=1)
+        return 0.5 * (-torch.diagonal(zi) - torch.diagonal(zt))
+    return ((one(txt1) + one(txt2)) / 2).mean()
+
+
 def clip_loss_grads(img: Tensor, txt: Tensor, logit_scale: Tensor):
     """Closed-form gradients of clip_loss: G = (P_row + P_col - 2 I) / (2N),
     dI = s G T, dT = s G^T I, d(scale) = sum(G * z) / s."""

@@ -181,3 +181,25 @@ def test_full_size_properties_32k(ops):
         d_txt_ref += scale * Gb.t() @ ad[r0:r0 + 2048]
     err = (bf.grad[:256].double() - d_txt_ref).abs().max().item()
     assert err <= 2e-2 * d_txt_ref.abs().max().item(), (err, d_txt_ref.abs().max().item())
+
+
+def test_dual_caption_loss_matches_oracle():
+    """SURVEY.md 8(f) rank 3: image vs two caption sets, (ClipLoss(I, T1) + ClipLoss(I, T2)) / 2 (losses/common.py:139-171);
+    loss and the gradients w.r.t. the image features, both caption sets and the temperature against autograd on the oracle."""
+    import openvision_b200 as ovb
+    n, e, s = 200, 64, 14.2857
+    img, t1 = _feat(n, e, 11)
+    _, t2 = _feat(n, e, 12)
+    ref_in = [x.double().requires_grad_(True) for x in (img, t1, t2)]
+    ls = torch.tensor(s, dtype=torch.float64, requires_grad=True)
+    ref = O.dual_caption_loss(*ref_in, ls)
+    ref.backward()
+    xin = [x.cuda().requires_grad_(True) for x in (img, t1, t2)]
+    scale = torch.tensor(s, device="cuda", requires_grad=True)
+    loss = ovb.DualCaptionClipLoss()(xin[0], xin[1], xin[2], scale)
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-3 * abs(float(ref))
+    for got, want, what in zip(xin, ref_in, ("d image", "d captions 1", "d captions 2")):
+        err = (got.grad.double().cpu() - want.grad).abs().max().item()
+        assert err <= 2e-2 * want.grad.abs().max().item(), (what, err)
+    assert abs(float(scale.grad) - float(ls.grad)) <= 2e-2 * abs(float(ls.grad)) + 1e-6
