@@ -4,9 +4,13 @@
 //   P = exp(S*scale - LSE),  dP = dO V^T,  D = rowsum(dO . O),  dS = P . (dP - D)
 //   dV = P^T dO,  dK = scale * dS^T Q,  dQ = scale * dS K
 // Two launches, no atomics, outputs written once as bf16 straight into the packed d(qkv) [B, L, 3, H, 64] layout that
-// the in_proj backward GEMMs read:
-//   MODE_DQ  : one CTA per (128-query tile, head, batch); streams K/V tiles; also computes D and stores it.
-//   MODE_DKV : one CTA per (128-key tile, head, batch);   streams Q/dO tiles; reads D.
+// the in_proj backward GEMMs read.  Both are PERSISTENT: one CTA per SM walks work items (tile, head, batch) with stride
+// gridDim.x, keeping its TMEM allocation, barriers and the TMA ring alive, and (hd = 64) prefetching the next item's
+// stationary tiles into a second buffer while the current item computes:
+//   MODE_DQ  : item = (128-query tile, head, batch); streams K/V tiles; also computes D and stores it.
+//   MODE_DKV : item = (128-key tile, head, batch);   streams Q/dO tiles; reads D.
+// Per streamed tile the MMA warp issues S / dP of the NEXT tile before the accumulating MMAs of the current one: both
+// wait for the same event (the softmax warps are done with S / dP), and the softmax warps need the next S / dP first.
 // The bf16 P / dS tile lives in shared memory as [q rows][kv cols] with 128-byte swizzled rows: the same bytes serve as
 // a K-major A operand (dS K) and as an MN-major A operand (P^T dO, dS^T Q), so no transpose is ever materialised.
 #include "host_utils.h"
@@ -26,12 +30,15 @@ constexpr int AB_OFF_SB = AB_OFF_SA + 2 * AB_TILE;  // streamed B x2 (DQ: V_j | 
 constexpr int AB_OFF_P = AB_OFF_SB + 2 * AB_TILE;   // P  bf16 [128 x 128] as two 64-column atoms
 constexpr int AB_OFF_DS = AB_OFF_P + 2 * AB_TILE;   // dS bf16, same layout
 constexpr int AB_OFF_X = AB_OFF_DS + 2 * AB_TILE;   // extra tile (DQ: O_i for D = rowsum(dO . O))
-constexpr int AB_OFF_BAR = AB_OFF_X + AB_TILE;
-constexpr int AB_NUM_BARS = 10;
-constexpr int AB_SMEM_BYTES = AB_OFF_BAR + AB_NUM_BARS * 8 + 16;
+constexpr int AB_OFF_ST2 = AB_OFF_X + AB_TILE;      // second set of stationary tiles (ST0, ST1, X) for the NEXT item, hd = 64 only
+constexpr int AB_NUM_BARS = 13;
+// hd = 64: two stationary sets; wider heads keep one (their narrow tiles need the room)
+constexpr int ab_off_bar(int rb) { return rb ? AB_OFF_ST2 : AB_OFF_ST2 + 3 * AB_TILE; }
+constexpr int AB_SMEM_BYTES = ab_off_bar(0) + AB_NUM_BARS * 8 + 16;
+constexpr int AB_SMEM_BYTES_NARROW_BASE = ab_off_bar(16) + AB_NUM_BARS * 8 + 16;
 // head widths 64 < hd <= 80: the dims past 64 ride along as narrow [128 rows x 32 B] SWIZZLE_32B tiles (see attention.cu)
 constexpr int AB_BT = 128 * 32;
-constexpr int AB_OFF_ST0B = (AB_SMEM_BYTES + 1023) / 1024 * 1024;
+constexpr int AB_OFF_ST0B = (AB_SMEM_BYTES_NARROW_BASE + 1023) / 1024 * 1024;
 constexpr int AB_OFF_ST1B = AB_OFF_ST0B + AB_BT;
 constexpr int AB_OFF_SAB = AB_OFF_ST1B + AB_BT;       // x2
 constexpr int AB_OFF_SBB = AB_OFF_SAB + 2 * AB_BT;    // x2
@@ -54,41 +61,46 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
                      const __grid_constant__ CUtensorMap tmQKVb, const __grid_constant__ CUtensorMap tmOb,
                      const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
-                     const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale) {
+                     const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale, int total_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention_bwd: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_OFF_BAR);
-  uint64_t* st_full = bars + 0;
-  uint64_t* sf = bars + 1;        // stream_full[2]
-  uint64_t* se = bars + 3;        // stream_empty[2]
-  uint64_t* s_full = bars + 5;    // S and dP of this iteration are in TMEM
-  uint64_t* pds_ready = bars + 6; // softmax wrote P / dS (and finished reading S / dP)
-  uint64_t* mma_done = bars + 7;  // accumulating MMAs of this iteration finished (P / dS smem reusable)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + AB_OFF_BAR + AB_NUM_BARS * 8);
+  constexpr int NST = RB ? 1 : 2;   // stationary tile sets
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ab_off_bar(RB));
+  uint64_t* st_full = bars + 0;   // [2] stationary tiles of an item have landed
+  uint64_t* st_empty = bars + 2;  // [2] ... and are no longer read (MMAs of the item done; DQ: D computed)
+  uint64_t* sf = bars + 4;        // stream_full[2]
+  uint64_t* se = bars + 6;        // stream_empty[2]
+  uint64_t* s_full = bars + 8;    // S and dP of this iteration are in TMEM
+  uint64_t* pds_ready = bars + 9; // softmax wrote P / dS (and finished reading S / dP)
+  uint64_t* mma_done = bars + 10; // accumulating MMAs of this iteration finished (P / dS smem reusable)
+  uint64_t* acc_free = bars + 11; // the epilogue has read the accumulators of the previous item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + ab_off_bar(RB) + AB_NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const int t0 = blockIdx.x * AB_T;  // first row of the stationary tile
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nt = (L + AB_T - 1) / AB_T;  // number of streamed tiles
+  const int nt = (L + AB_T - 1) / AB_T;  // tiles per sequence: stationary tiles of an item, streamed tiles per item
   const float s2 = scale * 1.4426950408889634f;
+  // stationary tile `which` (0: ST0, 1: ST1, 2: X) of set `buf`
+  auto st_off = [](int buf, int which) { return buf == 0 ? (which == 0 ? AB_OFF_ST0 : which == 1 ? AB_OFF_ST1 : AB_OFF_X)
+                                                         : AB_OFF_ST2 + which * AB_TILE; };
 
   if (warp == AB_SOFTMAX_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQKV);
-    mbar_init(st_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&st_full[i], 1);
+      mbar_init(&st_empty[i], 1 + (MODE == MODE_DQ ? 32 * AB_SOFTMAX_WARPS : 0));
       mbar_init(&sf[i], 1);
       mbar_init(&se[i], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(pds_ready, 32 * AB_SOFTMAX_WARPS);
     mbar_init(mma_done, 1);
+    mbar_init(acc_free, 32 * AB_SOFTMAX_WARPS);
     fence_mbar_init();
   }
   if (warp == AB_SOFTMAX_WARPS + 1) tmem_alloc<AB_TMEM_COLS>(tmem_slot);
@@ -100,43 +112,50 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   if (warp == AB_SOFTMAX_WARPS) {
     if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
-      if (MODE == MODE_DQ) {
-        mbar_arrive_expect_tx(st_full, 3 * AB_TILE + (RB ? 3 * AB_BT : 0));
-        tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, h, t0, b);          // Q_i
-        tma_load_4d(smem + AB_OFF_ST1, &tmDO, st_full, 0, h, t0, b);           // dO_i
-        tma_load_4d(smem + AB_OFF_X, &tmO, st_full, 0, h, t0, b);              // O_i
-        if (RB) {
-          tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, st_full, 64, h, t0, b);
-          tma_load_4d(smem + AB_OFF_ST1B, &tmDOb, st_full, 64, h, t0, b);
-          tma_load_4d(smem + AB_OFF_XB, &tmOb, st_full, 64, h, t0, b);
-        }
-      } else {
-        mbar_arrive_expect_tx(st_full, 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
-        tma_load_4d(smem + AB_OFF_ST0, &tmQKV, st_full, 0, H + h, t0, b);      // K_j
-        tma_load_4d(smem + AB_OFF_ST1, &tmQKV, st_full, 0, 2 * H + h, t0, b);  // V_j
-        if (RB) {
-          tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, st_full, 64, H + h, t0, b);
-          tma_load_4d(smem + AB_OFF_ST1B, &tmQKVb, st_full, 64, 2 * H + h, t0, b);
-        }
-      }
-      for (int it = 0; it < nt; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&se[s], ph ^ 1, 20);
-        mbar_arrive_expect_tx(&sf[s], 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
+      int n = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        const int t0 = (item % nt) * AB_T, h = (item / nt) % H, b = item / (nt * H);
+        const int buf = n % NST;
+        uint64_t* stf = &st_full[buf];
+        mbar_wait(&st_empty[buf], ((n / NST) & 1) ^ 1, 19);
         if (MODE == MODE_DQ) {
-          tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, H + h, it * AB_T, b);      // K_j
-          tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmQKV, &sf[s], 0, 2 * H + h, it * AB_T, b);  // V_j
+          mbar_arrive_expect_tx(stf, 3 * AB_TILE + (RB ? 3 * AB_BT : 0));
+          tma_load_4d(smem + st_off(buf, 0), &tmQKV, stf, 0, h, t0, b);          // Q_i
+          tma_load_4d(smem + st_off(buf, 1), &tmDO, stf, 0, h, t0, b);           // dO_i
+          tma_load_4d(smem + st_off(buf, 2), &tmO, stf, 0, h, t0, b);            // O_i
           if (RB) {
-            tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, H + h, it * AB_T, b);
-            tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmQKVb, &sf[s], 64, 2 * H + h, it * AB_T, b);
+            tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, stf, 64, h, t0, b);
+            tma_load_4d(smem + AB_OFF_ST1B, &tmDOb, stf, 64, h, t0, b);
+            tma_load_4d(smem + AB_OFF_XB, &tmOb, stf, 64, h, t0, b);
           }
         } else {
-          tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, h, it * AB_T, b);          // Q_i
-          tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmDO, &sf[s], 0, h, it * AB_T, b);           // dO_i
+          mbar_arrive_expect_tx(stf, 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
+          tma_load_4d(smem + st_off(buf, 0), &tmQKV, stf, 0, H + h, t0, b);      // K_j
+          tma_load_4d(smem + st_off(buf, 1), &tmQKV, stf, 0, 2 * H + h, t0, b);  // V_j
           if (RB) {
-            tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, h, it * AB_T, b);
-            tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmDOb, &sf[s], 64, h, it * AB_T, b);
+            tma_load_4d(smem + AB_OFF_ST0B, &tmQKVb, stf, 64, H + h, t0, b);
+            tma_load_4d(smem + AB_OFF_ST1B, &tmQKVb, stf, 64, 2 * H + h, t0, b);
+          }
+        }
+        for (int it = 0; it < nt; ++it, ++g) {
+          const int s = g & 1;
+          const uint32_t ph = (g >> 1) & 1;
+          mbar_wait(&se[s], ph ^ 1, 20);
+          mbar_arrive_expect_tx(&sf[s], 2 * AB_TILE + (RB ? 2 * AB_BT : 0));
+          if (MODE == MODE_DQ) {
+            tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, H + h, it * AB_T, b);      // K_j
+            tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmQKV, &sf[s], 0, 2 * H + h, it * AB_T, b);  // V_j
+            if (RB) {
+              tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, H + h, it * AB_T, b);
+              tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmQKVb, &sf[s], 64, 2 * H + h, it * AB_T, b);
+            }
+          } else {
+            tma_load_4d(smem + AB_OFF_SA + s * AB_TILE, &tmQKV, &sf[s], 0, h, it * AB_T, b);          // Q_i
+            tma_load_4d(smem + AB_OFF_SB + s * AB_TILE, &tmDO, &sf[s], 0, h, it * AB_T, b);           // dO_i
+            if (RB) {
+              tma_load_4d(smem + AB_OFF_SAB + s * AB_BT, &tmQKVb, &sf[s], 64, h, it * AB_T, b);
+              tma_load_4d(smem + AB_OFF_SBB + s * AB_BT, &tmDOb, &sf[s], 64, h, it * AB_T, b);
+            }
           }
         }
       }
@@ -144,77 +163,98 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   } else if (warp == AB_SOFTMAX_WARPS + 1) {
     if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
-      mbar_wait(st_full, 0, 21);
-      const uint32_t st0 = smem_u32(smem + AB_OFF_ST0), st1 = smem_u32(smem + AB_OFF_ST1);
       const uint32_t p_addr = smem_u32(smem + AB_OFF_P), ds_addr = smem_u32(smem + AB_OFF_DS);
-      for (int it = 0; it < nt; ++it) {
-        const int s = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        const uint32_t sa = smem_u32(smem + AB_OFF_SA + s * AB_TILE), sb = smem_u32(smem + AB_OFF_SB + s * AB_TILE);
-        // key extent of this iteration's S / dP tiles
-        const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
-        const int q0 = (MODE == MODE_DQ) ? t0 : it * AB_T;
-        const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
-        const int nq = (min(AB_T, L - q0) + 15) & ~15;
-        const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
-        const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
-        const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
-        const uint32_t v_addr = (MODE == MODE_DQ) ? sb : st1;
-        const uint32_t st0b = smem_u32(smem + AB_OFF_ST0B), st1b = smem_u32(smem + AB_OFF_ST1B);
-        const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
-        const uint32_t qb_addr = (MODE == MODE_DQ) ? st0b : sab;
-        const uint32_t dob_addr = (MODE == MODE_DQ) ? st1b : sbb;
-        const uint32_t kb_addr = (MODE == MODE_DQ) ? sab : st0b;
-        const uint32_t vb_addr = (MODE == MODE_DQ) ? sbb : st1b;
-        mbar_wait(&sf[s], ph, 22);
-        tc_fence_after();
-        const uint32_t idesc_s = umma_idesc_bf16(AB_T, nkv, 0, 0);
+      const uint32_t st0b = smem_u32(smem + AB_OFF_ST0B), st1b = smem_u32(smem + AB_OFF_ST1B);
+      int n = 0, g = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+        const int t0 = (item % nt) * AB_T;
+        const int buf = n % NST;
+        const uint32_t st0 = smem_u32(smem + st_off(buf, 0)), st1 = smem_u32(smem + st_off(buf, 1));
+        mbar_wait(&st_full[buf], (n / NST) & 1, 21);
+        // S = Q K^T and dP = dO V^T of streamed tile `it` (global iteration gg) into TMEM
+        auto issue_s = [&](int it, int gg) {
+          const int s = gg & 1;
+          const uint32_t sa = smem_u32(smem + AB_OFF_SA + s * AB_TILE), sb = smem_u32(smem + AB_OFF_SB + s * AB_TILE);
+          const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
+          const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
+          const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
+          const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
+          const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
+          const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
+          const uint32_t v_addr = (MODE == MODE_DQ) ? sb : st1;
+          const uint32_t qb_addr = (MODE == MODE_DQ) ? st0b : sab;
+          const uint32_t dob_addr = (MODE == MODE_DQ) ? st1b : sbb;
+          const uint32_t kb_addr = (MODE == MODE_DQ) ? sab : st0b;
+          const uint32_t vb_addr = (MODE == MODE_DQ) ? sbb : st1b;
+          mbar_wait(&sf[s], (gg >> 1) & 1, 22);
+          tc_fence_after();
+          const uint32_t idesc_s = umma_idesc_bf16(AB_T, nkv, 0, 0);
 #pragma unroll
-        for (int k = 0; k < AB_HD / 16; ++k)   // S = Q K^T
-          umma_bf16_ss(tmem_base + AB_TM_S, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
-                       idesc_s, k != 0);
-        if (RB) umma_bf16_ss(tmem_base + AB_TM_S, ab_desc_sw32(qb_addr), ab_desc_sw32(kb_addr), idesc_s, 1);
+          for (int k = 0; k < AB_HD / 16; ++k)   // S = Q K^T
+            umma_bf16_ss(tmem_base + AB_TM_S, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
+                         idesc_s, k != 0);
+          if (RB) umma_bf16_ss(tmem_base + AB_TM_S, ab_desc_sw32(qb_addr), ab_desc_sw32(kb_addr), idesc_s, 1);
 #pragma unroll
-        for (int k = 0; k < AB_HD / 16; ++k)   // dP = dO V^T
-          umma_bf16_ss(tmem_base + AB_TM_DP, umma_desc_kmajor_sw128(do_addr + k * 32), umma_desc_kmajor_sw128(v_addr + k * 32),
-                       idesc_s, k != 0);
-        if (RB) umma_bf16_ss(tmem_base + AB_TM_DP, ab_desc_sw32(dob_addr), ab_desc_sw32(vb_addr), idesc_s, 1);
-        umma_commit(s_full);
-        mbar_wait(pds_ready, it & 1, 23);
-        tc_fence_after();
-        if (MODE == MODE_DQ) {
-          // dQ += dS K_j : A = dS K-major (two 64-column atoms), B = K_j MN-major (rows = keys)
-          constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 0, 1);
-          for (int kk = 0; kk < nkv / 16; ++kk)
-            umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
-                         umma_desc_mnmajor_sw128(k_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
-          if (RB) {
-            constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 0, 1);
+          for (int k = 0; k < AB_HD / 16; ++k)   // dP = dO V^T
+            umma_bf16_ss(tmem_base + AB_TM_DP, umma_desc_kmajor_sw128(do_addr + k * 32), umma_desc_kmajor_sw128(v_addr + k * 32),
+                         idesc_s, k != 0);
+          if (RB) umma_bf16_ss(tmem_base + AB_TM_DP, ab_desc_sw32(dob_addr), ab_desc_sw32(vb_addr), idesc_s, 1);
+          umma_commit(s_full);
+        };
+        issue_s(0, g);   // S / dP are free: pds_ready of the previous item's last iteration was waited on below
+        for (int it = 0; it < nt; ++it, ++g) {
+          const int s = g & 1;
+          const uint32_t sa = smem_u32(smem + AB_OFF_SA + s * AB_TILE), sb = smem_u32(smem + AB_OFF_SB + s * AB_TILE);
+          const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
+          const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
+          const int q0 = (MODE == MODE_DQ) ? t0 : it * AB_T;
+          const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
+          const int nq = (min(AB_T, L - q0) + 15) & ~15;
+          const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
+          const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
+          const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
+          const uint32_t qb_addr = (MODE == MODE_DQ) ? st0b : sab;
+          const uint32_t dob_addr = (MODE == MODE_DQ) ? st1b : sbb;
+          const uint32_t kb_addr = (MODE == MODE_DQ) ? sab : st0b;
+          mbar_wait(pds_ready, g & 1, 23);   // the softmax warps are done with S / dP(it) and have written P / dS(it)
+          if (it + 1 < nt) issue_s(it + 1, g + 1);
+          if (it == 0) mbar_wait(acc_free, (n & 1) ^ 1, 28);   // the previous item's epilogue has read the accumulators
+          tc_fence_after();
+          if (MODE == MODE_DQ) {
+            // dQ += dS K_j : A = dS K-major (two 64-column atoms), B = K_j MN-major (rows = keys)
+            constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 0, 1);
             for (int kk = 0; kk < nkv / 16; ++kk)
-              umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
-                           ab_desc_sw32(kb_addr + kk * 512), idescb, (it | kk) != 0);
-          }
-        } else {
-          // dV += P^T dO_i, dK += dS^T Q_i : A = (P | dS)^T MN-major (M = keys: two 64-key panels), B MN-major (rows = queries)
-          constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 1, 1);
-          for (int kk = 0; kk < nq / 16; ++kk)
-            umma_bf16_ss(tmem_base + AB_TM_ACC1, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
-                         umma_desc_mnmajor_sw128(do_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
-          for (int kk = 0; kk < nq / 16; ++kk)
-            umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
-                         umma_desc_mnmajor_sw128(q_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
-          if (RB) {
-            constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 1, 1);
+              umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                           umma_desc_mnmajor_sw128(k_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+            if (RB) {
+              constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 0, 1);
+              for (int kk = 0; kk < nkv / 16; ++kk)
+                umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                             ab_desc_sw32(kb_addr + kk * 512), idescb, (it | kk) != 0);
+            }
+          } else {
+            // dV += P^T dO_i, dK += dS^T Q_i : A = (P | dS)^T MN-major (M = keys: two 64-key panels), B MN-major (rows = queries)
+            constexpr uint32_t idesc = umma_idesc_bf16(AB_T, AB_HD, 1, 1);
             for (int kk = 0; kk < nq / 16; ++kk)
-              umma_bf16_ss(tmem_base + AB_TM_ACC1B, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
-                           ab_desc_sw32(dob_addr + kk * 512), idescb, (it | kk) != 0);
+              umma_bf16_ss(tmem_base + AB_TM_ACC1, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
+                           umma_desc_mnmajor_sw128(do_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
             for (int kk = 0; kk < nq / 16; ++kk)
-              umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
-                           ab_desc_sw32(qb_addr + kk * 512), idescb, (it | kk) != 0);
+              umma_bf16_ss(tmem_base + AB_TM_ACC0, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
+                           umma_desc_mnmajor_sw128(q_addr + kk * 2048, AB_TILE), idesc, (it | kk) != 0);
+            if (RB) {
+              constexpr uint32_t idescb = umma_idesc_bf16(AB_T, 16, 1, 1);
+              for (int kk = 0; kk < nq / 16; ++kk)
+                umma_bf16_ss(tmem_base + AB_TM_ACC1B, umma_desc_mnmajor_sw128(p_addr + kk * 2048, AB_TILE),
+                             ab_desc_sw32(dob_addr + kk * 512), idescb, (it | kk) != 0);
+              for (int kk = 0; kk < nq / 16; ++kk)
+                umma_bf16_ss(tmem_base + AB_TM_ACC0B, umma_desc_mnmajor_sw128(ds_addr + kk * 2048, AB_TILE),
+                             ab_desc_sw32(qb_addr + kk * 512), idescb, (it | kk) != 0);
+            }
           }
+          umma_commit(&se[s]);
+          umma_commit(mma_done);
+          if (it == nt - 1) umma_commit(&st_empty[buf]);   // the item's stationary tiles are no longer read by any MMA
         }
-        umma_commit(&se[s]);
-        umma_commit(mma_done);
       }
     }
   } else {
@@ -223,12 +263,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int hsel = warp >> 2;           // which 64 of the 128 key columns this thread handles
     const int r = quad * 32 + lane;       // query row inside the tile = TMEM lane
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
+    int n = 0, g = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+    const int t0 = (item % nt) * AB_T, h = (item / nt) % H, b = item / (nt * H);
+    const int buf = n % NST;
     const long long bh = static_cast<long long>(b) * H + h;
     float lse2 = INFINITY, dlt = 0.f;
+    // the previous item's output tiles (staged in the P region) must have left shared memory before P / dS are rewritten
+    if (threadIdx.x == 0) tma_store_wait_read<0>();
+    named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
     if (MODE == MODE_DQ) {
       // D_i = rowsum(dO_i . O_i) from the stationary tiles (each of the two threads of a row computes all 64 terms)
-      mbar_wait(st_full, 0, 24);
-      const uint32_t o_s = smem_u32(smem + AB_OFF_X), do_s = smem_u32(smem + AB_OFF_ST1);
+      mbar_wait(&st_full[buf], (n / NST) & 1, 24);
+      const uint32_t o_s = smem_u32(smem + st_off(buf, 2)), do_s = smem_u32(smem + st_off(buf, 1));
       float d = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -250,13 +297,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
       }
       dlt = d;
+      mbar_arrive(&st_empty[buf]);   // this thread is done reading the stationary tiles
       const int row = t0 + r;
       if (row < L) {
         lse2 = lse[bh * L + row] * 1.4426950408889634f;
         if (hsel == 0) delta[bh * L + row] = d;
       }
     }
-    for (int it = 0; it < nt; ++it) {
+    for (int it = 0; it < nt; ++it, ++g) {
       const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
       const int valid_kv = min(AB_T, L - kv0);
       if (MODE == MODE_DKV) {
@@ -264,9 +312,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         lse2 = row < L ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
         dlt = row < L ? delta[bh * L + row] : 0.f;
       }
-      mbar_wait(s_full, it & 1, 25);
+      mbar_wait(s_full, g & 1, 25);
       tc_fence_after();
-      if (it > 0) mbar_wait(mma_done, (it - 1) & 1, 26);  // previous accumulating MMAs no longer read P / dS
+      if (g > 0) mbar_wait(mma_done, (g - 1) & 1, 26);  // previous accumulating MMAs no longer read P / dS
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
         const int col = hsel * 64 + c;
@@ -311,7 +359,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_arrive(pds_ready);
     }
     // -------------------------------------------------------------------- epilogue: accumulators -> bf16 -> TMA store
-    mbar_wait(mma_done, (nt - 1) & 1, 27);
+    mbar_wait(mma_done, (g - 1) & 1, 27);
     tc_fence_after();
     // staging reuses the P region: atom 0 <- ACC0 (dQ or dK), atom 1 <- ACC1 (dV)
     if (MODE == MODE_DQ) {
@@ -358,6 +406,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                           pack_bf16x2(__uint_as_float(ob[8 * c + 4]) * mulb, __uint_as_float(ob[8 * c + 5]) * mulb),
                           pack_bf16x2(__uint_as_float(ob[8 * c + 6]) * mulb, __uint_as_float(ob[8 * c + 7]) * mulb)));
     }
+    tc_fence_before();
+    mbar_arrive(acc_free);   // accumulators read: the next item's first accumulating MMA may overwrite them
     fence_proxy_async_smem();
     named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
     if (threadIdx.x == 0) {
@@ -373,8 +423,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
       }
       tma_store_commit();
-      tma_store_wait_all<0>();
     }
+    }   // items
+    if (threadIdx.x == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -394,7 +445,6 @@ extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* d
   if (hd < 64 || hd > 80 || (hd % 8))
     return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (64, 72 or 80)", hd);
   const bool ext = hd > AB_HD;
-  if (B > 65535 || H > 65535) return set_error(OVK_ERR_SHAPE, "attention_bwd: B and H must be <= 65535");
   if (!lse || !delta) return set_error(OVK_ERR_SHAPE, "attention_bwd: lse and delta buffers are required");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmQKV, tmDQKV, tmO, tmDO, tmQKVb, tmDQKVb, tmOb, tmDOb;
@@ -431,19 +481,22 @@ extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* d
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((L + AB_T - 1) / AB_T, H, B);
+  const long long items_ll = static_cast<long long>((L + AB_T - 1) / AB_T) * H * B;
+  if (items_ll > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention_bwd: too many work items");
+  const int items = static_cast<int>(items_ll);
+  const int grid = items < num_sms() ? items : num_sms();   // persistent: one CTA per SM (512 TMEM columns each)
   if (ext) {
     attention_bwd_kernel<MODE_DQ, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                 tmDQKVb, lse, delta, L, H, scale);
+                                                                                 tmDQKVb, lse, delta, L, H, scale, items);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                  tmDQKVb, lse, delta, L, H, scale);
+                                                                                  tmDQKVb, lse, delta, L, H, scale, items);
   } else {
     attention_bwd_kernel<MODE_DQ, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                             tmDQKVb, lse, delta, L, H, scale);
+                                                                             tmDQKVb, lse, delta, L, H, scale, items);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                              tmDQKVb, lse, delta, L, H, scale);
+                                                                              tmDQKVb, lse, delta, L, H, scale, items);
   }
   return check_launch("attention_bwd_kernel<dKdV>");
 }
