@@ -315,9 +315,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_wait(s_full, g & 1, 25);
       tc_fence_after();
       if (g > 0) mbar_wait(mma_done, (g - 1) & 1, 26);  // previous accumulating MMAs no longer read P / dS
+      // Which parts of the P / dS tile the accumulating MMAs read (the rest may hold anything: it only reaches output
+      // rows that the TMA store clips).  DQ: A = dS[q rows][keys < nkv].  DKV: A = (P | dS)^T, contraction over the first
+      // nq query rows, key columns >= valid_kv only feed clipped dK / dV rows.  With L = 128 k + 1 most of the remainder
+      // tile's work falls away here.
+      const int rows_read = (MODE == MODE_DQ) ? min(AB_T, L - t0) : ((min(AB_T, L - it * AB_T) + 15) & ~15);
+      const int cols_read = (MODE == MODE_DQ) ? ((valid_kv + 15) & ~15) : valid_kv;
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
         const int col = hsel * 64 + c;
+        if (col >= cols_read || quad * 32 >= rows_read) continue;   // warp-uniform
         uint32_t sv[32], dv[32];
         tmem_ld_x32(tmem_base + t_lane + AB_TM_S + col, sv);
         tmem_ld_x32(tmem_base + t_lane + AB_TM_DP + col, dv);
