@@ -271,6 +271,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
       const int qt = item % nq, h = (item / nq) % H, b = item / (nq * H);
       const int q0 = qt * ATT_BQ;
+      const bool rows_live = quad * 32 < L - q0;   // warp-uniform (a last tile of 1 row leaves 3 of 4 lane quadrants idle)
       // the previous item's output tile (staged in the P region) must have left shared memory
       if (threadIdx.x == 0) tma_store_wait_read<0>();
       named_bar_sync(1, SMT);
@@ -301,6 +302,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int nblk = ((min(ATT_BKV, Lm - j * ATT_BKV) + 15) & ~15) - 64 * half;
         mbar_wait(s_full, g & 1, 16);
         tc_fence_after();
+        if (!rows_live) {   // all 32 rows of this warp lie past the end of the sequence: nothing they produce is stored
+          named_bar_sync(2, SMT);
+          tc_fence_before();
+          mbar_arrive(p_ready);
+          continue;
+        }
         if (RB == 0 && ntail > 0 && j == 0) {   // this row against the remainder key (out of the small s_k MMA)
           uint32_t u;
           tmem_ld_x1(tmem_base + t_lane + ATT_TMEM_SK, u);
@@ -450,6 +457,12 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         mbar_arrive(p_ready);
       }
       // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> smem -> TMA store
+      if (!rows_live) {   // keep the barrier protocol, skip the work (these rows are clipped by the TMA store)
+        mbar_arrive(o_free);
+        named_bar_sync(2, SMT);
+        named_bar_sync(1, SMT);
+        continue;
+      }
       mbar_wait(pv_done, (g - 1) & 1, 18);
       tc_fence_after();
       uint32_t o[32];
