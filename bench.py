@@ -509,7 +509,7 @@ def run_train(args):
     batch = args.batch if args.batch != 1024 or name != "B16-384" else 512
     torch.manual_seed(0)
     tower = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"]).cuda().train()
-    tower.set_grad_checkpointing(args.checkpoint)
+    tower.set_grad_checkpointing("mlp" if args.checkpoint == "mlp" else args.checkpoint == "block")
     side = cfg["vision"]["image_size"]
     g = torch.Generator(device="cuda").manual_seed(rank)
     images = torch.randn(batch, 3, side, side, device="cuda", generator=g)
@@ -584,7 +584,9 @@ def main():
                     help="bracket one forward step + a short loss leg with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--workload", default="l14_fwd", choices=["l14_fwd", "b16_384_train", "h14_train", "l14_train"],
                     help="l14_fwd = the headline benchmark (default); *_train = extra fwd+bwd(+loss) workloads")
-    ap.add_argument("--checkpoint", action="store_true", help="activation checkpointing per block (train workloads)")
+    ap.add_argument("--checkpoint", nargs="?", const="block", default="none", choices=["none", "block", "mlp"],
+                    help="activation checkpointing (train workloads): per block (the reference's switch), or 'mlp' = keep the "
+                         "attention-side activations and recompute only the MLP hidden pair in backward")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

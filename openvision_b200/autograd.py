@@ -380,11 +380,14 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
             a = ops.attention(qkv, B, L, H, hd)
         st_mid = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
         x_mid = ops.gemm_ln(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None, stats_out=st_mid)
-        u = torch.empty((M, w1.shape[0]), dtype=torch.bfloat16, device=x2.device) if save else None
+        remlp = getattr(blk, "_recompute_mlp_hidden", False)   # selective recompute: u / f are rebuilt in backward
+        u = torch.empty((M, w1.shape[0]), dtype=torch.bfloat16, device=x2.device) if save and not remlp else None
         f = ops.gemm_ln(x_mid, w1, bias=dd1, row_stats=st_mid, eps=blk.ln_2.eps, act=act, preact_out=u)
         st_y = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
         y = ops.gemm_ln(f, p["w2"], bias=p["c2"], residual=x_mid, out=None if save else x_mid, stats_out=st_y)
         if save:   # LayerNorm statistics are recomputed in backward together with h1 / h2
+            if remlp:
+                f = None
             return y, (x2, None, None, qkv, a, lse, x_mid, None, None, u, f), st_y
         return y, None, st_y
     if save:
@@ -399,9 +402,12 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
     x_mid = ops.gemm(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None)
     if save:
         h, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True, out=h)
-        u = torch.empty((x2.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x2.device)
+        remlp = getattr(blk, "_recompute_mlp_hidden", False)
+        u = None if remlp else torch.empty((x2.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x2.device)
         f = ops.gemm(h, p["w1"], bias=p["c1"], act=act, preact_out=u)
         y = ops.gemm(f, p["w2"], bias=p["c2"], residual=x_mid)
+        if remlp:
+            f = None
         return y, (x2, mean1, rstd1, qkv, a, lse, x_mid, mean2, rstd2, u, f), None
     h = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, out=h)
     f = ops.gemm(h, p["w1"], bias=p["c1"], act=act)
@@ -431,11 +437,21 @@ class _Block(torch.autograd.Function):
         dy = _c(dy)
         need_w = any(ctx.needs_input_grad[5:])
         # ---- MLP branch
+        h2 = None
+        if u is None:   # selective recompute: ln_2 output, then fc1 + GELU with the pre-activation saved
+            if mean2 is None:
+                h2, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True)
+            else:
+                h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps)
+            u = torch.empty((x_mid.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x_mid.device)
+            f = ops.gemm(h2, p["w1"], bias=p["c1"], act=act, preact_out=u)
         du = ops.gemm_nn(dy, p["w2"], preact=u, act=act)                                    # (dY W2) . act'(u)
         g_pj_w = ops.gemm_tn(dy, f, out_dtype=_grad_dtype(pj_w)) if need_w else None
         g_pj_b = ops.colsum(dy) if need_w and pj_b is not None else None
         del f, u
-        if mean2 is None:   # LayerNorm was folded into the forward GEMMs: statistics come with the recomputed h2
+        if h2 is not None:
+            pass                # already recomputed above
+        elif mean2 is None:   # LayerNorm was folded into the forward GEMMs: statistics come with the recomputed h2
             h2, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True)
         else:
             h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps) if need_w else None   # recomputed, not stored

@@ -204,7 +204,8 @@ class TextTransformer(nn.Module):
 
     @torch.jit.ignore
     def set_grad_checkpointing(self, enable=True):
-        self.transformer.grad_checkpointing = enable
+        self.transformer.grad_checkpointing = enable is True
+        self.transformer.recompute_mlp_hidden = enable == 'mlp'
 
     def build_causal_mask(self):
         mask = torch.empty(self.num_pos, self.num_pos)
@@ -290,8 +291,10 @@ class CLIP(nn.Module):
 
     @torch.jit.ignore
     def set_grad_checkpointing(self, enable=True):
+        """model.py:260-263; enable='mlp' = selective mode (see Transformer.recompute_mlp_hidden)."""
         self.visual.set_grad_checkpointing(enable)
-        self.transformer.grad_checkpointing = enable
+        self.transformer.grad_checkpointing = enable is True
+        self.transformer.recompute_mlp_hidden = enable == 'mlp'
 
     def encode_image(self, image, normalize: bool = False):
         features = self.visual(image)

@@ -307,6 +307,10 @@ class Transformer(nn.Module):
         self.layers = layers
         self.batch_first = batch_first
         self.grad_checkpointing = False
+        # extension of the reference's switch: 'mlp' keeps the attention-side activations of every block and recomputes only
+        # the MLP hidden pair (pre- / post-GELU, 8 of the 14 D-sized tensors a block saves) in backward: one extra fc1 GEMM
+        # per block instead of a whole block forward.  Set through set_grad_checkpointing('mlp').
+        self.recompute_mlp_hidden = False
         self.resblocks = nn.ModuleList([
             ResidualAttentionBlock(width, heads, mlp_ratio, ls_init_value=ls_init_value, act_layer=act_layer,
                                    norm_layer=norm_layer, batch_first=True)
@@ -323,6 +327,7 @@ class Transformer(nn.Module):
         stats = None   # LayerNorm statistics of x2, produced by the epilogue of the GEMM that wrote it
         for r in self.resblocks:
             if r._fusable():
+                r._recompute_mlp_hidden = self.recompute_mlp_hidden
                 if self.grad_checkpointing and torch.is_grad_enabled() and x2.requires_grad:
                     x2, stats = checkpoint(r.forward_tokens, x2, B, L, False, stats, use_reentrant=False)
                 else:
@@ -438,7 +443,9 @@ class VisionTransformer(nn.Module):
 
     @torch.jit.ignore
     def set_grad_checkpointing(self, enable=True):
-        self.transformer.grad_checkpointing = enable
+        """transformer.py:594-596; enable='mlp' selects the selective mode (Transformer.recompute_mlp_hidden)."""
+        self.transformer.grad_checkpointing = enable is True
+        self.transformer.recompute_mlp_hidden = enable == 'mlp'
 
     def _global_pool(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         if self.pool_type == 'avg':

@@ -209,7 +209,7 @@ def test_ti16_image_gradient_and_checkpointing(golden):
     m = m.cuda().train()
     text = synth.make_text(cfg_name, batch, 0).cuda()
     grads = []
-    for ckpt in (False, True):
+    for ckpt in (False, True, "mlp"):
         m.set_grad_checkpointing(ckpt)
         m.zero_grad(set_to_none=True)
         images = synth.make_images(cfg_name, batch, 0).cuda().requires_grad_(True)
@@ -219,6 +219,11 @@ def test_ti16_image_gradient_and_checkpointing(golden):
     got = grads[0][0].float().cpu().numpy().reshape(-1)[::5]
     assert_grad(got, g["grad_images"], "Ti16 d images", 8e-2)
     assert torch.equal(grads[0][0], grads[1][0]) and torch.equal(grads[0][1], grads[1][1]), "checkpointed != plain"
+    # selective mode ('mlp'): backward rebuilds the MLP hidden pair from the stand-alone LayerNorm + fc1 (the forward ran
+    # them folded), so the gradients agree to bf16 rounding, not bit for bit
+    for a, b, what in ((grads[2][0], grads[0][0], "d images"), (grads[2][1], grads[0][1], "d conv1.weight")):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 3e-2 * b.float().abs().max().item(), (what, err)
 
 
 def test_gelu_hook_gradients_reach_the_image():
