@@ -45,3 +45,19 @@ fwdbwd(); torch.cuda.synchronize()
 for k, l in sorted(rec.items()):
     ms = sum(a.elapsed_time(b) for a, b, _ in l); w = sum(x for _, _, x in l)
     print(f"   {k:16s} {len(l):4d} launches {ms:8.2f} ms  {w/ms/1e9:8.1f} {'TFLOP/s' if k in ('gemm','attention','attention_bwd') else 'GB/s*1e3'}")
+
+# per-kind device time of one fwd+bwd (CUDA events around every libovk launch)
+class _Rec:
+    def __init__(self): self.r = {}
+    def __call__(self, kind, work):
+        rec = self
+        class B:
+            def __enter__(s):
+                s.a, s.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True); s.a.record()
+            def __exit__(s, *x):
+                s.b.record(); rec.r.setdefault(kind, []).append((s.a, s.b)); return False
+        return B()
+rec = _Rec(); ops.recorder = rec
+fwdbwd(); torch.cuda.synchronize(); ops.recorder = None
+parts = {k: sum(a.elapsed_time(b) for a, b in e) for k, e in rec.r.items()}
+print("per-kind ms in one fwd+bwd: " + "  ".join(f"{k}={t:.1f}({len(rec.r[k])})" for k, t in sorted(parts.items(), key=lambda kv: -kv[1])), "  sum=%.1f" % sum(parts.values()), flush=True)
