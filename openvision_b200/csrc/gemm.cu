@@ -302,13 +302,37 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   const int tiles = ((g.M + bm - 1) / bm) * ((g.N + BN - 1) / BN);
   const int units = PAIR ? num_sms() / 2 : num_sms();   // CTA pairs or CTAs that can be resident
   // split-K (fp32 outputs only: the weight-gradient GEMMs have few output tiles and a huge K = tokens): partial sums
-  // are added into a zeroed C by TMA reduce-add stores
+  // are added into a zeroed C by TMA reduce-add stores.  The split count is the one (<= 16, at least 8 k-blocks each)
+  // that fills the waves best: e.g. 75 tiles on 74 CTA pairs are two waves at 51 % unsplit, nine waves at 90 % split 8
+  // ways; every extra split costs one more fp32 reduce-add pass over the output, hence the penalty term.
   int splits = 1;
-  if (OUT_F32 && tiles * 10 < units * 7) {
+  const char* pol = getenv("OVK_SPLITK_SIMPLE");   // =1: the first-cut rule (fill one wave), kept for A/B measurements
+  if (OUT_F32 && pol != nullptr && pol[0] == '1') {
+    if (tiles * 10 < units * 7) {
+      const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+      splits = units / tiles;
+      if (splits > num_kb / 8) splits = num_kb / 8;
+      if (splits < 1) splits = 1;
+    }
+  } else if (OUT_F32) {
     const int num_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
-    splits = units / tiles;
-    if (splits > num_kb / 8) splits = num_kb / 8;
-    if (splits < 1) splits = 1;
+    const int max_s = num_kb / 8 < 16 ? num_kb / 8 : 16;
+    float best = -1.f;
+    for (int sct = 1; sct <= max_s; ++sct) {
+      const int kb_per = (num_kb + sct - 1) / sct;
+      const int eff_s = (num_kb + kb_per - 1) / kb_per;   // splits the scheduler will really make
+      if (eff_s != sct) continue;
+      const long long items_s = static_cast<long long>(tiles) * sct;
+      const long long waves = (items_s + units - 1) / units;
+      // every split adds one fp32 reduce-add pass over the output: measured ~2.5 TB/s through L2, i.e. ~1040 / K of the
+      // GEMM's own time per split
+      const float eff = static_cast<float>(items_s) / static_cast<float>(waves * units) -
+                        (1040.f / static_cast<float>(g.K)) * static_cast<float>(sct - 1);
+      if (eff > best) {
+        best = eff;
+        splits = sct;
+      }
+    }
   }
   if (splits > 1) {
     cudaError_t e = cudaMemset2DAsync(g.C, static_cast<size_t>(g.ldc) * 4, 0, static_cast<size_t>(g.N) * 4, g.M, stream);
