@@ -123,3 +123,36 @@ def test_batch_shard_independence_full_config():
         parts = torch.cat([v(images[:2]), v(images[2:])])
     assert torch.isfinite(full).all()
     assert torch.equal(full, parts)
+
+
+def test_headline_config_shards_and_kernel_variants_agree():
+    """ViT-L/14@224 (the benchmark's config; too big for a CPU reference at this batch): (1) encoding a batch equals encoding
+    its shards bit-exactly; (2) the alternative kernels of the path — stand-alone LayerNorm instead of the LayerNorm folded
+    into the GEMMs, the one-tile attention kernel instead of the pair kernel — give the same normalised embeddings to bf16
+    rounding (cosine >= 0.9995, the north-star bar, against each other)."""
+    import os
+    cfg = synth.CONFIGS["L14-224"]
+    torch.manual_seed(0)
+    v = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"]).cuda().eval()
+    images = torch.randn(48, 3, 224, 224, device="cuda")
+    saved = {k: os.environ.get(k) for k in ("OVK_LN_FOLD", "OVK_ATT_V1")}
+    try:
+        with torch.no_grad():
+            full = v(images)
+            parts = torch.cat([v(images[:16]), v(images[16:])])
+            assert torch.isfinite(full).all() and torch.equal(full, parts)
+            ref = torch.nn.functional.normalize(full.float(), dim=-1)
+            for var in ("OVK_LN_FOLD=0", "OVK_ATT_V1=1"):
+                k, val = var.split("=")
+                os.environ[k] = val
+                alt = torch.nn.functional.normalize(v(images).float(), dim=-1)
+                os.environ.pop(k)
+                cos = (ref * alt).sum(-1)
+                assert cos.min().item() >= 0.9995, (var, cos.min().item())
+                assert (ref - alt).abs().max().item() <= 2e-2, (var, (ref - alt).abs().max().item())
+    finally:
+        for k, val in saved.items():
+            if val is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = val
