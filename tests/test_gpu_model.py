@@ -156,3 +156,24 @@ def test_headline_config_shards_and_kernel_variants_agree():
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = val
+
+
+@pytest.mark.parametrize("cfg_name,batch", [("L14-224", 4), ("B16-384", 2)])
+def test_full_size_towers_match_the_fp32_oracle(cfg_name, batch):
+    """The benchmark's own towers (24 x 1024 @ 257 tokens; 12 x 768 @ 577 tokens) against the fp32 CPU oracle on a few
+    images: normalised embeddings within the north-star bar.  Exercises the production kernel selection (LayerNorm folded
+    into the GEMMs, CTA-pair GEMMs, pair / one-tile attention kernels, remainder-token handling at L = 257)."""
+    sd = synth.make_state_dict(cfg_name, 0, vision_only=True)
+    images = synth.make_images(cfg_name, batch, 0)
+    with torch.no_grad():
+        ref = O.l2_normalize(O.vision_transformer(images, sd, synth.vision_heads(cfg_name), pool_type="avg",
+                                                  final_ln_after_pool=True))
+    cfg = synth.CONFIGS[cfg_name]
+    v = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"])
+    v.load_state_dict({k[len("visual."):]: t for k, t in sd.items() if k.startswith("visual.")}, strict=True)
+    v = v.cuda().eval()
+    with torch.no_grad():
+        # a batch big enough for the CTA-pair GEMMs (>= 512 rows): the checked images first, fillers after
+        filler = torch.randn(8, *images.shape[1:], generator=torch.Generator().manual_seed(5))
+        got = torch.nn.functional.normalize(v(torch.cat([images, filler]).cuda()).float(), dim=-1)[:batch]
+    check_embeddings(got, ref, f"{cfg_name} vs fp32 oracle")
