@@ -246,3 +246,34 @@ def test_gelu_hook_gradients_reach_the_image():
     O.vision_transformer(xf, sd, synth.vision_heads(cfg_name), taps=taps)
     (-taps["visual.transformer.resblocks.1.mlp.gelu"][:, :, 7].mean()).backward()
     assert_grad(images.grad, xf.grad, "d image through hooked GELU", 6e-2)
+
+
+def test_l14_full_size_gradients_match_oracle_autograd():
+    """The benchmark's tower (ViT-L/14@224, 24 layers, 257 tokens) through forward AND backward against autograd on the
+    fp32 CPU oracle, for a handful of parameters spread over the depth and for the input images.  Exercises the production
+    kernel selection in training mode: LayerNorm folded forward / recomputed backward, persistent attention backward with
+    the remainder tiles of L = 257, CTA-pair and split-K GEMMs."""
+    cfg_name, batch = "L14-224", 2
+    sd = synth.make_state_dict(cfg_name, 0, vision_only=True)
+    watch = ["visual.conv1.weight", "visual.transformer.resblocks.0.attn.in_proj_weight",
+             "visual.transformer.resblocks.0.ln_1.weight", "visual.transformer.resblocks.11.mlp.c_fc.weight",
+             "visual.transformer.resblocks.23.mlp.c_proj.bias", "visual.transformer.resblocks.23.attn.out_proj.weight",
+             "visual.ln_post.bias", "visual.proj"]
+    ref_sd = {k: (t.clone().requires_grad_(True) if k in watch else t) for k, t in sd.items()}
+    images = synth.make_images(cfg_name, batch, 0)
+    ref_img = images.clone().requires_grad_(True)
+    w = torch.randn(batch, synth.CONFIGS[cfg_name]["embed_dim"], generator=torch.Generator().manual_seed(3))
+    ref_out = O.l2_normalize(O.vision_transformer(ref_img, ref_sd, synth.vision_heads(cfg_name), pool_type="avg",
+                                                  final_ln_after_pool=True))
+    (ref_out * w).sum().backward()
+    cfg = synth.CONFIGS[cfg_name]
+    v = ovb.model._build_vision_tower(cfg["embed_dim"], cfg["vision"])
+    v.load_state_dict({k[len("visual."):]: t for k, t in sd.items() if k.startswith("visual.")}, strict=True)
+    v = v.cuda().train()
+    img = images.cuda().requires_grad_(True)
+    out = torch.nn.functional.normalize(v(img).float(), dim=-1)
+    (out * w.cuda()).sum().backward()
+    params = dict(v.named_parameters())
+    for k in watch:
+        assert_grad(params[k[len("visual."):]].grad, ref_sd[k].grad, k, 8e-2)
+    assert_grad(img.grad, ref_img.grad, "d images", 8e-2)
