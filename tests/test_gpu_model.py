@@ -158,7 +158,7 @@ def test_headline_config_shards_and_kernel_variants_agree():
                 os.environ[k] = val
 
 
-@pytest.mark.parametrize("cfg_name,batch", [("L14-224", 4), ("B16-384", 2)])
+@pytest.mark.parametrize("cfg_name,batch", [("L14-224", 4), ("B16-384", 2), ("H14-224", 2)])
 def test_full_size_towers_match_the_fp32_oracle(cfg_name, batch):
     """The benchmark's own towers (24 x 1024 @ 257 tokens; 12 x 768 @ 577 tokens) against the fp32 CPU oracle on a few
     images: normalised embeddings within the north-star bar.  Exercises the production kernel selection (LayerNorm folded
