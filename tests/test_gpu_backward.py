@@ -40,7 +40,8 @@ def assert_grad(got, ref, what, tol=5e-2, abs_floor=1e-6):
 
 
 @pytest.mark.parametrize("B,L,H", [(1, 128, 1), (2, 64, 2), (3, 101, 3), (2, 257, 4), (1, 577, 2), (1, 16, 1), (2, 129, 1),
-                                   (1, 1, 1), (2, 200, 2)])
+                                   (1, 1, 1), (2, 200, 2),
+                                   (24, 257, 8), (9, 577, 6)])   # > 148 work items: persistent CTAs walk several items each
 def test_attention_bwd(ops, B, L, H):
     hd = 64
     qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
@@ -60,7 +61,7 @@ def test_attention_bwd(ops, B, L, H):
 
 
 @pytest.mark.parametrize("hd", [72, 80])
-@pytest.mark.parametrize("B,L,H", [(2, 257, 2), (1, 101, 3), (1, 577, 1), (2, 130, 1)])
+@pytest.mark.parametrize("B,L,H", [(2, 257, 2), (1, 101, 3), (1, 577, 1), (2, 130, 1), (16, 257, 4)])
 def test_attention_bwd_wide_heads(ops, hd, B, L, H):
     qkv = rnd(B * L, 3 * H * hd, seed=L + hd).bfloat16()
     dout = rnd(B * L, H * hd, seed=L + hd + 1).bfloat16()

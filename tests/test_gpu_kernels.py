@@ -152,7 +152,8 @@ def _attn_ref(qkv, B, L, H, hd):
 
 @pytest.mark.parametrize("B,L,H", [(1, 128, 1), (2, 128, 2), (2, 64, 1), (3, 101, 3), (2, 257, 4), (2, 577, 3),
                                    (1, 16, 1), (1, 200, 2), (1, 1, 1), (2, 129, 2), (1, 8, 16), (2, 130, 1), (1, 258, 2),
-                                   (1, 131, 1), (1, 513, 1), (1, 1025, 1)])
+                                   (1, 131, 1), (1, 513, 1), (1, 1025, 1),
+                                   (20, 257, 16), (40, 256, 8), (8, 577, 12)])   # > 148 (pair) items: several items per CTA
 def test_attention_fwd(ops, B, L, H):
     hd = 64
     qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
