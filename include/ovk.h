@@ -89,6 +89,12 @@ int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, long long ldb,
                      const void* residual, long long ldr, void* preact, long long ldp, float* row_stats_out, int flags,
                      void* stream);
 int ovk_row_stats(const void* x, long long ldx, float* stats, int rows, int D, void* stream);
+/* Patch-embedding GEMM fused with the class-token / positional-embedding add (transformer.py:610-617):
+ *   C[row] = A[row] B^T + row_add[row % row_period],  row_add bf16 [row_period, N] (N % 64 == 0).
+ * With A = ovk_im2col_patches(..., lead_rows = 1) (a zero row in every image's cls slot), row_period = tokens per image and
+ * row_add[0] = class_embedding + pos[0], row_add[t] = pos[t], C is the finished [B, L, D] token buffer. */
+int ovk_gemm_bf16_rowadd(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                         int K, const void* row_add, int row_period, void* stream);
 /* Backward GEMMs (what autograd derives from F.linear): operands are read in place, nothing is transposed in memory.
  *   ovk_gemm_bf16_nn : C[M,N] = alpha * A[M,K] * B[K,N]      (B row-major [K,N])   dX = dY * W
  *                      optional fused GELU backward: C = alpha * (A*B) (.) act'(preact), preact bf16 [M, ldp], act = OVK_EPI_GELU_*

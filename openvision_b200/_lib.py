@@ -43,6 +43,8 @@ _PROTOTYPES = {
     "ovk_sumsq": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
     "ovk_adamw_step": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float,
                                c_float, c_float, c_int, c_float, c_void_p, c_float, c_void_p]),
+    "ovk_gemm_bf16_rowadd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                     c_void_p, c_int, c_void_p]),
     "ovk_pack_ln_linear": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                    c_void_p, c_int, c_int, c_void_p]),
     "ovk_row_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),

@@ -26,6 +26,10 @@ struct GemmEpi {
   float* row_stats_out;      // f32[ceil(N/128)][M][2] partial (sum, sum sq) of the output rows, or null
   int stats_parts_in;
   float inv_k, ln_eps;
+  // FUSE kernels, linear epilogue: C[row] += row_add[row % row_period] (bf16 [row_period, N] table): the positional
+  // embedding (+ class token in row 0) added to the patch-embedding GEMM's output, transformer.py:615-617
+  const __nv_bfloat16* row_add;
+  int row_period;
 };
 
 // EPI_LINEAR: C = alpha*acc + bias (+ R)                   R  = residual tile [M,N] bf16 (tmR), may alias C
@@ -201,6 +205,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               } else {
                 x[8 * j + 2 * q] += r0;
                 x[8 * j + 2 * q + 1] += r1;
+              }
+            }
+          }
+        }
+        if constexpr (FUSE && EPI == EPI_LINEAR && !OUT_F32) {
+          if (ep.row_add != nullptr) {   // token row -> its positional-embedding row (N % 64 == 0 checked by the host)
+            const int row_g = ti.m0 + et;
+            if (row_g < M) {
+              const uint4* src = reinterpret_cast<const uint4*>(ep.row_add + static_cast<long long>(row_g % ep.row_period) * N + ncol0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 r = __ldg(src + j);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  x[8 * j + 2 * q] += bf16_lo(rw[q]);
+                  x[8 * j + 2 * q + 1] += bf16_hi(rw[q]);
+                }
               }
             }
           }
@@ -447,6 +469,21 @@ extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, lon
   return launch_gemm_bn<true, true, EPI_LINEAR, false>(g, s);
 }
 
+
+extern "C" int ovk_gemm_bf16_rowadd(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M,
+                                    int N, int K, const void* row_add, int row_period, void* stream) {
+  GemmArgs g{A, lda, false, B, ldb, false, C, ldc, false, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  if (row_add == nullptr || row_period <= 0) return set_error(OVK_ERR_SHAPE, "gemm_rowadd: row_add table and period are required");
+  if (N % 64) return set_error(OVK_ERR_SHAPE, "gemm_rowadd: N must be a multiple of 64");
+  if (reinterpret_cast<uintptr_t>(row_add) & 15) return set_error(OVK_ERR_ALIGN, "gemm_rowadd: row_add must be 16-byte aligned");
+  g.ep.alpha = 1.f;
+  g.ep.act = act_coef(0);
+  g.ep.row_add = reinterpret_cast<const __nv_bfloat16*>(row_add);
+  g.ep.row_period = row_period;
+  int rc = check_common(g, "gemm_rowadd");
+  if (rc) return rc;
+  return launch_gemm_bn<false, false, EPI_LINEAR, false, true>(g, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int ovk_gemm_bf16_ln(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
                                 int M, int N, int K, const float* bias, const float* row_stats_in, int stats_parts_in,

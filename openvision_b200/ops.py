@@ -178,6 +178,25 @@ def pack_ln_linear(w: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bia
     return wc, d
 
 
+def gemm_rowadd(a: torch.Tensor, w: torch.Tensor, row_add: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[row] = a[row] @ w^T + row_add[row % period]: the patch-embedding GEMM with the class-token / positional-embedding
+    add in its epilogue (transformer.py:610-617). row_add: bf16 [period, N]."""
+    _require(a, torch.bfloat16, "gemm_rowadd.a", 2)
+    _require(w, torch.bfloat16, "gemm_rowadd.w", 2)
+    _require(row_add, torch.bfloat16, "gemm_rowadd.row_add", 2)
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K or row_add.shape[1] != N or not row_add.is_contiguous():
+        raise OvkError("gemm_rowadd: shapes do not match (a [M,K], w [N,K], row_add contiguous [period,N])")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_rowadd", _p(a), a.stride(0), _p(w), w.stride(0), _p(out), out.stride(0), M, N, K,
+                  _p(row_add), row_add.shape[0], _stream())
+    _count()
+    return out
+
+
 def row_stats(x: torch.Tensor) -> torch.Tensor:
     """(sum, sum of squares) per row of x bf16 [rows, D] -> fp32 [1, rows, 2] (one partial slot). Kernel: row_stats_kernel."""
     _require(x, torch.bfloat16, "row_stats.x", 2)

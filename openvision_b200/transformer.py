@@ -16,6 +16,8 @@ import math
 from collections import OrderedDict
 from typing import Callable, Optional, Sequence, Tuple
 
+import os
+
 import torch
 from torch import nn
 from torch.utils.checkpoint import checkpoint
@@ -456,13 +458,51 @@ class VisionTransformer(nn.Module):
             pooled = tokens = x
         return pooled, tokens
 
+    def _embed_fused(self, images: torch.Tensor):
+        """Inference path of transformer.py:610-617: patch GEMM whose epilogue adds the positional embedding (class token
+        folded into row 0 of the table; the im2col buffer has a zero row in every image's cls slot), so the GEMM output IS
+        the [B, L, D] token buffer.  Returns None when gradients are needed or the shapes do not fit (then the stand-alone
+        embed_assemble kernel runs)."""
+        from .autograd import _needs_grad
+        conv = self.conv1
+        if _needs_grad(images, conv.weight, self.class_embedding, self.positional_embedding) or not images.is_cuda:
+            return None
+        if conv.kernel_size != conv.stride or conv.kernel_size[0] != conv.kernel_size[1] or conv.bias is not None:
+            return None
+        P = conv.kernel_size[0]
+        B, _, H, W = images.shape
+        N = (H // P) * (W // P)
+        D = conv.out_channels
+        pos, cls = self.positional_embedding, self.class_embedding
+        if D % 64 or pos.dim() != 2 or pos.shape[0] != N + 1 or os.environ.get("OVK_EMBED_FUSE", "1") == "0":
+            return None
+        cache = self.__dict__.setdefault("_ovk_cache", {})
+        tag = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in (pos, cls))
+        hit = cache.get("pos_cls")
+        if hit is None or hit[0] != tag:
+            with torch.no_grad():
+                table = pos.detach().float().clone()
+                table[0] += cls.detach().float()
+                hit = (tag, table.to(torch.bfloat16).contiguous())
+            cache["pos_cls"] = hit
+        if images.dtype not in (torch.float32, torch.bfloat16):
+            images = images.to(torch.float32)
+        w, kpad = conv.packed_weight()
+        cols = ops.im2col_patches(images.contiguous(), P, kpad, lead_rows=1)
+        return ops.gemm_rowadd(cols, w, hit[1]), B, N
+
     def forward(self, x: torch.Tensor):
         from .autograd import embed_assemble_fn, layer_norm_fn, linear_fn, pool_fn
         images = x
         out_dtype = _out_dtype(images)
-        tok, B, N = self.conv1.tokens(images)                                   # :610-612
-        L = N + 1
-        x2 = embed_assemble_fn(tok, self.class_embedding, self.positional_embedding, B, N, self)   # :615-617
+        x2 = self._embed_fused(images)                                          # :610-617 in one GEMM (inference)
+        if x2 is not None:
+            x2, B, N = x2
+            L = N + 1
+        else:
+            tok, B, N = self.conv1.tokens(images)                               # :610-612
+            L = N + 1
+            x2 = embed_assemble_fn(tok, self.class_embedding, self.positional_embedding, B, N, self)   # :615-617
         D = x2.shape[-1]
         if not isinstance(self.patch_dropout, nn.Identity) and self.training:   # :619
             x3 = self.patch_dropout(x2.reshape(B, L, D))

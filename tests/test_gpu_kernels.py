@@ -359,3 +359,25 @@ def test_attention_remainder_row_rides_in_main_kernel(ops, L, grow):
     assert_close(last, ref.view(B, L, H * hd)[:, L - 1], 2e-2, f"attention L{L}: remainder query row")
     assert_close(lse, lse_ref, 1e-3, "attention lse")
     assert_close(lse[:, :, L - 1], lse_ref[:, :, L - 1], 1e-3, "attention lse of the remainder row")
+
+
+@pytest.mark.parametrize("B,H,P,D", [(3, 32, 8, 64), (2, 224, 14, 1024), (5, 160, 16, 192)])
+def test_patch_embed_gemm_with_fused_positional_add(ops, B, H, P, D):
+    """transformer.py:610-617 in one GEMM: im2col (zero row in every image's cls slot) x conv weight, the class token /
+    positional-embedding table added per token row in the epilogue -> the [B, L, D] token buffer."""
+    gh = H // P
+    N = gh * gh
+    img = rnd(B, 3, H, H, seed=1)
+    wconv = rnd(D, 3, P, P, seed=2, scale=0.05)
+    cls, pos = rnd(D, seed=3), rnd(N + 1, D, seed=4)
+    K = 3 * P * P
+    kpad = (K + 7) // 8 * 8
+    cols = ops.im2col_patches(img.cuda(), P, kpad, lead_rows=1)
+    wp = torch.zeros(D, kpad, dtype=torch.bfloat16)
+    wp[:, :K] = wconv.reshape(D, K).bfloat16()
+    table = pos.clone()
+    table[0] += cls
+    x = ops.gemm_rowadd(cols, wp.cuda(), table.bfloat16().cuda())
+    ref = O.patch_embed(img.bfloat16().float(), wconv.bfloat16().float())
+    ref = torch.cat([cls.expand(B, 1, D), ref], 1) + pos
+    assert_close(x.view(B, N + 1, D), ref, 1e-2, "patch embed + positional add")
