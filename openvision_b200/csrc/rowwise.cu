@@ -30,76 +30,96 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float* __restrict__ mean_out,
                                                             float* __restrict__ rstd_out, int rows, int D, float eps) {
-  // one warp owns LN_RPW consecutive rows and issues all their loads before touching any of them (more bytes in
-  // flight per SM: the kernel is pure HBM streaming)
-  constexpr int RPW = MAXV >= 8 ? 1 : 2;   // wide rows (D > 1024) already keep 8 vectors per lane in flight
-  const int warps_per_block = blockDim.x >> 5;
-  const int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * RPW;
-  if (row0 >= rows) return;
+  // Persistent: a warp walks rows with stride (warps in the grid) and keeps the gamma / beta of its own columns in
+  // registers for all of them (re-reading them per row costs four L1 loads per 16 bytes of data, which is what limited
+  // the first version).  MAXV <= 4: RPW = 2 rows are loaded before either is touched (more bytes in flight per SM).
+  constexpr int RPW = MAXV >= 8 ? 1 : 2;
+  constexpr bool GB_IN_REGS = MAXV <= 4;   // 16 * MAXV registers; wider rows read gamma / beta through L1 as before
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  uint4 raw[RPW][MAXV];
-#pragma unroll
-  for (int rr = 0; rr < RPW; ++rr) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row0 + rr) * ldx);
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  const int warp_g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float4 g0[GB_IN_REGS ? MAXV : 1], g1[GB_IN_REGS ? MAXV : 1], b0[GB_IN_REGS ? MAXV : 1], b1[GB_IN_REGS ? MAXV : 1];
+  if (GB_IN_REGS) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
-      raw[rr][i] = (v < nvec && row0 + rr < rows) ? xr[v] : make_uint4(0, 0, 0, 0);
+      const bool live = v < nvec;
+      g0[i] = live ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g1[i] = live ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      b0[i] = live ? __ldg(reinterpret_cast<const float4*>(beta) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      b1[i] = live ? __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  for (int row0 = warp_g * RPW; row0 < rows; row0 += warps_total * RPW) {
+    uint4 raw[RPW][MAXV];
 #pragma unroll
-  for (int rr = 0; rr < RPW; ++rr) {
-    const int row = row0 + rr;
-    if (row >= rows) break;
-    float s = 0.f;
+    for (int rr = 0; rr < RPW; ++rr) {
+      const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row0 + rr) * ldx);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      float f[8];
-      unpack8(raw[rr][i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[j];
-    }
-    const float mean = warp_sum(s) / static_cast<float>(D);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      if (lane + i * 32 < nvec) {
-        float f[8];
-        unpack8(raw[rr][i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = f[j] - mean;
-          q = fmaf(d, d, q);
-        }
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        raw[rr][i] = (v < nvec && row0 + rr < rows) ? xr[v] : make_uint4(0, 0, 0, 0);
       }
     }
-    const float var = warp_sum(q) / static_cast<float>(D);
-    const float rstd = rsqrtf(var + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int v = lane + i * 32;
-      if (v < nvec) {
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int row = row0 + rr;
+      if (row >= rows) break;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
         float f[8];
         unpack8(raw[rr][i], f);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
-        f[0] = fmaf((f[0] - mean) * rstd, g0.x, b0.x);
-        f[1] = fmaf((f[1] - mean) * rstd, g0.y, b0.y);
-        f[2] = fmaf((f[2] - mean) * rstd, g0.z, b0.z);
-        f[3] = fmaf((f[3] - mean) * rstd, g0.w, b0.w);
-        f[4] = fmaf((f[4] - mean) * rstd, g1.x, b1.x);
-        f[5] = fmaf((f[5] - mean) * rstd, g1.y, b1.y);
-        f[6] = fmaf((f[6] - mean) * rstd, g1.z, b1.z);
-        f[7] = fmaf((f[7] - mean) * rstd, g1.w, b1.w);
-        yr[v] = pack8(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+      }
+      const float mean = warp_sum(s) / static_cast<float>(D);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        if (lane + i * 32 < nvec) {
+          float f[8];
+          unpack8(raw[rr][i], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - mean;
+            q = fmaf(d, d, q);
+          }
+        }
+      }
+      const float var = warp_sum(q) / static_cast<float>(D);
+      const float rstd = rsqrtf(var + eps);
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+      }
+      uint4* yr = reinterpret_cast<uint4*>(y + static_cast<long long>(row) * ldy);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+          float f[8];
+          unpack8(raw[rr][i], f);
+          float4 a0, a1, c0, c1;
+          if (GB_IN_REGS) {
+            a0 = g0[i]; a1 = g1[i]; c0 = b0[i]; c1 = b1[i];
+          } else {
+            a0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+            a1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+            c0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v);
+            c1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * v + 1);
+          }
+          f[0] = fmaf((f[0] - mean) * rstd, a0.x, c0.x);
+          f[1] = fmaf((f[1] - mean) * rstd, a0.y, c0.y);
+          f[2] = fmaf((f[2] - mean) * rstd, a0.z, c0.z);
+          f[3] = fmaf((f[3] - mean) * rstd, a0.w, c0.w);
+          f[4] = fmaf((f[4] - mean) * rstd, a1.x, c1.x);
+          f[5] = fmaf((f[5] - mean) * rstd, a1.y, c1.y);
+          f[6] = fmaf((f[6] - mean) * rstd, a1.z, c1.z);
+          f[7] = fmaf((f[7] - mean) * rstd, a1.w, c1.w);
+          yr[v] = pack8(f);
+        }
       }
     }
   }
@@ -144,60 +164,170 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
                                                                const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                const __nv_bfloat16* dres, long long lddres,
                                                                __nv_bfloat16* dx, long long lddx, int rows, int D) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // persistent like the forward: a warp walks rows with a grid stride and keeps gamma of its columns in registers
+  constexpr bool G_IN_REGS = MAXV <= 4;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
-  const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
-  const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
-  uint4 rx[MAXV], rd[MAXV], rr[MAXV];
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float4 gr0[G_IN_REGS ? MAXV : 1], gr1[G_IN_REGS ? MAXV : 1];
+  if (G_IN_REGS) {
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    const bool ok = v < nvec;
-    rx[i] = ok ? xr[v] : make_uint4(0, 0, 0, 0);
-    rd[i] = ok ? dyr[v] : make_uint4(0, 0, 0, 0);
-    rr[i] = (ok && drr) ? drr[v] : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      gr0[i] = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gr1[i] = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
-  const float mu = mean[row], rs = rstd[row];
-  float s1 = 0.f, s2 = 0.f;
+  for (int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
+    const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
+    uint4 rx[MAXV], rd[MAXV], rr[MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float fx[8], fd[8];
-      unpack8(rx[i], fx);
-      unpack8(rd[i], fd);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      const bool ok = v < nvec;
+      rx[i] = ok ? xr[v] : make_uint4(0, 0, 0, 0);
+      rd[i] = ok ? dyr[v] : make_uint4(0, 0, 0, 0);
+      rr[i] = (ok && drr) ? drr[v] : make_uint4(0, 0, 0, 0);
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float g = fd[j] * gm[j];
-        s1 += g;
-        s2 = fmaf(g, (fx[j] - mu) * rs, s2);
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float fx[8], fd[8];
+        unpack8(rx[i], fx);
+        unpack8(rd[i], fd);
+        const float4 g0 = G_IN_REGS ? gr0[i] : __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+        const float4 g1 = G_IN_REGS ? gr1[i] : __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = fd[j] * gm[j];
+          s1 += g;
+          s2 = fmaf(g, (fx[j] - mu) * rs, s2);
+        }
+      }
+    }
+    const float m1 = warp_sum(s1) / static_cast<float>(D);
+    const float m2 = warp_sum(s2) / static_cast<float>(D);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float fx[8], fd[8], fr[8], o[8];
+        unpack8(rx[i], fx);
+        unpack8(rd[i], fd);
+        unpack8(rr[i], fr);
+        const float4 g0 = G_IN_REGS ? gr0[i] : __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
+        const float4 g1 = G_IN_REGS ? gr1[i] : __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gm[j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
+        dxr[v] = pack8(o);
       }
     }
   }
-  const float m1 = warp_sum(s1) / static_cast<float>(D);
-  const float m2 = warp_sum(s2) / static_cast<float>(D);
-  uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+}
+
+// One-pass variant for D <= 1024 (MAXV <= 4): the same persistent row walk also accumulates this lane's columns of
+// dgamma = sum dy * xhat and dbeta = sum dy in registers over all the rows of the warp, then the block reduces its eight
+// warps through shared memory and issues one atomicAdd per column.  Saves the second pass over dy and x that the separate
+// column-sum kernel needs (6 -> 4 passes over [rows, D] with the residual gradient).
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy,
+                                                                  const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                  const __nv_bfloat16* dres, long long lddres,
+                                                                  __nv_bfloat16* dx, long long lddx, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta, int rows, int D) {
+  extern __shared__ float red[];   // [8 warps][2][MAXV * 256]
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int nvec = D >> 3;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float gm[MAXV][8], dg[MAXV][8], db[MAXV][8];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
-    if (v < nvec) {
-      float fx[8], fd[8], fr[8], o[8];
+    const float4 g0 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 g1 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
+    gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+  }
+  for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
+    const uint4* drr = dres ? reinterpret_cast<const uint4*>(dres + static_cast<long long>(row) * lddres) : nullptr;
+    uint4 rx[MAXV], rd[MAXV], rr[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      const bool ok = v < nvec;
+      rx[i] = ok ? xr[v] : make_uint4(0, 0, 0, 0);
+      rd[i] = ok ? dyr[v] : make_uint4(0, 0, 0, 0);
+      rr[i] = (ok && drr) ? drr[v] : make_uint4(0, 0, 0, 0);
+    }
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      float fx[8], fd[8];
       unpack8(rx[i], fx);
       unpack8(rd[i], fd);
-      unpack8(rr[i], fr);
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gm[j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
-      dxr[v] = pack8(o);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (fx[j] - mu) * rs;
+        const float g = fd[j] * gm[i][j];
+        s1 += g;
+        s2 = fmaf(g, xh, s2);
+        dg[i][j] = fmaf(fd[j], xh, dg[i][j]);
+        db[i][j] += fd[j];
+      }
     }
+    const float m1 = warp_sum(s1) / static_cast<float>(D);
+    const float m2 = warp_sum(s2) / static_cast<float>(D);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float fx[8], fd[8], fr[8], o[8];
+        unpack8(rx[i], fx);
+        unpack8(rd[i], fd);
+        unpack8(rr[i], fr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gm[i][j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
+        dxr[v] = pack8(o);
+      }
+    }
+  }
+  // block reduction of the column sums, then one atomicAdd per column and block
+  const int DP = MAXV * 256;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane + i * 32) * 8 + j;
+      red[(wib * 2 + 0) * DP + c] = dg[i][j];
+      red[(wib * 2 + 1) * DP + c] = db[i][j];
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[(w * 2 + 0) * DP + c];
+      b += red[(w * 2 + 1) * DP + c];
+    }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
   }
 }
 
@@ -407,7 +537,9 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int rpb = 8 * (D > 1024 ? 1 : 2);  // 8 warps x rows per warp (layernorm_fwd_kernel::RPW)
-  const int grid = (rows + rpb - 1) / rpb;
+  const int need = (rows + rpb - 1) / rpb;
+  const int cap = 4 * num_sms();           // persistent: CTAs walk the rows with a grid stride
+  const int grid = need < cap ? need : cap;
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (D <= 256) layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
@@ -437,6 +569,29 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   auto drp = reinterpret_cast<const __nv_bfloat16*>(dres);
+  if (dgamma != nullptr && dbeta != nullptr && D <= 1024) {   // one pass: dx and the parameter gradients together
+    const int need = (rows + 7) / 8;
+    const int cap = (D <= 512 ? 2 : 1) * num_sms();   // D > 512: 213 registers per thread, one CTA per SM
+    const int grid = need < cap ? need : cap;
+    int rc;
+#define OVK_LNB_FUSED(MV)                                                                                                     \
+    {                                                                                                                         \
+      const size_t sm = 8 * 2 * (MV) * 256 * sizeof(float);                                                                   \
+      static bool attr_##MV = false;                                                                                          \
+      if (!attr_##MV) {                                                                                                       \
+        cudaFuncSetAttribute(layernorm_bwd_fused_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)); \
+        attr_##MV = true;                                                                                                     \
+      }                                                                                                                       \
+      layernorm_bwd_fused_kernel<MV><<<grid, 256, sm, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx,      \
+                                                           dgamma, dbeta, rows, D);                                           \
+    }
+    if (D <= 256) OVK_LNB_FUSED(1)
+    else if (D <= 512) OVK_LNB_FUSED(2)
+    else OVK_LNB_FUSED(4)
+#undef OVK_LNB_FUSED
+    rc = check_launch("layernorm_bwd_fused_kernel");
+    return rc;
+  }
   if (dgamma != nullptr && dbeta != nullptr) {   // parameter gradients first: dx may alias dy
     const int gy = (D / 8 + 31) / 32;
     int gx = (num_sms() * 8 + gy - 1) / gy;
@@ -448,7 +603,8 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
     int rc = check_launch("layernorm_bwd_dgdb_kernel");
     if (rc) return rc;
   }
-  const int grid = (rows + 7) / 8;
+  const int need_dx = (rows + 7) / 8;
+  const int grid = need_dx < 4 * num_sms() ? need_dx : 4 * num_sms();   // persistent: warps walk the rows with a grid stride
   if (D <= 256) layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 512) layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
