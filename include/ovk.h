@@ -104,6 +104,17 @@ int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb,
                      int M, int N, int K, float alpha, const void* preact, long long ldp, int act, void* stream);
 int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
                      int M, int N, int K, float alpha, void* stream);
+/* C[M,N] = alpha * (*alpha_dev) * op(A) * op(B), op = the storage flags below; bf16 operands, bf16 or (c_is_f32) fp32 output.
+ *   a_mn = 0: A stored [M,K] (K contiguous);  a_mn = 1: A stored [K,M]
+ *   b_mn = 0: B stored [N,K] (the nn.Linear layout);  b_mn = 1: B stored [K,N]           (a_mn = 1 with b_mn = 0 is not provided)
+ * alpha_dev: optional DEVICE f32 scalar (NULL = 1) multiplied in by the epilogue, so a temperature that lives on the device
+ * (logit_scale.exp(), model.py:250,286-293) never has to be read back by the host.  Call sites: ClipLoss.get_logits
+ * (loss.py:102-118: logit_scale * image_features @ text_features.T, fp32 logits) and its autograd. */
+int ovk_gemm_bf16_scaled(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C,
+                         long long ldc, int c_is_f32, int M, int N, int K, float alpha, const float* alpha_dev, void* stream);
+/* y = a + b, bf16, n elements (multiple of 8): the residual add of transformer.py:263-264 as a stand-alone call, used when
+ * forward hooks sit on the branch's modules (cliptoolsoptimized.py:480-489) and the add cannot ride in a GEMM epilogue. */
+int ovk_add_bf16(const void* a, const void* b, void* y, long long n, void* stream);
 /* The activation as a standalone module call (nn.GELU / QuickGELU hooked by the ov-* scripts, transformer.py:33-36,
  * 232-236): y = act(x), and dx = dy * act'(x); bf16, n elements (multiple of 8), act = OVK_EPI_GELU_*. */
 int ovk_act_fwd(const void* x, void* y, long long n, int act, void* stream);

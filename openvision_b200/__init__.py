@@ -7,7 +7,8 @@ All compute goes through libovk.so (include/ovk.h); there is no CPU / ATen fallb
 """
 from ._lib import OvkError, load as load_library  # noqa: F401
 from .loss import ClipLoss, DualCaptionClipLoss, gather_features  # noqa: F401
-from .optim import FlatAdamW, cosine_schedule  # noqa: F401
+from .optim import FlatAdamW, cosine_schedule, decay_mask_from_modules  # noqa: F401
+from .configs import CONFIGS  # noqa: F401
 from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, TextTransformer, convert_weights_to_lp,  # noqa: F401
                     get_cast_dtype, get_input_dtype)
 from .transformer import (LayerNorm, LayerNormFp32, QuickGELU, ResidualAttentionBlock, Transformer,  # noqa: F401

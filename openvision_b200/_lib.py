@@ -52,6 +52,9 @@ _PROTOTYPES = {
                                  c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_gemm_bf16_tn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p]),
+    "ovk_gemm_bf16_scaled": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int,
+                                     c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "ovk_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "ovk_act_fwd": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "ovk_layernorm_fwd": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -148,6 +148,24 @@ class _Act(torch.autograd.Function):
         return ops.act_bwd(x, _c(dy).reshape(x.shape), ctx.kind), None
 
 
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add_fn(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b on add_kernel (the stand-alone residual add of the hooked, module-by-module block path)."""
+    if a.numel() % 8:
+        raise OvkError("add: element count must be a multiple of 8")
+    a, b = a.contiguous(), b.contiguous()
+    return _Add.apply(a, b) if _needs_grad(a, b) else ops.add(a, b)
+
+
 def act_fn(x: torch.Tensor, kind: str) -> torch.Tensor:
     return _Act.apply(x, kind) if _needs_grad(x) else ops.act_fwd(x, kind)
 

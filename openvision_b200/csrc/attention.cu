@@ -686,13 +686,13 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
     const uint32_t boxb[4] = {16, 1, ATT_BQ, 1};
     if ((rc = make_tmap_nd_bf16(&tmOb, out, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttL<0>::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttL<16>::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_once.done();
   }
   // a short remainder of query rows goes to the FMA-pipe tail kernel instead of a padded 128-row tile (hd = 64 only)
   int tail = L % ATT_BQ;

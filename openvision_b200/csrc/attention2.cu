@@ -484,11 +484,11 @@ int ovk_attention_fwd2_launch(const void* qkv, void* out, float* lse, int B, int
     const uint32_t box[4] = {A2_HD, 1, A2_BQ, 1};
     if ((rc = make_tmap_nd_bf16(&tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaError_t e = cudaFuncSetAttribute(attention_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention2): %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_once.done();
   }
   const int tail = (L > A2_BQ && L % A2_BQ == 1) ? 1 : 0;   // cls + power-of-two grid: remainder token handled outside the tiles
   const int l_main = L - tail;

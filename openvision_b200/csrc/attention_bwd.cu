@@ -476,8 +476,8 @@ extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* d
     if ((rc = make_tmap_nd_bf16(&tmOb, out, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
     if ((rc = make_tmap_nd_bf16(&tmDOb, dout, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
@@ -486,7 +486,7 @@ extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* d
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_once.done();
   }
   const long long items_ll = static_cast<long long>((L + AB_T - 1) / AB_T) * H * B;
   if (items_ll > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention_bwd: too many work items");

@@ -185,7 +185,8 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
           for (int q = 0; q < 4; ++q) S = fmaf(p[q].y, fast_exp2(p[q].x - M), S);
         }
-        if (col < n_all) ws_col[static_cast<long long>(tile_m) * n_all + col] = make_float2(M, S);
+        // (PAIR: the second CTA of the last pair may sit entirely past the last row; it has no slot in ws_col)
+        if (ti.m0 < n_loc && col < n_all) ws_col[static_cast<long long>(tile_m) * n_all + col] = make_float2(M, S);
       }
       named_bar_sync(bar_id, GEMM_GROUP_THREADS);
     }

@@ -17,6 +17,7 @@ constexpr int GEMM_MAX_STAT_PARTS = 64;   // partial-sum slots (one per 128 colu
 struct GemmEpi {
   const float* bias;  // f32[N] or null
   float alpha;
+  const float* alpha_dev;  // optional DEVICE scalar multiplied into alpha (the temperature: no host sync to read it)
   int flags;          // OVK_EPI_BIAS | OVK_EPI_RESIDUAL | act id | OVK_EPI_SAVE_PREACT
   ActCoef act;
   // LayerNorm folded into the GEMM (FUSE kernels): y = rstd_i * acc + d_n with B = the row-centred W . gamma
@@ -102,7 +103,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool has_bias = (ep.flags & OVK_EPI_BIAS) != 0;
     const bool has_res = !OUT_F32 && (EPI == EPI_DACT || (EPI == EPI_LINEAR && (ep.flags & OVK_EPI_RESIDUAL) != 0));
     const bool save_pre = EPI == EPI_ACT && (ep.flags & OVK_EPI_SAVE_PREACT) != 0;
-    const float alpha = ep.alpha;
+    const float alpha = ep.alpha_dev != nullptr ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
     GemmSched sched(M, N, BN, K, splits, PAIR, cx.rank);
     const bool reduce_out = OUT_F32 && sched.splits > 1;   // split-K partial sums are ADDED into a zeroed C
     int it = 0;
@@ -314,11 +315,11 @@ static int launch_gemm_t(const GemmArgs& g, cudaStream_t stream) {
   if (g.R && (rc = make_tmap_2d_bf16(&tmR, g.R, g.N, g.M, g.ldr, 64, GEMM_BM))) return rc;
   if (g.D && (rc = make_tmap_2d_bf16(&tmD, g.D, g.N, g.M, g.ldd, 64, GEMM_BM))) return rc;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EPI, OUT_F32, PAIR, FUSE>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_once.done();
   }
   const int bm = PAIR ? 2 * GEMM_BM : GEMM_BM;
   const int tiles = ((g.M + bm - 1) / bm) * ((g.N + BN - 1) / BN);
@@ -469,6 +470,23 @@ extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, lon
   return launch_gemm_bn<true, true, EPI_LINEAR, false>(g, s);
 }
 
+extern "C" int ovk_gemm_bf16_scaled(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C,
+                                    long long ldc, int c_is_f32, int M, int N, int K, float alpha, const float* alpha_dev,
+                                    void* stream) {
+  GemmArgs g{A, lda, a_mn != 0, B, ldb, b_mn != 0, C, ldc, c_is_f32 != 0, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  g.ep.bias = nullptr;
+  g.ep.alpha = alpha;
+  g.ep.alpha_dev = alpha_dev;
+  g.ep.flags = 0;
+  g.ep.act = act_coef(0);
+  int rc = check_common(g, "gemm_scaled");
+  if (rc) return rc;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a_mn && !b_mn) return set_error(OVK_ERR_SHAPE, "gemm_scaled: A^T * B^T is not provided (no call site needs it)");
+  if (!a_mn && !b_mn) return c_is_f32 ? launch_gemm_bn<false, false, EPI_LINEAR, true>(g, s) : launch_gemm_bn<false, false, EPI_LINEAR, false>(g, s);
+  if (!a_mn && b_mn) return c_is_f32 ? launch_gemm_bn<false, true, EPI_LINEAR, true>(g, s) : launch_gemm_bn<false, true, EPI_LINEAR, false>(g, s);
+  return c_is_f32 ? launch_gemm_bn<true, true, EPI_LINEAR, true>(g, s) : launch_gemm_bn<true, true, EPI_LINEAR, false>(g, s);
+}
 
 extern "C" int ovk_gemm_bf16_rowadd(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M,
                                     int N, int K, const void* row_add, int row_period, void* stream) {

@@ -12,6 +12,26 @@ int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int num_sms();
 
+// Per-device latch for function attributes (cudaFuncSetAttribute is per device, a process may drive several GPUs):
+//   static PerDeviceOnce once;  if (once.need()) { ...cudaFuncSetAttribute...; once.done(); }
+// Two threads racing through need() both set the attribute, which is harmless.
+struct PerDeviceOnce {
+  unsigned long long mask = 0;
+  static int slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= 64) ? -1 : dev;   // devices past 63: never latched, attribute set on every launch
+  }
+  bool need() const {
+    const int s = slot();
+    return s < 0 || ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> s) & 1ull) == 0;
+  }
+  void done() {
+    const int s = slot();
+    if (s >= 0) __atomic_fetch_or(&mask, 1ull << s, __ATOMIC_RELEASE);
+  }
+};
+
 // 2-D bf16 row-major tensor [outer, inner] with row stride ld (elements); box = [box_outer, box_inner];
 // SWIZZLE_128B (box_inner * 2 bytes must be <= 128).
 int make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,

@@ -577,10 +577,10 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
 #define OVK_LNB_FUSED(MV)                                                                                                     \
     {                                                                                                                         \
       const size_t sm = 8 * 2 * (MV) * 256 * sizeof(float);                                                                   \
-      static bool attr_##MV = false;                                                                                          \
-      if (!attr_##MV) {                                                                                                       \
+      static PerDeviceOnce attr_##MV;                                                                                         \
+      if (attr_##MV.need()) {                                                                                                 \
         cudaFuncSetAttribute(layernorm_bwd_fused_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)); \
-        attr_##MV = true;                                                                                                     \
+        attr_##MV.done();                                                                                                     \
       }                                                                                                                       \
       layernorm_bwd_fused_kernel<MV><<<grid, 256, sm, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx,      \
                                                            dgamma, dbeta, rows, D);                                           \

@@ -175,6 +175,21 @@ __global__ void __launch_bounds__(256) act_kernel(const __nv_bfloat16* __restric
   }
 }
 
+// y = a + b (bf16): the residual add of transformer.py:263-264 when a hooked sub-module produced the branch (its output may
+// have been replaced by the hook, so the add cannot ride in a GEMM epilogue).
+__global__ void __launch_bounds__(256) add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                                  __nv_bfloat16* __restrict__ y, long long nvec) {
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < nvec;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float fa[8], fb[8], o[8];
+    unpack8b(reinterpret_cast<const uint4*>(a)[idx], fa);
+    unpack8b(reinterpret_cast<const uint4*>(b)[idx], fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fa[j] + fb[j];
+    reinterpret_cast<uint4*>(y)[idx] = pack8b(o);
+  }
+}
+
 static int grid_for_b(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   const long long cap = static_cast<long long>(num_sms()) * 16;
@@ -259,4 +274,12 @@ extern "C" int ovk_act_bwd(const void* x, const void* dy, void* dx, long long n,
                                                        reinterpret_cast<const __nv_bfloat16*>(dy),
                                                        reinterpret_cast<__nv_bfloat16*>(dx), n / 8, act_coef(act & OVK_EPI_ACT_MASK));
   return check_launch("act_kernel<bwd>");
+}
+
+extern "C" int ovk_add_bf16(const void* a, const void* b, void* y, long long n, void* stream) {
+  if (n <= 0 || (n % 8)) return set_error(OVK_ERR_SHAPE, "add: element count must be a positive multiple of 8");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  add_kernel<<<grid_for_b(n / 8, 256), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b),
+                                                   reinterpret_cast<__nv_bfloat16*>(y), n / 8);
+  return check_launch("add_kernel");
 }

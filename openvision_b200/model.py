@@ -17,7 +17,7 @@ from torch import nn
 from . import ops
 from ._lib import OvkError
 from .transformer import (GELU, LayerNorm, LayerNormFp32, Linear, MultiheadSelfAttention, QuickGELU, Transformer, VisionTransformer,
-                          _as_bf16_2d, _out_dtype)
+                          _as_bf16_2d, _global_hooks, _out_dtype, _own_hooks)
 
 
 @dataclass
@@ -309,10 +309,15 @@ class CLIP(nn.Module):
         B, L = text.shape
         x = self.token_embedding(text) + self.positional_embedding[:L]          # gather + add (index plumbing)
         out_dtype = _out_dtype(x)
-        x2 = self.transformer.forward_tokens(_as_bf16_2d(x), B, L, owned=True)
-        D = x2.shape[-1]
-        # LayerNorm is per token, so ln_final(x)[pool] == ln_final(x[pool]): pool first, normalise B rows instead of B*L
-        x3 = x2.view(B, L, D)
+        hooked = _global_hooks() or _own_hooks(self.transformer) or _own_hooks(self.ln_final)
+        if hooked:   # model.py:276-277 through __call__, so hooks on the text transformer / ln_final see the stock tensors
+            x3 = self.ln_final(self.transformer(x.to(torch.bfloat16)))
+            D = x3.shape[-1]
+        else:
+            x2 = self.transformer.forward_tokens(_as_bf16_2d(x), B, L, owned=True)
+            D = x2.shape[-1]
+            # LayerNorm is per token, so ln_final(x)[pool] == ln_final(x[pool]): pool first, normalise B rows instead of B*L
+            x3 = x2.view(B, L, D)
         if self.text_pool_type == 'last':
             pooled = x3[:, -1]
         elif self.text_pool_type == 'first':
@@ -321,8 +326,10 @@ class CLIP(nn.Module):
             pooled = x3[torch.arange(B, device=x3.device), text.argmax(dim=-1)]
         else:
             raise OvkError("text pool_type='none' is outside the hot path of this build")
-        pooled = layer_norm_fn(pooled.contiguous(), self.ln_final.weight, self.ln_final.bias, self.ln_final.eps,
-                               self.ln_final)
+        if not hooked:
+            pooled = layer_norm_fn(pooled.contiguous(), self.ln_final.weight, self.ln_final.bias, self.ln_final.eps,
+                                   self.ln_final)
+        pooled = _as_bf16_2d(pooled)
         if self.text_projection is not None:
             if isinstance(self.text_projection, nn.Linear):
                 pooled = self.text_projection(pooled)
@@ -334,7 +341,8 @@ class CLIP(nn.Module):
     def get_logits(self, image, text):
         image_features = self.encode_image(image, normalize=True)
         text_features = self.encode_text(text, normalize=True)
-        image_logits = self.logit_scale.exp() * image_features @ text_features.T
+        from .loss import logits_fn
+        image_logits = logits_fn(image_features, text_features, self.logit_scale.exp())   # tcgen05 GEMM, fp32 logits
         if self.logit_bias is not None:
             image_logits += self.logit_bias
         text_logits = image_logits.T

@@ -62,6 +62,11 @@ def _require(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
         raise OvkError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
     if t.stride(-1) != 1:
         raise OvkError(f"{name}: innermost dimension must be contiguous")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream: a tensor of another GPU would be touched from the
+        # wrong device / stream (wrap the call in `with torch.cuda.device(t.device):`)
+        raise OvkError(f"{name}: tensor lives on cuda:{t.device.index} but the current device is "
+                       f"cuda:{torch.cuda.current_device()}")
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
@@ -252,6 +257,45 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torc
                   int(out_dtype == torch.float32), M, N, K, float(alpha), _stream())
     _count()
     return out
+
+
+def gemm_scaled(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, alpha: float = 1.0,
+                alpha_dev: Optional[torch.Tensor] = None, out_dtype=torch.float32,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = alpha * alpha_dev * op(a) @ op(b); a stored [M,K] (or [K,M] when a_mn), b stored [N,K] (or [K,N] when b_mn);
+    alpha_dev: optional fp32 device scalar (the temperature, never read back by the host). Kernel: gemm_bf16_kernel."""
+    _require(a, torch.bfloat16, "gemm_scaled.a", 2)
+    _require(b, torch.bfloat16, "gemm_scaled.b", 2)
+    K, M = (a.shape if a_mn else a.shape[::-1])
+    K2, N = (b.shape if b_mn else b.shape[::-1])
+    if K2 != K:
+        raise OvkError(f"gemm_scaled: reduction dimensions differ ({K} vs {K2})")
+    if alpha_dev is not None:
+        _require(alpha_dev, torch.float32, "gemm_scaled.alpha_dev")
+        if alpha_dev.numel() != 1:
+            raise OvkError("gemm_scaled: alpha_dev must hold one element")
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _require(out, out_dtype, "gemm_scaled.out", 2)
+    if tuple(out.shape) != (M, N):
+        raise OvkError("gemm_scaled.out has the wrong shape")
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_scaled", _p(a), a.stride(0), int(a_mn), _p(b), b.stride(0), int(b_mn), _p(out), out.stride(0),
+                  int(out_dtype == torch.float32), M, N, K, float(alpha), _p(alpha_dev), _stream())
+    _count()
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a + b (bf16, same shape, contiguous, numel % 8 == 0). Kernel: add_kernel."""
+    _require(a, torch.bfloat16, "add.a")
+    _require(b, torch.bfloat16, "add.b")
+    if a.shape != b.shape or not a.is_contiguous() or not b.is_contiguous():
+        raise OvkError("add: operands must be contiguous and of the same shape")
+    y = torch.empty_like(a)
+    _lib.call("ovk_add_bf16", _p(a), _p(b), _p(y), a.numel(), _stream())
+    _count()
+    return y
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, save_stats: bool = False,

@@ -30,11 +30,33 @@ def cosine_schedule(step: int, total_steps: int, warmup_steps: int, min_mult: fl
 
 
 def default_decay_mask(name: str, p: torch.Tensor) -> bool:
-    """wd_mults = [('.*/kernel$', 1.0)] (build_optax.py:257): the weight matrices / conv kernels decay, biases, LayerNorm
-    parameters, cls / positional embeddings and the temperature do not.  On the PyTorch surface: >= 2-D `*weight`, the packed
-    `in_proj_weight` and the `proj` matrix."""
-    leaf = name.rsplit(".", 1)[-1]
+    """wd_mults = [('.*/kernel$', 1.0)] (build_optax.py:257): the weight matrices / conv kernels decay; biases, LayerNorm
+    parameters, cls / positional embeddings, the temperature AND the vocabulary embedding do not (the reference's text
+    embedding is nn.Embed, whose parameter is called 'embedding' — models/text_transformer.py:633 — and matches no
+    '/kernel$').  On the PyTorch surface: >= 2-D `*weight` of Linear / Conv / out_proj, the packed `in_proj_weight`, and the
+    raw `proj` / `text_projection` matrices; `*embedding.weight` (nn.Embedding) is excluded."""
+    parts = name.rsplit(".", 2)
+    leaf = parts[-1]
+    if leaf == "weight" and len(parts) >= 2 and parts[-2].endswith("embedding"):
+        return False
     return p.dim() >= 2 and (leaf in ("weight", "in_proj_weight", "proj", "text_projection"))
+
+
+def decay_mask_from_modules(model: torch.nn.Module) -> Callable[[str, torch.Tensor], bool]:
+    """The same '/kernel$' rule derived from module TYPES instead of names (robust against renamed submodules): weights of
+    nn.Linear / nn.ConvNd / nn.MultiheadAttention and raw >= 2-D projection parameters named proj / text_projection decay,
+    everything owned by nn.Embedding / nn.LayerNorm does not."""
+    decayed = set()
+    for mod_name, mod in model.named_modules():
+        prefix = mod_name + "." if mod_name else ""
+        if isinstance(mod, (torch.nn.Linear, torch.nn.Conv1d, torch.nn.Conv2d)):
+            decayed.add(prefix + "weight")
+        elif isinstance(mod, torch.nn.MultiheadAttention):
+            decayed.update(prefix + n for n in ("in_proj_weight", "q_proj_weight", "k_proj_weight", "v_proj_weight"))
+        for n, q in mod.named_parameters(recurse=False):
+            if n in ("proj", "text_projection") and q.dim() >= 2:
+                decayed.add(prefix + n)
+    return lambda name, p: name in decayed
 
 
 class _Group:

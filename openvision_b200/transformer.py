@@ -69,6 +69,37 @@ def _out_dtype(x: torch.Tensor) -> torch.dtype:
     return x.dtype if x.is_floating_point() else torch.float32
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# hooks: the fused paths call kernels, not sub-modules, so a forward / backward hook registered on a sub-module would never
+# fire there.  Callers of the reference hook arbitrary modules (cliptoolsoptimized.py:480-489, :1149-1164), so every
+# fused path first checks for hooks and otherwise goes module by module through nn.Module.__call__.
+# ----------------------------------------------------------------------------------------------------------------
+def _own_hooks(m: nn.Module) -> bool:
+    return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks or m._backward_pre_hooks)
+
+
+def _global_hooks() -> bool:
+    mm = torch.nn.modules.module
+    return bool(mm._global_forward_hooks or mm._global_forward_pre_hooks or mm._global_backward_hooks or
+                mm._global_backward_pre_hooks)
+
+
+def _tree_hooks(m: nn.Module, include_self: bool = True) -> bool:
+    """any hook on m's sub-modules (and on m itself when include_self)"""
+    if _global_hooks():
+        return True
+    it = m.modules()
+    if not include_self:
+        next(it)
+    return any(_own_hooks(x) for x in it)
+
+
+def _residual_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    from .autograd import add_fn
+    shape = a.shape
+    return add_fn(_as_bf16_2d(a), _as_bf16_2d(b)).reshape(shape)
+
+
 class LayerNorm(nn.LayerNorm):
     """transformer.py:24-30 — LayerNorm returning the input dtype; statistics in fp32 (layernorm_fwd_kernel)."""
 
@@ -250,10 +281,10 @@ class ResidualAttentionBlock(nn.Module):
         return None  # unknown activation module: run it as a module
 
     def _fusable(self) -> bool:
-        g = self.mlp.gelu
-        hooked = bool(g._forward_hooks) or bool(g._forward_pre_hooks) or bool(g._backward_hooks)
+        """True when the whole block may run as one fused kernel sequence: no LayerScale, a known activation, and NO hook
+        on any sub-module (hooks on the block itself fire in __call__ and do not prevent fusing)."""
         plain = isinstance(self.ls_1, nn.Identity) and isinstance(self.ls_2, nn.Identity)
-        return plain and not hooked and self._act_kind() is not None
+        return plain and self._act_kind() is not None and not _tree_hooks(self, include_self=False)
 
     def attention(self, q_x, k_x=None, v_x=None, attn_mask=None):
         return self.attn(q_x, k_x, v_x, need_weights=False, attn_mask=attn_mask)[0]
@@ -274,20 +305,12 @@ class ResidualAttentionBlock(nn.Module):
         if self._fusable():
             y, _ = self.forward_tokens(_as_bf16_2d(q_x), B, L, inplace=False)
             return y.reshape(B, L, D).to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
-        # module-by-module path (hooks on nn.GELU, LayerScale): every submodule still runs on libovk kernels
-        if isinstance(self.ls_1, nn.Identity) and isinstance(self.ls_2, nn.Identity):
-            from .autograd import attention_block_fn, linear_fn
-            x2 = _as_bf16_2d(q_x)
-            h = _as_bf16_2d(self.ln_1(x2))
-            x_mid = attention_block_fn(h, self.attn, B, L, residual=x2)                 # x + attn(ln_1(x))
-            f = self.mlp.gelu(self.mlp.c_fc(self.ln_2(x_mid).reshape(B, L, D)))          # hooks on mlp.gelu fire here
-            pj = self.mlp.c_proj
-            y = linear_fn(_as_bf16_2d(f), pj.weight, pj.bias, x_mid, None, pj)           # x + c_proj(...)
-            return y.reshape(B, L, D).to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
-        # LayerScale variants (not used by any OpenVision config): generic composition
-        x = q_x + self.ls_1(self.attention(q_x=self.ln_1(q_x)))
-        x = x + self.ls_2(self.mlp(self.ln_2(x)))
-        return x
+        # module-by-module path (hooks on any sub-module, LayerScale, unknown activation): the reference's forward
+        # (transformer.py:254-265) with every sub-module invoked through __call__ so its hooks fire, all on libovk kernels
+        x = q_x if q_x.dtype == torch.bfloat16 else q_x.to(torch.bfloat16)
+        x = _residual_add(x, _as_bf16_2d(self.ls_1(self.attention(q_x=self.ln_1(x)))).reshape(B, L, D))
+        x = _residual_add(x, _as_bf16_2d(self.ls_2(self.mlp(self.ln_2(x)))).reshape(B, L, D))
+        return x.to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
 
 
 class Transformer(nn.Module):
@@ -328,7 +351,7 @@ class Transformer(nn.Module):
         """bf16 [B*L, D] -> bf16 [B*L, D]; `owned` says whether x2 may be overwritten."""
         stats = None   # LayerNorm statistics of x2, produced by the epilogue of the GEMM that wrote it
         for r in self.resblocks:
-            if r._fusable():
+            if r._fusable() and not _own_hooks(r):
                 r._recompute_mlp_hidden = self.recompute_mlp_hidden
                 if self.grad_checkpointing and torch.is_grad_enabled() and x2.requires_grad:
                     x2, stats = checkpoint(r.forward_tokens, x2, B, L, False, stats, use_reentrant=False)
@@ -491,8 +514,42 @@ class VisionTransformer(nn.Module):
         cols = ops.im2col_patches(images.contiguous(), P, kpad, lead_rows=1)
         return ops.gemm_rowadd(cols, w, hit[1]), B, N
 
+    def _forward_modules(self, x: torch.Tensor):
+        """transformer.py:609-651 line by line, every sub-module invoked through __call__ (forward / backward hooks on conv1,
+        ln_pre, transformer, ln_post fire with the stock tensor contracts); taken when one of them carries a hook."""
+        from .autograd import embed_assemble_fn, linear_fn, pool_fn
+        out_dtype = _out_dtype(x)
+        y = self.conv1(x)                                                       # :610  [B, D, gh, gw]
+        B, D = y.shape[0], y.shape[1]
+        tok = y.reshape(B, D, -1).permute(0, 2, 1)                              # :611-612  [B, N, D]
+        N = tok.shape[1]
+        x2 = embed_assemble_fn(_as_bf16_2d(tok), self.class_embedding, self.positional_embedding, B, N, self)   # :615-617
+        L = N + 1
+        x3 = self.patch_dropout(x2.reshape(B, L, D))                            # :619
+        L = x3.shape[1]
+        x3 = self.ln_pre(x3)                                                    # :620
+        x3 = self.transformer(x3)                                               # :621
+        if self.pool_type == 'none':
+            raise OvkError("pool_type='none' is outside the hot path of this build")
+        if self.final_ln_after_pool:                                            # :638-640
+            x2 = _as_bf16_2d(x3)
+            pooled = self.ln_post(pool_fn(x2, B, L, self.pool_type))
+        else:                                                                   # :641-643
+            x3 = self.ln_post(x3)
+            x2 = _as_bf16_2d(x3)
+            pooled = pool_fn(x2, B, L, self.pool_type)
+        if self.proj is not None:                                               # :645-646
+            pooled = linear_fn(_as_bf16_2d(pooled), self.proj, None, None, None, self, transpose_weight=True)
+        pooled = pooled.to(out_dtype)
+        if self.output_tokens:
+            return pooled, x2.reshape(B, L, D)[:, 1:].to(out_dtype)
+        return pooled
+
     def forward(self, x: torch.Tensor):
         from .autograd import embed_assemble_fn, layer_norm_fn, linear_fn, pool_fn
+        if _global_hooks() or any(_own_hooks(m) for m in (self.conv1, self.patch_dropout, self.ln_pre, self.transformer,
+                                                          self.ln_post)):
+            return self._forward_modules(x)
         images = x
         out_dtype = _out_dtype(images)
         x2 = self._embed_fused(images)                                          # :610-617 in one GEMM (inference)

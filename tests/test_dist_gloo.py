@@ -72,3 +72,50 @@ def test_loss_weights_table():
     assert loss_weights(1.0, 16, 64, 4, False, False) == 1 / 128     # global objective, own-slice gradient
     assert loss_weights(1.0, 16, 64, 4, False, True) == 1 / 32       # W copies of the global objective
     assert loss_weights(2.0, 16, 64, 4, False, False) == 2 / 128
+
+
+def _gather_worker(rank, world, local_loss, gwg, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from openvision_b200.loss import gather_features
+    from oracle import synth
+    img, txt = synth.make_features(16, 8, seed=5, dtype=torch.float64)
+    nl = 16 // world
+    i_l = img[rank * nl:(rank + 1) * nl].clone().requires_grad_(True)
+    t_l = txt[rank * nl:(rank + 1) * nl].clone().requires_grad_(True)
+    ai, at = gather_features(i_l, t_l, local_loss, gwg, rank, world)
+    # a loss that weights every gathered row differently, so the gradient shows which copies carry autograd
+    w = torch.arange(1, 17, dtype=torch.float64)[:, None]
+    total = (ai * w).sum() + 2.0 * (at * w).sum()
+    if total.requires_grad:      # local_loss without gather_with_grad: the gathered copies are detached (loss.py:52-55)
+        total.backward()
+    torch.save(dict(ai=ai.detach(), at=at.detach(), gi=i_l.grad, gt=t_l.grad), os.path.join(outdir, f"g{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("local_loss,gwg", [(False, False), (True, False), (False, True)])
+def test_gather_features_semantics(local_loss, gwg):
+    """loss.py:19-63: every rank sees the concatenation in rank order; with gather_with_grad the gradient of ALL ranks'
+    copies flows back (summed over ranks by torch.distributed.nn.all_gather), without it only the rank's own slice carries
+    autograd, and only when local_loss is False (loss.py:56-61)."""
+    from oracle import synth
+    world = 2
+    img, txt = synth.make_features(16, 8, seed=5, dtype=torch.float64)
+    port = 29810 + int(local_loss) * 2 + int(gwg)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_gather_worker, args=(world, local_loss, gwg, port, d), nprocs=world, join=True)
+        res = [torch.load(os.path.join(d, f"g{r}.pt")) for r in range(world)]
+    w = torch.arange(1, 17, dtype=torch.float64)[:, None].expand(16, 8)
+    for r, x in enumerate(res):
+        assert torch.equal(x["ai"], img) and torch.equal(x["at"], txt)
+        sl = slice(r * 8, (r + 1) * 8)
+        if gwg:          # both ranks' losses differentiate this rank's rows
+            assert torch.allclose(x["gi"], world * w[sl]) and torch.allclose(x["gt"], 2.0 * world * w[sl])
+        elif not local_loss:
+            assert torch.allclose(x["gi"], w[sl]) and torch.allclose(x["gt"], 2.0 * w[sl])
+        else:            # no gradient reaches the local features through the gathered copies
+            assert x["gi"] is None and x["gt"] is None

@@ -91,3 +91,50 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
                 assert "vit_oracle" not in src, f"{f} references the oracle"
+
+
+def test_product_configs_are_the_oracle_configs():
+    """bench.py's GPU arm takes its model configurations from the product package (no oracle import on that arm)."""
+    from openvision_b200.configs import CONFIGS
+    assert CONFIGS == synth.CONFIGS
+
+
+def test_hooks_anywhere_in_a_block_disable_the_fused_path():
+    m = build("mini-ov")
+    blk = m.visual.transformer.resblocks[0]
+    for mod in (blk.ln_1, blk.attn, blk.attn.out_proj, blk.mlp, blk.mlp.c_fc, blk.mlp.c_proj, blk.ln_2):
+        assert blk._fusable()
+        for reg in (mod.register_forward_hook, mod.register_forward_pre_hook, mod.register_full_backward_hook):
+            h = reg(lambda *a: None)
+            assert not blk._fusable(), (type(mod).__name__, reg.__name__)
+            h.remove()
+    h = blk.register_forward_hook(lambda *a: None)       # a hook on the block itself fires in __call__: fusing stays legal
+    assert blk._fusable()
+    from openvision_b200.transformer import _own_hooks
+    assert _own_hooks(blk)
+    h.remove()
+    g = torch.nn.modules.module.register_module_forward_hook(lambda *a: None)
+    assert not blk._fusable()
+    g.remove()
+    assert blk._fusable()
+
+
+def test_decay_mask_is_the_reference_kernel_rule():
+    """build_optax.py:257 wd_mults=[('.*/kernel$', 1.0)]: Dense / conv kernels decay; biases, LayerNorm scales, cls / pos
+    embeddings, the temperature and the vocabulary embedding (nn.Embed 'embedding', text_transformer.py:633) do not."""
+    from openvision_b200.optim import decay_mask_from_modules, default_decay_mask
+    m = build("mini-ov")
+    named = dict(m.named_parameters())
+    by_type = decay_mask_from_modules(m)
+    decayed = {n for n, p in named.items() if default_decay_mask(n, p)}
+    assert decayed == {n for n, p in named.items() if by_type(n, p)}
+    assert "token_embedding.weight" not in decayed
+    assert "positional_embedding" not in decayed and "visual.positional_embedding" not in decayed
+    assert "visual.class_embedding" not in decayed and "logit_scale" not in decayed
+    assert not any(n.endswith(".bias") or "ln_" in n for n in decayed)
+    want = {"visual.conv1.weight", "visual.proj", "text_projection"}
+    for pre, nl in (("visual.transformer.resblocks.", 2), ("transformer.resblocks.", 2)):
+        for i in range(nl):
+            want |= {f"{pre}{i}.attn.in_proj_weight", f"{pre}{i}.attn.out_proj.weight", f"{pre}{i}.mlp.c_fc.weight",
+                     f"{pre}{i}.mlp.c_proj.weight"}
+    assert decayed == want
