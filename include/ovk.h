@@ -193,29 +193,39 @@ int ovk_l2_normalize_bwd(const void* x, const void* dy, int dy_is_f32, void* dx,
  *   z = scale * A_loc · B_all^T   (rows = this rank's image features, cols = all text features);
  *   labels: row i <-> column (row_offset + i)                                   (loss.py:89-100 get_ground_truth)
  *   a_loc : bf16 [n_loc, E]    b_all : bf16 [n_all, E]
- * ovk_clip_loss_fwd outputs (all f32, natural-log units):
- *   row_lse[n_loc]  = logsumexp_j z_ij            diag[n_loc] = z_i,label(i)
+ * The temperature is read ON THE DEVICE (scale_dev: f32[1] = logit_scale.exp(), model.py:250,295-315), so no call forces a
+ * host synchronisation.
+ * ovk_clip_loss_fwd : partial statistics of the column window [col_offset, col_offset + n_cols) of the row block, b_rows =
+ *   bf16 [n_cols, E] = the features of THOSE columns (col_offset % 256 == 0; every window but the last a multiple of 256
+ *   wide).  One call with col_offset = 0, n_cols = n_all covers everything; several calls with disjoint windows tiling
+ *   [0, n_all) let a rank start on its own text block while the all-gather of the others is still in flight.  Writes
+ *   diag[i] = z_i,label(i) for the rows whose label falls into the window, and per-tile (max, sum) partials into `workspace`
+ *   (f32 scratch of ovk_clip_loss_workspace_floats(n_loc, n_all) elements, shared by all windows).
+ * ovk_clip_loss_finalize : merges the partials (all windows must have run) into, all f32, natural-log units:
+ *   row_lse[n_loc]  = logsumexp_j z_ij
  *   col_max[n_all], col_sum[n_all] : THIS row block's column statistics, sum_i exp(z_ij - col_max_j) = col_sum_j,
  *                                    so that W ranks can merge their row blocks into global column LSEs.
- *   workspace: f32 scratch of ovk_clip_loss_workspace_floats(n_loc, n_all) elements.
  * ovk_clip_loss_combine : col_lse[j] = log sum_w exp(col_max[w][j]) * col_sum[w][j]   over `parts` stacked [parts, n_all] arrays
  * ovk_clip_loss_value   : out3[0] = 0.5/n_loc * (sum_i (row_lse_i - diag_i) + sum_i (col_lse[row_offset+i] - diag_i)),
  *                         out3[1], out3[2] = the two sums                             (loss.py:126-129)
- * ovk_clip_loss_grad_logits : G[i,j] = w_row * exp(z_ij - row_lse_i) + w_col * exp(z_ij - col_lse_j)
- *                                     - (w_row + w_col) * [j == row_offset + i],  bf16 [n_loc, ldg];
+ * ovk_clip_loss_grad_logits : G[i,j] = g * (w_row * exp(z_ij - row_lse_i) + w_col * exp(z_ij - col_lse_j)
+ *                                     - (w_row + w_col) * [j == row_offset + i]),  bf16 [n_loc, ldg];
+ *                         g = *grad_out_dev (the upstream gradient, a device scalar; NULL = 1);
  *                         d_scale_partial (f32[1], ACCUMULATED) += sum_ij G_ij * z_ij / scale.
- *   The feature gradients are then dA = scale * G · B_all (ovk_gemm_bf16_nn) and dB = scale * G^T · A_loc (ovk_gemm_bf16_tn).
+ *   The feature gradients are then dA = scale * G · B_all and dB = scale * G^T · A_loc (ovk_gemm_bf16_scaled, alpha_dev = scale_dev).
  */
 long long ovk_clip_loss_workspace_floats(int n_loc, int n_all);
-int ovk_clip_loss_fwd(const void* a_loc, const void* b_all, int n_loc, int n_all, int E, int row_offset, float scale,
-                      float* row_lse, float* diag, float* col_max, float* col_sum, float* workspace, void* stream);
+int ovk_clip_loss_fwd(const void* a_loc, const void* b_rows, int n_loc, int n_cols, int col_offset, int n_all, int E,
+                      int row_offset, const float* scale_dev, float* diag, float* workspace, void* stream);
+int ovk_clip_loss_finalize(const float* workspace, int n_loc, int n_all, float* row_lse, float* col_max, float* col_sum,
+                           void* stream);
 int ovk_clip_loss_combine(const float* col_max_parts, const float* col_sum_parts, int parts, int n_all, float* col_lse,
                           void* stream);
 int ovk_clip_loss_value(const float* row_lse, const float* col_lse, const float* diag, int n_loc, int row_offset,
                         float* out3, void* stream);
 int ovk_clip_loss_grad_logits(const void* a_loc, const void* b_all, int n_loc, int n_all, int E, int row_offset,
-                              float scale, const float* row_lse, const float* col_lse, float w_row, float w_col,
-                              void* G, long long ldg, float* d_scale_partial, void* stream);
+                              const float* scale_dev, const float* row_lse, const float* col_lse, float w_row, float w_col,
+                              const float* grad_out_dev, void* G, long long ldg, float* d_scale_partial, void* stream);
 
 /* Optimizer step of the training recipe (src/optim/build_optax.py:188-278: clip_by_global_norm -> scale_by_adam(b1, b2,
  * mu_dtype=bf16) -> add_decayed_weights -> scale(lr) -> schedule -> -1; configs/openvision.py:265-289) on flat buffers:

@@ -72,12 +72,13 @@ _PROTOTYPES = {
     "ovk_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "ovk_pool_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ovk_clip_loss_workspace_floats": (c_longlong, [c_int, c_int]),
-    "ovk_clip_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_void_p]),
+    "ovk_clip_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "ovk_clip_loss_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ovk_clip_loss_combine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ovk_clip_loss_value": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "ovk_clip_loss_grad_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
-                                          c_float, c_float, c_void_p, c_longlong, c_void_p, c_void_p]),
+    "ovk_clip_loss_grad_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_float, c_float, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p]),
     "ovk_l2_normalize": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),
 }
 

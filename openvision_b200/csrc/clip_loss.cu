@@ -56,7 +56,7 @@ template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      float2* __restrict__ ws_row, float2* __restrict__ ws_col, float* __restrict__ diag, int n_loc,
-                     int n_all, int E, int row_offset, float scale) {
+                     int n_cols, int col_offset, int n_all, int E, int row_offset, const float* __restrict__ scale_ptr) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using L = FwdLayout<PAIR>;
   GemmCtx<CL_BN, L> cx(smem_raw);
@@ -64,9 +64,9 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5;
 
   if (warp == 0) {
-    if (elect_one()) gemm_producer<CL_BN, false, false>(cx, &tmA, &tmB, n_loc, n_all, E);
+    if (elect_one()) gemm_producer<CL_BN, false, false>(cx, &tmA, &tmB, n_loc, n_cols, E);
   } else if (warp == 1) {
-    if (elect_one()) gemm_mma_issuer<CL_BN, false, false>(cx, tmem_base, n_loc, n_all, E);
+    if (elect_one()) gemm_mma_issuer<CL_BN, false, false>(cx, tmem_base, n_loc, n_cols, E);
   } else if (warp >= GEMM_CTRL_WARPS) {
     const int ew = warp - GEMM_CTRL_WARPS;
     const int grp = ew >> 2;
@@ -75,18 +75,19 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int et = quad * 32 + lane;
     const uint32_t bar_id = 1 + grp;
     const uint32_t scol = smem_u32(cx.epi_scratch());  // float2 [4][256]
+    const float scale = __ldg(scale_ptr);              // the temperature lives on the device (no host read-back)
     const float s2 = scale * LOG2E;
-    GemmSched sched(n_loc, n_all, CL_BN, E, 1, PAIR, cx.rank);
+    GemmSched sched(n_loc, n_cols, CL_BN, E, 1, PAIR, cx.rank);
     int it = 0;
     for (int t = cx.first; t < sched.total; t += cx.stride, ++it) {
       const GemmTileInfo ti = sched.tile(t, CL_BN);
-      const int tile_n = ti.n0 / CL_BN;
+      const int tile_n = (col_offset + ti.n0) / CL_BN;   // slot index over ALL columns (col_offset % 256 == 0)
       const int tile_m = ti.m0 / GEMM_BM;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = ti.m0 + et;
       const bool row_valid = row < n_loc;
-      const int label = row_offset + row;  // column holding this row's positive pair
+      const int label = row_offset + row - col_offset;  // column (of this window) holding this row's positive pair
       float m_row = NEG_INF, l_row = 0.f;
       mbar_wait(&cx.tmem_full[acc], acc_phase, 4);
       tc_fence_after();
@@ -96,7 +97,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int col_in_tile = grp * 128 + c * 32;
         const int col0 = ti.n0 + col_in_tile;
         const uint32_t sdst = scol + ((quad * CL_BN + col_in_tile + lane) << 3);
-        if (col0 >= n_all) {  // uniform: chunk entirely past the last column
+        if (col0 >= n_cols) {  // uniform: chunk entirely past the last column
           sts_f32x2(sdst, NEG_INF, 0.f);
           continue;
         }
@@ -107,7 +108,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float cm[4] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF};   // four independent chains (the epilogue is latency-bound)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          z[j] = (row_valid && col0 + j < n_all) ? __uint_as_float(v[j]) * s2 : NEG_INF;
+          z[j] = (row_valid && col0 + j < n_cols) ? __uint_as_float(v[j]) * s2 : NEG_INF;
           cm[j & 3] = fmaxf(cm[j & 3], z[j]);
         }
         const float cmax = fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3]));
@@ -147,7 +148,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         float cs = warp_column_sums(e, lane);  // lane j: sum over the warp's 32 rows of column col0 + j
         float cref_out = c_ref;
-        unsigned need = __ballot_sync(0xffffffffu, cs < 7.8886e-31f /* 2^-100 */ && col0 + (int)lane < n_all);
+        unsigned need = __ballot_sync(0xffffffffu, cs < 7.8886e-31f /* 2^-100 */ && col0 + (int)lane < n_cols);
         while (need) {  // columns far below the sub-block maximum: exact path, one column at a time
           const int jj = __ffs(need) - 1;
           need &= need - 1;
@@ -186,7 +187,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int q = 0; q < 4; ++q) S = fmaf(p[q].y, fast_exp2(p[q].x - M), S);
         }
         // (PAIR: the second CTA of the last pair may sit entirely past the last row; it has no slot in ws_col)
-        if (ti.m0 < n_loc && col < n_all) ws_col[static_cast<long long>(tile_m) * n_all + col] = make_float2(M, S);
+        if (ti.m0 < n_loc && col < n_cols) ws_col[static_cast<long long>(tile_m) * n_all + col_offset + col] = make_float2(M, S);
       }
       named_bar_sync(bar_id, GEMM_GROUP_THREADS);
     }
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmG, const float* __restrict__ row_lse,
                       const float* __restrict__ col_lse, float* __restrict__ d_scale, int n_loc, int n_all, int E,
-                      int row_offset, float scale, float w_row, float w_col) {
+                      int row_offset, const float* __restrict__ scale_ptr, const float* __restrict__ gout_ptr, float w_row,
+                      float w_col) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   using L = GradLayout<PAIR>;
   GemmCtx<CL_BN, L> cx(smem_raw);
@@ -298,7 +300,12 @@ clip_loss_grad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t bar_id = 1 + grp;
     const uint32_t sbuf = smem_u32(cx.c_stage(grp));
     const uint32_t clse_base = smem_u32(cx.epi_scratch());
-    const float s2 = scale * LOG2E;
+    const float s2 = __ldg(scale_ptr) * LOG2E;
+    if (gout_ptr != nullptr) {   // upstream dL (a device scalar) folded into the weights
+      const float go = __ldg(gout_ptr);
+      w_row *= go;
+      w_col *= go;
+    }
     const float w_diag = w_row + w_col;
     float ds = 0.f;  // sum G_ij * acc_ij  (= sum G * z / scale)
     GemmSched sched(n_loc, n_all, CL_BN, E, 1, PAIR, cx.rank);
@@ -415,31 +422,40 @@ extern "C" long long ovk_clip_loss_workspace_floats(int n_loc, int n_all) {
   return 2LL * (2LL * cl_tiles_n(n_all) * n_loc + static_cast<long long>(cl_tiles_m(n_loc)) * n_all);
 }
 
-extern "C" int ovk_clip_loss_fwd(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E, int row_offset,
-                                 float scale, float* row_lse, float* diag, float* col_max, float* col_sum,
-                                 float* workspace, void* stream) {
-  if (n_loc <= 0 || n_all <= 0 || E <= 0) return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: empty problem");
+extern "C" int ovk_clip_loss_fwd(const void* a_loc, const void* b_rows, int n_loc, int n_cols, int col_offset, int n_all,
+                                 int E, int row_offset, const float* scale_dev, float* diag, float* workspace, void* stream) {
+  if (n_loc <= 0 || n_cols <= 0 || n_all <= 0 || E <= 0) return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: empty problem");
   if (E % 8) return set_error(OVK_ERR_ALIGN, "clip_loss_fwd: E must be a multiple of 8");
+  if (col_offset < 0 || col_offset + n_cols > n_all || (col_offset % CL_BN))
+    return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: column window [%d, %d) must start on a multiple of %d inside [0, %d)", col_offset,
+                     col_offset + n_cols, CL_BN, n_all);
+  if (col_offset + n_cols < n_all && (n_cols % CL_BN))
+    return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: only the last column window may end off a multiple of %d", CL_BN);
   if (row_offset < 0 || row_offset + n_loc > n_all)
     return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: rows [%d, %d) have no matching columns in [0, %d)", row_offset, row_offset + n_loc, n_all);
-  if (!workspace) return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: workspace is required");
+  if (!workspace || !scale_dev) return set_error(OVK_ERR_SHAPE, "clip_loss_fwd: workspace and scale_dev are required");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = make_tmap_2d_bf16(&tmA, img_loc, E, n_loc, E, GEMM_BK, GEMM_BM))) return rc;
-  if ((rc = make_tmap_2d_bf16(&tmB, txt_all, E, n_all, E, GEMM_BK, n_loc >= 512 ? CL_BN / 2 : CL_BN))) return rc;
-  const int tm = cl_tiles_m(n_loc), tn = cl_tiles_n(n_all);
+  if ((rc = make_tmap_2d_bf16(&tmA, a_loc, E, n_loc, E, GEMM_BK, GEMM_BM))) return rc;
+  if ((rc = make_tmap_2d_bf16(&tmB, b_rows, E, n_cols, E, GEMM_BK, n_loc >= 512 ? CL_BN / 2 : CL_BN))) return rc;
+  const int tm = cl_tiles_m(n_loc), tn_all = cl_tiles_n(n_all), tn = cl_tiles_n(n_cols);
   float2* ws_row = reinterpret_cast<float2*>(workspace);
-  float2* ws_col = ws_row + 2LL * tn * n_loc;
-  if (n_loc >= 512) {   // CTA pairs (256-row tiles)
-    if ((rc = launch_loss_kernel<true>(clip_loss_fwd_kernel<true>, FwdLayout<true>::DYN_BYTES, ((n_loc + 255) / 256) * tn, s,
-                                       tmA, tmB, ws_row, ws_col, diag, n_loc, n_all, E, row_offset, scale)))
-      return rc;
-  } else {
-    if ((rc = launch_loss_kernel<false>(clip_loss_fwd_kernel<false>, FwdLayout<false>::DYN_BYTES, tm * tn, s, tmA, tmB, ws_row,
-                                        ws_col, diag, n_loc, n_all, E, row_offset, scale)))
-      return rc;
-  }
+  float2* ws_col = ws_row + 2LL * tn_all * n_loc;
+  if (n_loc >= 512)   // CTA pairs (256-row tiles)
+    return launch_loss_kernel<true>(clip_loss_fwd_kernel<true>, FwdLayout<true>::DYN_BYTES, ((n_loc + 255) / 256) * tn, s, tmA, tmB,
+                                    ws_row, ws_col, diag, n_loc, n_cols, col_offset, n_all, E, row_offset, scale_dev);
+  return launch_loss_kernel<false>(clip_loss_fwd_kernel<false>, FwdLayout<false>::DYN_BYTES, tm * tn, s, tmA, tmB, ws_row, ws_col,
+                                   diag, n_loc, n_cols, col_offset, n_all, E, row_offset, scale_dev);
+}
+
+extern "C" int ovk_clip_loss_finalize(const float* workspace, int n_loc, int n_all, float* row_lse, float* col_max,
+                                      float* col_sum, void* stream) {
+  if (n_loc <= 0 || n_all <= 0) return set_error(OVK_ERR_SHAPE, "clip_loss_finalize: empty problem");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int tm = cl_tiles_m(n_loc), tn = cl_tiles_n(n_all);
+  const float2* ws_row = reinterpret_cast<const float2*>(workspace);
+  const float2* ws_col = ws_row + 2LL * tn * n_loc;
   const int total = n_loc + n_all;
   clip_loss_finalize_kernel<<<(total + 255) / 256, 256, 0, s>>>(ws_row, ws_col, n_loc, n_all, 2 * tn, tm, row_lse, col_max, col_sum);
   return check_launch("clip_loss_finalize_kernel");
@@ -462,11 +478,12 @@ extern "C" int ovk_clip_loss_value(const float* row_lse, const float* col_lse, c
 }
 
 extern "C" int ovk_clip_loss_grad_logits(const void* img_loc, const void* txt_all, int n_loc, int n_all, int E,
-                                         int row_offset, float scale, const float* row_lse, const float* col_lse,
-                                         float w_row, float w_col, void* G, long long ldg, float* d_scale_partial,
-                                         void* stream) {
+                                         int row_offset, const float* scale_dev, const float* row_lse, const float* col_lse,
+                                         float w_row, float w_col, const float* grad_out_dev, void* G, long long ldg,
+                                         float* d_scale_partial, void* stream) {
   if (n_loc <= 0 || n_all <= 0 || E <= 0) return set_error(OVK_ERR_SHAPE, "clip_loss_grad: empty problem");
   if ((E % 8) || (ldg % 8)) return set_error(OVK_ERR_ALIGN, "clip_loss_grad: E and ldg must be multiples of 8");
+  if (!scale_dev) return set_error(OVK_ERR_SHAPE, "clip_loss_grad: scale_dev is required");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   CUtensorMap tmA, tmB, tmG;
   int rc;
@@ -476,8 +493,8 @@ extern "C" int ovk_clip_loss_grad_logits(const void* img_loc, const void* txt_al
   if (n_loc >= 512)
     return launch_loss_kernel<true>(clip_loss_grad_kernel<true>, GradLayout<true>::DYN_BYTES,
                                     ((n_loc + 255) / 256) * cl_tiles_n(n_all), s, tmA, tmB, tmG, row_lse, col_lse,
-                                    d_scale_partial, n_loc, n_all, E, row_offset, scale, w_row, w_col);
+                                    d_scale_partial, n_loc, n_all, E, row_offset, scale_dev, grad_out_dev, w_row, w_col);
   return launch_loss_kernel<false>(clip_loss_grad_kernel<false>, GradLayout<false>::DYN_BYTES,
                                    cl_tiles_m(n_loc) * cl_tiles_n(n_all), s, tmA, tmB, tmG, row_lse, col_lse, d_scale_partial,
-                                   n_loc, n_all, E, row_offset, scale, w_row, w_col);
+                                   n_loc, n_all, E, row_offset, scale_dev, grad_out_dev, w_row, w_col);
 }

@@ -61,48 +61,57 @@ def _all_gather_cat(x: torch.Tensor, world_size: int) -> torch.Tensor:
 
 def loss_weights(grad_out: float, n_loc: int, n_all: int, world_size: int, local_loss: bool, gather_with_grad: bool):
     """Weight of one row / one column cross-entropy term in the objective whose gradient a rank returns (host logic,
-    unit-tested on CPU against the reference's multi-rank gradients; see the module docstring)."""
+    unit-tested on CPU against the reference's multi-rank gradients; see the module docstring).  The upstream gradient is
+    applied on the device (ops.clip_loss_grad_logits(grad_out=...)); pass grad_out=1.0 here for the structural weight."""
     if world_size == 1 or local_loss or gather_with_grad:
         return grad_out / (2.0 * n_loc)
     return grad_out / (2.0 * n_all)
 
 
-class _Logits(torch.autograd.Function):
-    """z = logit_scale * A @ B^T (fp32 [n, N]) and its autograd on libovk GEMMs (loss.py:109-116)."""
-
-    @staticmethod
-    def forward(ctx, a, b, logit_scale):
-        a16 = a.detach().to(torch.bfloat16).contiguous()
-        b16 = b.detach().to(torch.bfloat16).contiguous()
-        s = logit_scale.detach().to(torch.float32).reshape(1)
-        z = ops.gemm_scaled(a16, b16, alpha_dev=s, out_dtype=torch.float32)
-        ctx.save_for_backward(a16, b16, s, z)
-        ctx.meta = (a.dtype, b.dtype, logit_scale.dtype, logit_scale.shape)
-        return z
-
-    @staticmethod
-    def backward(ctx, dz):
-        a16, b16, s, z = ctx.saved_tensors
-        dt_a, dt_b, dt_s, shape_s = ctx.meta
-        d_scale = ((dz.float() * z).sum() / s).reshape(shape_s).to(dt_s) if ctx.needs_input_grad[2] else None
-        g = dz.to(torch.bfloat16)
-        if g.shape[1] % 8:      # TMA strides are multiples of 16 bytes: pad the row pitch
-            pad = torch.zeros((g.shape[0], (g.shape[1] + 7) // 8 * 8), dtype=torch.bfloat16, device=g.device)
-            pad[:, :g.shape[1]] = g
-            g = pad[:, :dz.shape[1]]
-        elif not g.is_contiguous():
-            g = g.contiguous()
-        da = ops.gemm_scaled(g, b16, b_mn=True, alpha_dev=s).to(dt_a) if ctx.needs_input_grad[0] else None   # s dZ B
-        db = ops.gemm_scaled(g, a16, a_mn=True, b_mn=True, alpha_dev=s).to(dt_b) if ctx.needs_input_grad[1] else None   # s dZ^T A
-        return da, db, d_scale
+_side_streams = {}
 
 
-def logits_fn(a: torch.Tensor, b: torch.Tensor, logit_scale) -> torch.Tensor:
-    if not torch.is_tensor(logit_scale):
-        logit_scale = torch.tensor(float(logit_scale), device=a.device)
-    if a.shape[1] != b.shape[1] or a.shape[1] % 8:
-        raise OvkError("get_logits: feature widths must match and be multiples of 8")
-    return _Logits.apply(a, b, logit_scale)
+def _side_stream(device) -> "torch.cuda.Stream":
+    """one extra stream per device for the text all-gather that runs under the first forward window"""
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _forward_statistics(img, txt, scale_t, rank, world_size):
+    """(txt_all, row_lse, diag, col_max, col_sum) of this rank's row block.  With several ranks the all-gather of the text
+    features runs on a side stream while the kernel already works on the rank's OWN column block (its text features are
+    local); the remaining column windows follow once the gather has landed."""
+    n, E = img.shape
+    if world_size == 1:
+        row_lse, diag, col_max, col_sum = ops.clip_loss_fwd(img, txt, 0, scale_t)
+        return txt, row_lse, diag, col_max, col_sum
+    n_all = n * world_size
+    row_offset = rank * n
+    txt_all = torch.empty((n_all, E), dtype=txt.dtype, device=txt.device)
+    overlap = img.is_cuda and n % ops.CL_WINDOW == 0
+    if not overlap:
+        dist.all_gather_into_tensor(txt_all, txt)
+        row_lse, diag, col_max, col_sum = ops.clip_loss_fwd(img, txt_all, row_offset, scale_t)
+        return txt_all, row_lse, diag, col_max, col_sum
+    cur = torch.cuda.current_stream()
+    side = _side_stream(img.device)
+    side.wait_stream(cur)                      # txt (and the fresh txt_all allocation) are ready on the current stream
+    with torch.cuda.stream(side):
+        dist.all_gather_into_tensor(txt_all, txt)
+        gathered = torch.cuda.Event()
+        gathered.record(side)
+    diag = torch.empty(n, dtype=torch.float32, device=img.device)
+    ws = ops.clip_loss_workspace(n, n_all, img.device)
+    ops.clip_loss_fwd_window(img, txt, row_offset, n_all, row_offset, scale_t, diag, ws)          # own block: no wait
+    cur.wait_event(gathered)
+    if row_offset > 0:
+        ops.clip_loss_fwd_window(img, txt_all[:row_offset], 0, n_all, row_offset, scale_t, diag, ws)
+    if row_offset + n < n_all:
+        ops.clip_loss_fwd_window(img, txt_all[row_offset + n:], row_offset + n, n_all, row_offset, scale_t, diag, ws)
+    row_lse, col_max, col_sum = ops.clip_loss_finalize(ws, n, n_all)
+    return txt_all, row_lse, diag, col_max, col_sum
 
 
 class _FusedClipLoss(torch.autograd.Function):
@@ -111,12 +120,12 @@ class _FusedClipLoss(torch.autograd.Function):
         n = image_features.shape[0]      # CPU tensors are rejected by the kernel wrappers (ops._require): no fallback
         if text_features.shape != image_features.shape:
             raise OvkError("ClipLoss: image and text features must have the same shape")
-        scale = float(logit_scale)
+        # the temperature stays on the device: no float(logit_scale) host synchronisation anywhere in the step
+        scale_t = logit_scale.detach().to(torch.float32).reshape(1)
         img = image_features.detach().to(torch.bfloat16).contiguous()
         txt = text_features.detach().to(torch.bfloat16).contiguous()
-        txt_all = _all_gather_cat(txt, world_size) if world_size > 1 else txt
         row_offset = rank * n if world_size > 1 else 0
-        row_lse, diag, col_max, col_sum = ops.clip_loss_fwd(img, txt_all, row_offset, scale)
+        txt_all, row_lse, diag, col_max, col_sum = _forward_statistics(img, txt, scale_t, rank, world_size)
         if world_size > 1:
             stats = _all_gather_cat(torch.stack([col_max, col_sum]).unsqueeze(0), world_size)   # [W, 2, N]
             col_lse = ops.clip_loss_combine(stats[:, 0].contiguous(), stats[:, 1].contiguous())
@@ -127,41 +136,38 @@ class _FusedClipLoss(torch.autograd.Function):
         if world_size > 1 and not local_loss:      # every rank reports the global loss (loss.py:111-113)
             dist.all_reduce(loss)
             loss = loss / world_size
-        ctx.save_for_backward(img, txt_all, row_lse, col_lse)
-        ctx.meta = (scale, n, row_offset, local_loss, gather_with_grad, rank, world_size, image_features.dtype,
+        ctx.save_for_backward(img, txt_all, row_lse, col_lse, scale_t)
+        ctx.meta = (n, row_offset, local_loss, gather_with_grad, rank, world_size, image_features.dtype,
                     text_features.dtype, logit_scale.dtype, logit_scale.shape)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        img, txt_all, row_lse, col_lse = ctx.saved_tensors
-        scale, n, row_offset, local_loss, gather_with_grad, rank, world_size, dt_i, dt_t, dt_s, shape_s = ctx.meta
+        img, txt_all, row_lse, col_lse, scale_t = ctx.saved_tensors
+        n, row_offset, local_loss, gather_with_grad, rank, world_size, dt_i, dt_t, dt_s, shape_s = ctx.meta
         n_all = txt_all.shape[0]
-        w = loss_weights(float(grad_out), n, n_all, world_size, local_loss, gather_with_grad)
+        w = loss_weights(1.0, n, n_all, world_size, local_loss, gather_with_grad)   # x grad_out on the device
         d_scale = torch.zeros(1, dtype=torch.float32, device=img.device)
         # The text-gradient partial dT = s G^T I_r is produced FIRST so that its reduce-scatter over NVLink (async NCCL)
-        # runs under the image-gradient GEMM dI = s G T.
-        def reduce_scatter_async(d_txt_part):
-            d_txt = torch.empty((n, d_txt_part.shape[1]), dtype=torch.float32, device=img.device)
-            return d_txt, dist.reduce_scatter_tensor(d_txt, d_txt_part, async_op=True)
+        # runs under the image-gradient GEMM dI = s G T.  The partial travels in bf16 (half the NVLink bytes; its entries
+        # are sums of bf16 products already) and the rank's slice is widened afterwards.
+        def text_grad(G):
+            if world_size == 1:
+                return ops.gemm_scaled(G, img, a_mn=True, b_mn=True, alpha_dev=scale_t, out_dtype=torch.float32), None
+            part = ops.gemm_scaled(G, img, a_mn=True, b_mn=True, alpha_dev=scale_t, out_dtype=torch.bfloat16)
+            d_txt = torch.empty((n, part.shape[1]), dtype=torch.bfloat16, device=img.device)
+            return d_txt, dist.reduce_scatter_tensor(d_txt, part, async_op=True)
 
-        work = None
         if world_size > 1 and local_loss and not gather_with_grad:
             # loss.py:52-61: no gradient through the gathered copies -> dI from the row terms only, dT from the column
             # terms only (not the gradient of the global objective; kept for surface parity)
-            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, 0.0, w, d_scale)
-            d_txt_part = ops.gemm_tn(G, img, alpha=scale, out_dtype=torch.float32)
-            d_txt, work = reduce_scatter_async(d_txt_part)
-            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, w, 0.0, d_scale)
-            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)
+            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale_t, row_lse, col_lse, 0.0, w, d_scale, grad_out)
+            d_txt, work = text_grad(G)
+            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale_t, row_lse, col_lse, w, 0.0, d_scale, grad_out)
         else:
-            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale, row_lse, col_lse, w, w, d_scale)
-            d_txt_part = ops.gemm_tn(G, img, alpha=scale, out_dtype=torch.float32)           # dT = s G^T I
-            if world_size > 1:
-                d_txt, work = reduce_scatter_async(d_txt_part)
-            else:
-                d_txt = d_txt_part
-            d_img = ops.gemm_nn(G, txt_all, alpha=scale, out_dtype=torch.float32)            # dI = s G T
+            G = ops.clip_loss_grad_logits(img, txt_all, row_offset, scale_t, row_lse, col_lse, w, w, d_scale, grad_out)
+            d_txt, work = text_grad(G)                                                        # dT = s G^T I
+        d_img = ops.gemm_scaled(G, txt_all, b_mn=True, alpha_dev=scale_t, out_dtype=torch.float32)   # dI = s G T
         del G
         if world_size > 1:
             work.wait()

@@ -427,27 +427,64 @@ def l2_normalize(x: torch.Tensor, out_dtype=torch.float32, eps: float = 1e-12, r
 # fused CLIP contrastive loss (kernels: clip_loss_fwd_kernel, clip_loss_finalize_kernel, clip_loss_combine_kernel,
 # clip_loss_value_kernel, clip_loss_grad_kernel)
 # ----------------------------------------------------------------------------------------------------------------
-def clip_loss_fwd(a_loc: torch.Tensor, b_all: torch.Tensor, row_offset: int, scale: float):
-    """Row LSEs, positive-pair logits and this row block's column statistics of z = scale * a_loc @ b_all^T without
-    materialising z.  a_loc bf16 [n_loc,E], b_all bf16 [n_all,E].  Returns (row_lse, diag, col_max, col_sum), fp32."""
+def _scalar_dev(x, device, name: str) -> torch.Tensor:
+    """fp32[1] device tensor from a python number or a tensor (tensors stay on the device: no host read-back)."""
+    if torch.is_tensor(x):
+        t = x.detach()
+        if t.numel() != 1:
+            raise OvkError(f"{name}: expected a scalar")
+        if not t.is_cuda:
+            t = t.to(device)
+        return t.to(torch.float32).reshape(1)
+    return torch.full((1,), float(x), dtype=torch.float32, device=device)
+
+
+CL_WINDOW = 256   # column windows of clip_loss_fwd start on multiples of this (the kernel's tile width)
+
+
+def clip_loss_workspace(n_loc: int, n_all: int, device) -> torch.Tensor:
+    return torch.empty(_lib.load().ovk_clip_loss_workspace_floats(n_loc, n_all), dtype=torch.float32, device=device)
+
+
+def clip_loss_fwd_window(a_loc: torch.Tensor, b_rows: torch.Tensor, col_offset: int, n_all: int, row_offset: int, scale,
+                         diag: torch.Tensor, ws: torch.Tensor) -> None:
+    """Partial statistics of the column window [col_offset, col_offset + b_rows.shape[0]) of z = scale * a_loc @ b_all^T
+    (b_rows = the features of those columns) into the workspace; see include/ovk.h.  Kernel: clip_loss_fwd_kernel."""
     _require(a_loc, torch.bfloat16, "clip_loss.a_loc", 2)
-    _require(b_all, torch.bfloat16, "clip_loss.b_all", 2)
-    if not a_loc.is_contiguous() or not b_all.is_contiguous():
+    _require(b_rows, torch.bfloat16, "clip_loss.b_rows", 2)
+    if not a_loc.is_contiguous() or not b_rows.is_contiguous():
         raise OvkError("clip_loss: features must be contiguous")
     n_loc, E = a_loc.shape
-    n_all, E2 = b_all.shape
+    n_cols, E2 = b_rows.shape
     if E != E2:
         raise OvkError("clip_loss: embedding dims differ")
-    dev = a_loc.device
+    scale = _scalar_dev(scale, a_loc.device, "clip_loss.scale")
+    with _timed("clip_loss_fwd", 2.0 * n_loc * n_cols * E):
+        _lib.call("ovk_clip_loss_fwd", _p(a_loc), _p(b_rows), n_loc, n_cols, int(col_offset), int(n_all), E, int(row_offset),
+                  _p(scale), _p(diag), _p(ws), _stream())
+    _count()
+
+
+def clip_loss_finalize(ws: torch.Tensor, n_loc: int, n_all: int):
+    """Merge the per-tile partials of all column windows -> (row_lse, col_max, col_sum), fp32. Kernel: clip_loss_finalize_kernel."""
+    dev = ws.device
     row_lse = torch.empty(n_loc, dtype=torch.float32, device=dev)
-    diag = torch.empty(n_loc, dtype=torch.float32, device=dev)
     col_max = torch.empty(n_all, dtype=torch.float32, device=dev)
     col_sum = torch.empty(n_all, dtype=torch.float32, device=dev)
-    ws = torch.empty(_lib.load().ovk_clip_loss_workspace_floats(n_loc, n_all), dtype=torch.float32, device=dev)
-    with _timed("clip_loss_fwd", 2.0 * n_loc * n_all * E):
-        _lib.call("ovk_clip_loss_fwd", _p(a_loc), _p(b_all), n_loc, n_all, E, int(row_offset), float(scale), _p(row_lse),
-                  _p(diag), _p(col_max), _p(col_sum), _p(ws), _stream())
-    _count(2)
+    _lib.call("ovk_clip_loss_finalize", _p(ws), n_loc, n_all, _p(row_lse), _p(col_max), _p(col_sum), _stream())
+    _count()
+    return row_lse, col_max, col_sum
+
+
+def clip_loss_fwd(a_loc: torch.Tensor, b_all: torch.Tensor, row_offset: int, scale):
+    """Row LSEs, positive-pair logits and this row block's column statistics of z = scale * a_loc @ b_all^T without
+    materialising z.  a_loc bf16 [n_loc,E], b_all bf16 [n_all,E]; scale: python number or device scalar.
+    Returns (row_lse, diag, col_max, col_sum), fp32."""
+    n_loc, n_all = a_loc.shape[0], b_all.shape[0]
+    diag = torch.empty(n_loc, dtype=torch.float32, device=a_loc.device)
+    ws = clip_loss_workspace(n_loc, n_all, a_loc.device)
+    clip_loss_fwd_window(a_loc, b_all, 0, n_all, row_offset, scale, diag, ws)
+    row_lse, col_max, col_sum = clip_loss_finalize(ws, n_loc, n_all)
     return row_lse, diag, col_max, col_sum
 
 
@@ -472,16 +509,19 @@ def clip_loss_value(row_lse, col_lse, diag, row_offset: int) -> torch.Tensor:
     return out
 
 
-def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale: float, row_lse, col_lse, w_row: float, w_col: float,
-                          d_scale: torch.Tensor) -> torch.Tensor:
-    """G = dL/dz for this row block, bf16 [n_loc, n_all]; d_scale (fp32[1]) += sum(G * z) / scale."""
+def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale, row_lse, col_lse, w_row: float, w_col: float,
+                          d_scale: torch.Tensor, grad_out=None) -> torch.Tensor:
+    """G = dL/dz for this row block, bf16 [n_loc, n_all]; d_scale (fp32[1]) += sum(G * z) / scale.  `scale` and the optional
+    upstream gradient `grad_out` (multiplied into both weights) may be device scalars."""
     n_loc, E = a_loc.shape
     n_all = b_all.shape[0]
     ldg = (n_all + 7) // 8 * 8
     G = torch.empty((n_loc, ldg), dtype=torch.bfloat16, device=a_loc.device)
+    scale = _scalar_dev(scale, a_loc.device, "clip_loss_grad.scale")
+    go = None if grad_out is None else _scalar_dev(grad_out, a_loc.device, "clip_loss_grad.grad_out")
     with _timed("clip_loss_grad", 2.0 * n_loc * n_all * E):
-        _lib.call("ovk_clip_loss_grad_logits", _p(a_loc), _p(b_all), n_loc, n_all, E, int(row_offset), float(scale),
-                  _p(row_lse), _p(col_lse), float(w_row), float(w_col), _p(G), ldg, _p(d_scale), _stream())
+        _lib.call("ovk_clip_loss_grad_logits", _p(a_loc), _p(b_all), n_loc, n_all, E, int(row_offset), _p(scale),
+                  _p(row_lse), _p(col_lse), float(w_row), float(w_col), _p(go), _p(G), ldg, _p(d_scale), _stream())
     _count()
     return G[:, :n_all] if ldg != n_all else G
 

@@ -111,6 +111,19 @@ class FlatAdamW:
         """The flat gradient buffers, e.g. for `torch.distributed.all_reduce` (sum; pass grad_scale=1/world to step)."""
         return [g.flat_g for g in self.groups]
 
+    def all_reduce_grads(self, bucket_bytes: int = 256 << 20, group=None) -> None:
+        """Data-parallel gradient SUM over the ranks (main_clip.py:480-483 does a pmean inside the jitted step): NCCL
+        all-reduces over the flat gradient buffers in buckets of `bucket_bytes`, all enqueued asynchronously and waited for
+        together, so that NCCL pipelines them back to back (pass grad_scale = 1 / world to step())."""
+        import torch.distributed as dist
+        works = []
+        for g in self.groups:
+            per = max(1, bucket_bytes // g.flat_g.element_size())
+            for off in range(0, g.flat_g.numel(), per):
+                works.append(dist.all_reduce(g.flat_g[off:off + per], group=group, async_op=True))
+        for w in works:
+            w.wait()
+
     def step(self, lr_mult: float = 1.0, grad_scale: float = 1.0) -> None:
         self.step_count += 1
         gnorm = None

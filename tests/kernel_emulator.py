@@ -27,9 +27,11 @@ def clip_loss_value(row_lse, col_lse, diag, row_offset):
     return torch.stack([0.5 * (a + b) / n, a, b]).float()
 
 
-def clip_loss_grad_logits(a_loc, b_all, row_offset, scale, row_lse, col_lse, w_row, w_col, d_scale):
+def clip_loss_grad_logits(a_loc, b_all, row_offset, scale, row_lse, col_lse, w_row, w_col, d_scale, grad_out=None):
     z = scale * a_loc.double() @ b_all.double().t()
     n = a_loc.shape[0]
+    if grad_out is not None:
+        w_row, w_col = w_row * float(grad_out), w_col * float(grad_out)
     G = w_row * torch.exp(z - row_lse.double()[:, None]) + w_col * torch.exp(z - col_lse.double()[None, :])
     G[torch.arange(n), torch.arange(n) + row_offset] -= (w_row + w_col)
     d_scale += float((G * z).sum() / scale)
@@ -42,3 +44,10 @@ def gemm_nn(a, b, alpha=1.0, out_dtype=torch.float32, **kw):
 
 def gemm_tn(a, b, alpha=1.0, out_dtype=torch.float32, **kw):
     return (alpha * a.double().t() @ b.double()).to(out_dtype)
+
+
+def gemm_scaled(a, b, a_mn=False, b_mn=False, alpha=1.0, alpha_dev=None, out_dtype=torch.float32, out=None):
+    A = a.double().t() if a_mn else a.double()
+    B = b.double() if b_mn else b.double().t()
+    s = alpha * (float(alpha_dev) if alpha_dev is not None else 1.0)
+    return (s * A @ B).to(out_dtype)

@@ -1,0 +1,85 @@
+"""GPU, >= 2 devices: the multi-rank contrastive loss on the REAL kernels over NCCL (one process per GPU) against
+(a) the gradients of the unmodified reference run under gloo (tests/golden/loss_dist_W2_*) and (b) the single-GPU fused loss
+on the same global feature set (reference branches loss.py:48-61,103-113).  Skipped on a one-GPU box; the
+driver's scaling run repeats check (b) at N = 32 768 inside bench.py (clip_loss.parity_ok)."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, outdir, cases):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import openvision_b200 as ovb
+    from oracle import synth
+    out = {}
+    for (n, e, local_loss, gwg, seed) in cases:
+        img, txt = synth.make_features(n, e, seed=seed)
+        nl = n // world
+        img_l = img[rank * nl:(rank + 1) * nl].cuda().requires_grad_(True)
+        txt_l = txt[rank * nl:(rank + 1) * nl].cuda().requires_grad_(True)
+        ls = torch.tensor(float(np.log(1 / 0.07)), device="cuda", requires_grad=True)
+        crit = ovb.ClipLoss(local_loss=local_loss, gather_with_grad=gwg, rank=rank, world_size=world)
+        loss = crit(img_l, txt_l, ls.exp())
+        loss.backward()
+        torch.cuda.synchronize()
+        out[(n, e, local_loss, gwg)] = dict(loss=loss.detach().cpu(), d_img=img_l.grad.cpu(), d_txt=txt_l.grad.cpu(),
+                                            d_ls=ls.grad.cpu())
+    torch.save(out, os.path.join(outdir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_two_rank_loss_matches_reference_and_single_gpu(golden):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import openvision_b200 as ovb
+    from oracle import synth
+    world = 2
+    cases = [(64, 32, True, True, 96), (64, 32, False, False, 96), (64, 32, False, True, 96),
+             (2048, 256, True, True, 7), (1280, 768, True, True, 8)]      # 1280 / 2 = 640 rows per rank: odd number of row tiles
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, 29911, d, cases), nprocs=world, join=True)
+        res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
+    # (a) the reference under gloo, three modes
+    for (local_loss, gwg) in ((True, True), (False, False), (False, True)):
+        g = golden(f"loss_dist_W2_N64_E32_local{int(local_loss)}_gwg{int(gwg)}.npz")
+        for r in range(world):
+            x = res[r][(64, 32, local_loss, gwg)]
+            assert abs(float(x["loss"]) - float(g[f"loss_r{r}"])) < 2e-2 * abs(float(g[f"loss_r{r}"])) + 1e-3
+            for k, kk in (("d_img", "d_img_r"), ("d_txt", "d_txt_r")):
+                ref = g[f"{kk}{r}"]
+                err = np.abs(x[k].numpy() - ref).max()
+                assert err <= 3e-2 * np.abs(ref).max(), (local_loss, gwg, k, r, err)
+        ours = np.mean([float(res[r][(64, 32, local_loss, gwg)]["d_ls"]) for r in range(world)])
+        ref = np.mean([float(g[f"d_logit_scale_r{r}"]) for r in range(world)])
+        assert abs(ours - ref) <= 3e-2 * abs(ref) + 1e-4
+    # (b) the single-GPU fused loss on the whole feature set: mean of rank losses, per-rank gradients / W
+    for (n, e, seed) in ((2048, 256, 7), (1280, 768, 8)):
+        img, txt = synth.make_features(n, e, seed=seed)
+        i1 = img.cuda().requires_grad_(True)
+        t1 = txt.cuda().requires_grad_(True)
+        ls = torch.tensor(float(np.log(1 / 0.07)), device="cuda", requires_grad=True)
+        l1 = ovb.ClipLoss()(i1, t1, ls.exp())
+        l1.backward()
+        xs = [res[r][(n, e, True, True)] for r in range(world)]
+        mean_loss = np.mean([float(x["loss"]) for x in xs])
+        assert abs(mean_loss - float(l1)) <= 1e-3 * abs(float(l1))
+        for k, ref in (("d_img", i1.grad), ("d_txt", t1.grad)):
+            got = torch.cat([x[k] for x in xs]) / world
+            rel = (got - ref.cpu()).norm() / ref.cpu().norm()
+            assert rel.item() <= 2e-2, (n, k, rel.item())
+        gs = np.mean([float(x["d_ls"]) for x in xs])
+        assert abs(gs - float(ls.grad)) <= 2e-2 * abs(float(ls.grad)) + 1e-6

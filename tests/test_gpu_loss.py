@@ -36,6 +36,51 @@ def test_fwd_statistics_match_oracle(ops, n, e, scale):
     assert abs(float(out[0]) - ref) <= 1e-3 * abs(ref) + 1e-5
 
 
+@pytest.mark.parametrize("n_loc", [515, 640, 896, 384])
+def test_fwd_never_writes_past_its_workspace(ops, n_loc):
+    """n_loc >= 512 with an odd number of 128-row tiles: the second CTA of the last pair has no rows (and no workspace slot).
+    Canary words directly behind the exact-size workspace must survive (out-of-bounds column-statistics store)."""
+    from openvision_b200 import _lib
+    n_all, e = 1024, 64
+    img, txt = _feat(n_all, e, 3)
+    img, txt = img[:n_loc].contiguous().cuda(), txt.cuda()
+    nws = _lib.load().ovk_clip_loss_workspace_floats(n_loc, n_all)
+    guard = 4 * n_all
+    buf = torch.full((nws + guard,), 12345.0, dtype=torch.float32, device="cuda")
+    diag = torch.empty(n_loc, dtype=torch.float32, device="cuda")
+    ops.clip_loss_fwd_window(img, txt, 0, n_all, 0, 20.0, diag, buf[:nws])
+    row_lse, col_max, col_sum = ops.clip_loss_finalize(buf[:nws], n_loc, n_all)
+    torch.cuda.synchronize()
+    assert bool((buf[nws:] == 12345.0).all()), "clip_loss_fwd wrote behind its workspace"
+    z = 20.0 * img.double().cpu() @ txt.double().cpu().t()
+    np.testing.assert_allclose(row_lse.cpu().numpy(), torch.logsumexp(z, 1).numpy(), rtol=0, atol=4e-3)
+
+
+@pytest.mark.parametrize("n_loc,n_all,row_offset,cuts", [(256, 1024, 256, (256, 512)), (640, 1280, 640, (640,)),
+                                                        (128, 1000, 256, (256, 768)), (512, 2048, 1024, (1024, 1536))])
+def test_fwd_column_windows_equal_one_pass(ops, n_loc, n_all, row_offset, cuts):
+    """The all-gather overlap of the multi-rank loss: column windows processed by separate launches (the rank's own block
+    first, in any order) must give the statistics of the single launch."""
+    e, scale = 96, 40.0
+    img, txt = _feat(n_all, e, 11)
+    a = img[row_offset:row_offset + n_loc].contiguous().cuda()
+    b = txt.cuda()
+    want = ops.clip_loss_fwd(a, b, row_offset, scale)
+    ws = ops.clip_loss_workspace(n_loc, n_all, a.device)
+    ws.fill_(float("nan"))
+    diag = torch.full((n_loc,), float("nan"), dtype=torch.float32, device="cuda")
+    edges = [0, *cuts, n_all]
+    wins = [(edges[i], edges[i + 1]) for i in range(len(edges) - 1)]
+    for (c0, c1) in reversed(wins):
+        ops.clip_loss_fwd_window(a, b[c0:c1].contiguous(), c0, n_all, row_offset, torch.tensor(scale, device="cuda"), diag, ws)
+    row_lse, col_max, col_sum = ops.clip_loss_finalize(ws, n_loc, n_all)
+    np.testing.assert_allclose(row_lse.cpu().numpy(), want[0].cpu().numpy(), rtol=0, atol=1e-4)
+    np.testing.assert_allclose(diag.cpu().numpy(), want[1].cpu().numpy(), rtol=0, atol=1e-5)
+    cl = ops.clip_loss_combine(col_max[None].contiguous(), col_sum[None].contiguous())
+    cl_want = ops.clip_loss_combine(want[2][None].contiguous(), want[3][None].contiguous())
+    np.testing.assert_allclose(cl.cpu().numpy(), cl_want.cpu().numpy(), rtol=0, atol=1e-4)
+
+
 def test_fwd_is_exact_for_badly_scaled_rows_and_columns(ops):
     """Rows / columns whose logits sit hundreds of nats below their neighbours (the single-exponential fast path would
     flush them to zero) must take the exact path: un-normalised features with norms spread over 3 decades."""
