@@ -216,12 +216,12 @@ class _EmbedAssemble(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tok, cls, pos, B, N, owner):
         x = ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N, inplace=False)
-        ctx.meta = (cls, pos, B, N)
+        ctx.meta = (cls, pos, B, N, tok.shape[0] == B * (N + 1))
         return x.view(B * (N + 1), -1)
 
     @staticmethod
     def backward(ctx, dx):
-        cls, pos, B, N = ctx.meta
+        cls, pos, B, N, lead = ctx.meta
         dx = _c(dx)
         D = dx.shape[-1]
         dpos = dcls = None
@@ -229,12 +229,15 @@ class _EmbedAssemble(torch.autograd.Function):
             s = ops.colsum(dx.view(B, (N + 1) * D)).view(N + 1, D)      # sum over images
             dpos = _like_param(s, pos) if ctx.needs_input_grad[2] else None
             dcls = _like_param(s[0].clone(), cls) if ctx.needs_input_grad[1] else None
+        if not lead:      # tokens came without the cls slot ([B*N, D]): their gradient is rows 1.. of every image
+            dx = dx.view(B, N + 1, D)[:, 1:].reshape(B * N, D)
         return dx, dcls, dpos, None, None, None
 
 
 def embed_assemble_fn(tok, cls, pos, B, N, owner):
     if not _needs_grad(tok, cls, pos):
-        x = ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N, inplace=True)
+        lead = tok.shape[0] == B * (N + 1)      # GEMM output with the cls slot in place: assemble in place
+        x = ops.embed_assemble(tok, _v_f32(owner, "cls", cls), _v_f32(owner, "pos", pos), B, N, inplace=lead)
         return x.view(B * (N + 1), -1)
     return _EmbedAssemble.apply(tok, cls, pos, B, N, owner)
 

@@ -647,6 +647,7 @@ attention_tail_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __re
 using namespace ovk;
 
 int ovk_attention_fwd2_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
+int ovk_attention_fwd3_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
 
 extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
                                  void* stream) {
@@ -664,7 +665,12 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   {
     const int t2 = (L > ATT_BQ && L % ATT_BQ == 1) ? 1 : 0;
     const int nq2 = (L - t2 + ATT_BQ - 1) / ATT_BQ;
-    if (!ext && !force_v1 && L <= 4096 && nq2 % 2 == 0) return ovk_attention_fwd2_launch(qkv, out, lse, B, L, H, scale, s);
+    if (!ext && !force_v1 && L <= 4096 && nq2 % 2 == 0) {
+      // attention3.cu: half-block double buffering + hand-pipelined exponentials; OVK_ATT_V2=1 selects the round-1 pair kernel
+      const char* v2 = getenv("OVK_ATT_V2");
+      if (v2 != nullptr && v2[0] == '1') return ovk_attention_fwd2_launch(qkv, out, lse, B, L, H, scale, s);
+      return ovk_attention_fwd3_launch(qkv, out, lse, B, L, H, scale, s);
+    }
   }
   CUtensorMap tmQKV, tmO, tmTail, tmQKVb, tmOb;
   int rc;

@@ -114,6 +114,45 @@ def _forward_statistics(img, txt, scale_t, rank, world_size):
     return txt_all, row_lse, diag, col_max, col_sum
 
 
+class _Logits(torch.autograd.Function):
+    """z = logit_scale * A @ B^T (fp32 [n, N]) and its autograd on libovk GEMMs (loss.py:109-116)."""
+
+    @staticmethod
+    def forward(ctx, a, b, logit_scale):
+        a16 = a.detach().to(torch.bfloat16).contiguous()
+        b16 = b.detach().to(torch.bfloat16).contiguous()
+        s = logit_scale.detach().to(torch.float32).reshape(1)
+        z = ops.gemm_scaled(a16, b16, alpha_dev=s, out_dtype=torch.float32)
+        ctx.save_for_backward(a16, b16, s, z)
+        ctx.meta = (a.dtype, b.dtype, logit_scale.dtype, logit_scale.shape)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        a16, b16, s, z = ctx.saved_tensors
+        dt_a, dt_b, dt_s, shape_s = ctx.meta
+        d_scale = ((dz.float() * z).sum() / s).reshape(shape_s).to(dt_s) if ctx.needs_input_grad[2] else None
+        g = dz.to(torch.bfloat16)
+        if g.shape[1] % 8:      # TMA strides are multiples of 16 bytes: pad the row pitch
+            pad = torch.zeros((g.shape[0], (g.shape[1] + 7) // 8 * 8), dtype=torch.bfloat16, device=g.device)
+            pad[:, :g.shape[1]] = g
+            g = pad[:, :dz.shape[1]]
+        elif not g.is_contiguous():
+            g = g.contiguous()
+        da = ops.gemm_scaled(g, b16, b_mn=True, alpha_dev=s).to(dt_a) if ctx.needs_input_grad[0] else None   # s dZ B
+        db = ops.gemm_scaled(g, a16, a_mn=True, b_mn=True, alpha_dev=s).to(dt_b) if ctx.needs_input_grad[1] else None   # s dZ^T A
+        return da, db, d_scale
+
+
+def logits_fn(a: torch.Tensor, b: torch.Tensor, logit_scale) -> torch.Tensor:
+    """logit_scale * a @ b.T as fp32 [n, N] (model.py:286-293, loss.py:109-116) on the tcgen05 GEMM, differentiable."""
+    if not torch.is_tensor(logit_scale):
+        logit_scale = torch.tensor(float(logit_scale), device=a.device)
+    if a.shape[1] != b.shape[1] or a.shape[1] % 8:
+        raise OvkError("get_logits: feature widths must match and be multiples of 8")
+    return _Logits.apply(a, b, logit_scale)
+
+
 class _FusedClipLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, local_loss, gather_with_grad, rank, world_size):

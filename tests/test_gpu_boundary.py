@@ -82,8 +82,10 @@ def test_backward_hooks_fire_and_gradients_match_the_fused_path():
     cfg_name = "mini-ov"
     m = build(cfg_name)
     images = synth.make_images(cfg_name, 4, 0).cuda().requires_grad_(True)
+    # (a weighted sum: the squared norm of normalised embeddings is constant and would make every gradient rounding noise)
+    wgt = torch.randn(4, 64, generator=torch.Generator().manual_seed(3)).cuda()
     out = m.encode_image(images, normalize=True)
-    out.float().square().sum().backward()
+    (out.float() * wgt).sum().backward()
     g_ref = images.grad.detach().clone()
     w_ref = m.visual.transformer.resblocks[1].mlp.c_fc.weight.grad.detach().clone()
     images.grad = None
@@ -93,7 +95,7 @@ def test_backward_hooks_fire_and_gradients_match_the_fused_path():
     h1 = blk.mlp.c_fc.register_full_backward_hook(lambda mod, gin, gout: seen.append(("c_fc", tuple(gout[0].shape))))
     h2 = blk.register_full_backward_hook(lambda mod, gin, gout: seen.append(("block", tuple(gout[0].shape))))
     out = m.encode_image(images, normalize=True)
-    out.float().square().sum().backward()
+    (out.float() * wgt).sum().backward()
     h1.remove()
     h2.remove()
     names = [n for n, _ in seen]
@@ -103,6 +105,15 @@ def test_backward_hooks_fire_and_gradients_match_the_fused_path():
     assert rel.item() <= 3e-2, rel.item()
     relw = (blk.mlp.c_fc.weight.grad - w_ref).norm() / w_ref.norm()
     assert relw.item() <= 3e-2, relw.item()
+    # hooks on the tower's direct children take the line-by-line path (VisionTransformer._forward_modules), with autograd
+    images.grad = None
+    m.zero_grad(set_to_none=True)
+    h3 = m.visual.transformer.register_forward_hook(lambda *a: None)
+    out = m.encode_image(images, normalize=True)
+    (out.float() * wgt).sum().backward()
+    h3.remove()
+    rel = (images.grad - g_ref).norm() / g_ref.norm()
+    assert rel.item() <= 3e-2, rel.item()
 
 
 def test_text_tower_hooks():

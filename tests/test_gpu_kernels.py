@@ -163,6 +163,42 @@ def test_attention_fwd(ops, B, L, H):
     assert_close(lse, lse_ref, 1e-3, "attention lse")
 
 
+@pytest.mark.parametrize("L", [256, 257, 512, 200, 1025])
+@pytest.mark.parametrize("variant", ["v3", "v2"])
+def test_attention_running_maximum_grows_every_block(ops, L, variant, monkeypatch):
+    """Keys whose projection on the (shared) query direction ramps up along the sequence: every row's maximum grows by far
+    more than the lazy-rescale margin (2^8) from one 64-key step to the next, so the accumulated output has to be rescaled at
+    every step — in the half-block kernel that is the path that first waits for the previous P V to land."""
+    if variant == "v2":
+        monkeypatch.setenv("OVK_ATT_V2", "1")
+    B, H, hd = 2, 3, 64
+    qkv = (rnd(B * L, 3 * H * hd, seed=L) * 0.5).bfloat16().view(B, L, 3, H, hd).clone()
+    d = torch.nn.functional.normalize(rnd(hd, seed=1), dim=0)
+    ramp = torch.linspace(0.0, 80.0, L).view(1, L, 1, 1)
+    qkv[:, :, 0] = (qkv[:, :, 0].float() + 3.0 * d).bfloat16()            # every query has a +3 component along d
+    qkv[:, :, 1] = (qkv[:, :, 1].float() + ramp * d).bfloat16()           # key j has j/L * 80 along d: scores ramp to ~30 nats
+    qkv = qkv.view(B * L, 3 * H * hd)
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, f"attention ramp L{L} {variant}")
+    assert_close(lse, lse_ref, 1e-3, "attention lse")
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 257, 4), (40, 256, 8), (1, 200, 2), (1, 513, 1)])
+def test_attention_round1_pair_kernel_still_agrees(ops, B, L, H, monkeypatch):
+    """OVK_ATT_V2=1 selects the round-1 pair kernel (attention2.cu) for A/B measurements; both must pass the same bar."""
+    hd = 64
+    qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
+    out3, lse3 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    monkeypatch.setenv("OVK_ATT_V2", "1")
+    out2, lse2 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out2, ref, 2e-2, "attention v2")
+    assert_close(out3, ref, 2e-2, "attention v3")
+    assert_close(lse2, lse_ref, 1e-3, "lse v2")
+    assert_close(lse3, lse_ref, 1e-3, "lse v3")
+
+
 def test_attention_large_scores_and_batch_independence(ops):
     """online-softmax stability with large logits + size-independent property: images do not interact."""
     B, L, H, hd = 4, 257, 2, 64

@@ -56,7 +56,7 @@ def test_fwd_never_writes_past_its_workspace(ops, n_loc):
     np.testing.assert_allclose(row_lse.cpu().numpy(), torch.logsumexp(z, 1).numpy(), rtol=0, atol=4e-3)
 
 
-@pytest.mark.parametrize("n_loc,n_all,row_offset,cuts", [(256, 1024, 256, (256, 512)), (640, 1280, 640, (640,)),
+@pytest.mark.parametrize("n_loc,n_all,row_offset,cuts", [(256, 1024, 256, (256, 512)), (640, 1280, 512, (512, 1024)),
                                                         (128, 1000, 256, (256, 768)), (512, 2048, 1024, (1024, 1536))])
 def test_fwd_column_windows_equal_one_pass(ops, n_loc, n_all, row_offset, cuts):
     """The all-gather overlap of the multi-rank loss: column windows processed by separate launches (the rank's own block
