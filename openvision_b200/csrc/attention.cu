@@ -648,6 +648,7 @@ using namespace ovk;
 
 int ovk_attention_fwd2_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
 int ovk_attention_fwd3_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
+int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int L, int H, float scale, cudaStream_t s);
 
 extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
                                  void* stream) {
@@ -665,11 +666,16 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   {
     const int t2 = (L > ATT_BQ && L % ATT_BQ == 1) ? 1 : 0;
     const int nq2 = (L - t2 + ATT_BQ - 1) / ATT_BQ;
-    if (!ext && !force_v1 && L <= 4096 && nq2 % 2 == 0) {
-      // attention3.cu: half-block double buffering + hand-pipelined exponentials; OVK_ATT_V2=1 selects the round-1 pair kernel
+    const char* odd_env = getenv("OVK_ATT_PAIR_ODD");   // =1: the pair kernels also for an odd tile count (tests of that path)
+    const bool pair_odd = odd_env != nullptr && odd_env[0] == '1';
+    if (!ext && !force_v1 && L <= 4096 && (nq2 % 2 == 0 || pair_odd)) {
+      // attention4.cu (half-block double buffering, one MMA warp per tile slot, cross-item prefetch, deferred epilogue) by
+      // default; OVK_ATT_VER=3 / 2 (or the older OVK_ATT_V2=1) select the earlier generations for A/B measurements
+      const char* ver = getenv("OVK_ATT_VER");
       const char* v2 = getenv("OVK_ATT_V2");
-      if (v2 != nullptr && v2[0] == '1') return ovk_attention_fwd2_launch(qkv, out, lse, B, L, H, scale, s);
-      return ovk_attention_fwd3_launch(qkv, out, lse, B, L, H, scale, s);
+      if ((v2 != nullptr && v2[0] == '1') || (ver != nullptr && ver[0] == '2')) return ovk_attention_fwd2_launch(qkv, out, lse, B, L, H, scale, s);
+      if (ver != nullptr && ver[0] == '3') return ovk_attention_fwd3_launch(qkv, out, lse, B, L, H, scale, s);
+      return ovk_attention_fwd4_launch(qkv, out, lse, B, L, H, scale, s);
     }
   }
   CUtensorMap tmQKV, tmO, tmTail, tmQKVb, tmOb;

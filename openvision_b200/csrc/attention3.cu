@@ -19,6 +19,7 @@
 // accumulators [384,464) as in attention2.cu.
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "host_utils.h"
 #include "ptx.cuh"
@@ -85,7 +86,35 @@ __device__ __forceinline__ float pack_chunk(const float (&e)[16], uint32_t (&pw)
   return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
 }
 
-__global__ void __launch_bounds__(A3_THREADS, 1)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// latency-critical waits (softmax group <-> MMA warp hand-offs): SPIN polls with test_wait instead of suspending the thread
+// in hardware (the suspended form wakes up late; the polling form costs issue slots of the scheduler the warp lives on)
+template <bool SPIN>
+__device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, int code) {
+  if constexpr (!SPIN) {
+    mbar_wait(bar, parity, code);
+  } else {
+    uint32_t polls = 0;
+    while (!mbar_test_wait(bar, parity)) {
+      if (++polls > (1u << 27)) hang_trap(code);
+    }
+  }
+}
+
+// DUAL: one MMA-issuing warp per tile slot (warps 9 and 10) instead of one warp alternating between the two slots, so that
+// neither softmax group ever waits for the other one's hand-off; K / V ring slots are then released by two arrivals.
+template <bool DUAL, bool SPIN>
+__global__ void __launch_bounds__(A3_THREADS + 32, 1)
 attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse_out,
                       __nv_bfloat16* __restrict__ out, int L, int Lm, int H, int nq, int total_items, float scale_log2) {
@@ -119,9 +148,9 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
     for (int i = 0; i < A3_NS; ++i) {
       mbar_init(&bars[A3_B_KFULL + i], 1);
-      mbar_init(&bars[A3_B_KEMPTY + i], 1);
+      mbar_init(&bars[A3_B_KEMPTY + i], DUAL ? 2 : 1);
       mbar_init(&bars[A3_B_VFULL + i], 1);
-      mbar_init(&bars[A3_B_VEMPTY + i], 1);
+      mbar_init(&bars[A3_B_VEMPTY + i], DUAL ? 2 : 1);
     }
     fence_mbar_init();
   }
@@ -162,9 +191,10 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 9 || (DUAL && warp == 10)) {
     if (elect_one()) {
-      // ------------------------------------------------------------------ MMA issuer
+      // ------------------------------------------------------------------ MMA issuer(s)
+      const int me = warp - 9;   // DUAL: the tile slot this warp serves
       int n = 0, g0 = 0;
       uint32_t p_par = 0;    // bit 2w + (hb & 1): parity of the next p_ready phase of that barrier
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
@@ -173,7 +203,20 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const int ntile = (2 * pr + 1 < nq) ? 2 : 1;
         const int tw = !tail ? -1 : (2 * pr == nq - 1 ? 0 : (2 * pr + 1 == nq - 1 ? 1 : -1));   // tile carrying the remainder query
         const uint32_t rows = smem_u32(smem + A3_OFF_ROWS + buf * 384);
-        mbar_wait(&bars[A3_B_QFULL + buf], (n >> 1) & 1, 43);
+        const int w_lo = DUAL ? me : 0, w_hi = DUAL ? min(me + 1, ntile) : ntile;
+        if (DUAL && me >= ntile) {   // no tile for this warp in this item: keep the K / V ring's two-arrival protocol going
+          for (int j = 0; j < nkv; ++j) {
+            const int gg = g0 + j;
+            const int s = gg % A3_NS;
+            mbar_wait(&bars[A3_B_KFULL + s], (gg / A3_NS) & 1, 52);
+            mbar_arrive(&bars[A3_B_KEMPTY + s]);
+            mbar_wait(&bars[A3_B_VFULL + s], (gg / A3_NS) & 1, 53);
+            mbar_arrive(&bars[A3_B_VEMPTY + s]);
+          }
+          g0 += nkv;
+          continue;
+        }
+        mbar_wait_x<SPIN>(&bars[A3_B_QFULL + buf], (n >> 1) & 1, 43);
         // S_w(hb) = Q_w K(hb)^T into buffer hb & 1 of the tile's score columns (+ the remainder-token side products)
         auto issue_s = [&](int w, int hb) {
           const int j = hb >> 1, half = hb & 1;
@@ -184,7 +227,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           const uint32_t q_addr = smem_u32(smem + A3_OFF_Q + (2 * buf + w) * A3_TILE);
           const uint32_t k_tile = smem_u32(smem + A3_OFF_K + s * A3_TILE);
           const uint32_t k_addr = k_tile + half * A3_HALF;
-          mbar_wait(&bars[A3_B_KFULL + s], (gg / A3_NS) & 1, 44);
+          mbar_wait_x<SPIN>(&bars[A3_B_KFULL + s], (gg / A3_NS) & 1, 44);
           tc_fence_after();
           const uint32_t idesc_s = umma_idesc_bf16(A3_BQ, nblk, 0, 0);
 #pragma unroll
@@ -210,12 +253,12 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                              k != 0);
             }
           }
-          if (w == ntile - 1 && (half == 1 || hb == nhb - 1)) umma_commit(&bars[A3_B_KEMPTY + s]);   // last reader of this K tile
+          if ((DUAL || w == ntile - 1) && (half == 1 || hb == nhb - 1)) umma_commit(&bars[A3_B_KEMPTY + s]);   // last read of this K tile
           umma_commit(&bars[A3_B_SFULL + 2 * w + half]);
         };
-        for (int w = 0; w < ntile; ++w) issue_s(w, 0);
+        for (int w = w_lo; w < w_hi; ++w) issue_s(w, 0);
         if (nhb > 1)
-          for (int w = 0; w < ntile; ++w) issue_s(w, 1);
+          for (int w = w_lo; w < w_hi; ++w) issue_s(w, 1);
         for (int hb = 0; hb < nhb; ++hb) {
           const int j = hb >> 1, half = hb & 1;
           const int gg = g0 + j;
@@ -224,10 +267,10 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           const int ksteps = ((valid + 15) & ~15) / 16;
           const uint32_t v_tile = smem_u32(smem + A3_OFF_V + s * A3_TILE);
           const uint32_t v_addr = v_tile + half * A3_HALF;
-          for (int w = 0; w < ntile; ++w) {
-            mbar_wait(&bars[A3_B_PREADY + 2 * w + half], (p_par >> (2 * w + half)) & 1, 45);   // P_w(hb) is in TMEM (O_w rescaled if needed)
+          for (int w = w_lo; w < w_hi; ++w) {
+            mbar_wait_x<SPIN>(&bars[A3_B_PREADY + 2 * w + half], (p_par >> (2 * w + half)) & 1, 45);   // P_w(hb) is in TMEM (O_w rescaled if needed)
             p_par ^= 1u << (2 * w + half);
-            mbar_wait(&bars[A3_B_VFULL + s], (gg / A3_NS) & 1, 46);
+            mbar_wait_x<SPIN>(&bars[A3_B_VFULL + s], (gg / A3_NS) & 1, 46);
             tc_fence_after();
             constexpr uint32_t idesc_pv = umma_idesc_bf16(A3_BQ, A3_HD, 0, 1);
             for (int kk = 0; kk < ksteps; ++kk)
@@ -240,7 +283,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                 umma_bf16_ss(tmem_base + A3_T_OT, umma_desc_mnmajor_sw128(v_tile + kk * 16 * 128, A3_TILE),
                              umma_desc_row0(pt_addr + kk * 32), idesc_ot, (j | kk) != 0);
             }
-            if (w == ntile - 1 && (half == 1 || hb == nhb - 1)) umma_commit(&bars[A3_B_VEMPTY + s]);   // last reader of this V tile
+            if ((DUAL || w == ntile - 1) && (half == 1 || hb == nhb - 1)) umma_commit(&bars[A3_B_VEMPTY + s]);   // last read of this V tile
             umma_commit(&bars[A3_B_PVDONE + 2 * w + half]);
             if (hb + 2 < nhb) issue_s(w, hb + 2);   // refills the buffer P V_w(hb) has just been queued to read
           }
@@ -283,7 +326,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         const int half = hb & 1;
         const int valid = min(A3_HB, Lm - hb * A3_HB);
         const uint32_t t_s = t_sw + 64 * half;
-        mbar_wait(&bars[A3_B_SFULL + 2 * w + half], (s_par >> half) & 1, 47);
+        mbar_wait_x<SPIN>(&bars[A3_B_SFULL + 2 * w + half], (s_par >> half) & 1, 47);
         s_par ^= 1u << half;
         tc_fence_after();
         uint32_t u_sk = 0, u_st = 0;
@@ -318,7 +361,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         } else {
           const bool grow = m_blk > m_ref + 8.f;
           if (__any_sync(0xffffffffu, grow)) {
-            mbar_wait(&bars[A3_B_PVDONE + 2 * w + (half ^ 1)], ((pv_base >> (half ^ 1)) + ((hb - 1) >> 1)) & 1, 50);
+            mbar_wait_x<SPIN>(&bars[A3_B_PVDONE + 2 * w + (half ^ 1)], ((pv_base >> (half ^ 1)) + ((hb - 1) >> 1)) & 1, 50);
             tc_fence_after();
             const float alpha = grow ? fast_exp2(m_ref - m_blk) : 1.f;
             m_ref = grow ? m_blk : m_ref;
@@ -420,7 +463,7 @@ attention_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> smem -> TMA store
       {
         const int e = (nhb - 1) & 1;   // the last P V; its barrier's previous phase (P V(nhb-3)) completed before S(nhb-1) did
-        mbar_wait(&bars[A3_B_PVDONE + 2 * w + e], ((pv_base >> e) + ((nhb - 1) >> 1)) & 1, 48);
+        mbar_wait_x<SPIN>(&bars[A3_B_PVDONE + 2 * w + e], ((pv_base >> e) + ((nhb - 1) >> 1)) & 1, 48);
         pv_base ^= (((nhb + 1) >> 1) & 1) | (((nhb >> 1) & 1) << 1);
       }
       tc_fence_after();
@@ -528,9 +571,16 @@ int ovk_attention_fwd3_launch(const void* qkv, void* out, float* lse, int B, int
     const uint32_t box[4] = {A3_HD, 1, A3_BQ, 1};
     if ((rc = make_tmap_nd_bf16(&tmO, out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
+  // OVK_ATT3_MODE (A/B switch, read per call): bit 0 = one MMA warp per tile slot, bit 1 = polling hand-off waits
+  static const int default_mode = 0;
+  const char* me = getenv("OVK_ATT3_MODE");
+  const int mode = (me != nullptr && me[0] >= '0' && me[0] <= '3') ? me[0] - '0' : default_mode;
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fwd3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fwd3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fwd3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention3): %s", cudaGetErrorString(e));
     attr_once.done();
   }
@@ -540,7 +590,14 @@ int ovk_attention_fwd3_launch(const void* qkv, void* out, float* lse, int B, int
   const long long items = static_cast<long long>((nq + 1) / 2) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
   const int grid = static_cast<int>(items < (long long)num_sms() ? items : (long long)num_sms());
-  attention_fwd3_kernel<<<grid, A3_THREADS, A3_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L, l_main, H,
-                                                         nq, static_cast<int>(items), scale * 1.4426950408889634f);
+  auto* o = reinterpret_cast<__nv_bfloat16*>(out);
+  const float sl2 = scale * 1.4426950408889634f;
+  const int it = static_cast<int>(items);
+  switch (mode) {
+    case 1: attention_fwd3_kernel<true, false><<<grid, A3_THREADS + 32, A3_SMEM, s>>>(tmQKV, tmO, tmRow, lse, o, L, l_main, H, nq, it, sl2); break;
+    case 2: attention_fwd3_kernel<false, true><<<grid, A3_THREADS, A3_SMEM, s>>>(tmQKV, tmO, tmRow, lse, o, L, l_main, H, nq, it, sl2); break;
+    case 3: attention_fwd3_kernel<true, true><<<grid, A3_THREADS + 32, A3_SMEM, s>>>(tmQKV, tmO, tmRow, lse, o, L, l_main, H, nq, it, sl2); break;
+    default: attention_fwd3_kernel<false, false><<<grid, A3_THREADS, A3_SMEM, s>>>(tmQKV, tmO, tmRow, lse, o, L, l_main, H, nq, it, sl2); break;
+  }
   return check_launch("attention_fwd3_kernel");
 }

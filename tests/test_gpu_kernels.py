@@ -164,13 +164,16 @@ def test_attention_fwd(ops, B, L, H):
 
 
 @pytest.mark.parametrize("L", [256, 257, 512, 200, 1025])
-@pytest.mark.parametrize("variant", ["v3", "v2"])
+@pytest.mark.parametrize("variant", ["v4", "v3m0", "v3m1", "v3m2", "v3m3", "v2"])
 def test_attention_running_maximum_grows_every_block(ops, L, variant, monkeypatch):
     """Keys whose projection on the (shared) query direction ramps up along the sequence: every row's maximum grows by far
     more than the lazy-rescale margin (2^8) from one 64-key step to the next, so the accumulated output has to be rescaled at
     every step — in the half-block kernel that is the path that first waits for the previous P V to land."""
     if variant == "v2":
-        monkeypatch.setenv("OVK_ATT_V2", "1")
+        monkeypatch.setenv("OVK_ATT_VER", "2")
+    elif variant.startswith("v3"):   # attention3 A/B modes: bit 0 = one MMA warp per tile slot, bit 1 = polling hand-off waits
+        monkeypatch.setenv("OVK_ATT_VER", "3")
+        monkeypatch.setenv("OVK_ATT3_MODE", variant[-1])
     B, H, hd = 2, 3, 64
     qkv = (rnd(B * L, 3 * H * hd, seed=L) * 0.5).bfloat16().view(B, L, 3, H, hd).clone()
     d = torch.nn.functional.normalize(rnd(hd, seed=1), dim=0)
@@ -184,19 +187,26 @@ def test_attention_running_maximum_grows_every_block(ops, L, variant, monkeypatc
     assert_close(lse, lse_ref, 1e-3, "attention lse")
 
 
-@pytest.mark.parametrize("B,L,H", [(2, 257, 4), (40, 256, 8), (1, 200, 2), (1, 513, 1)])
-def test_attention_round1_pair_kernel_still_agrees(ops, B, L, H, monkeypatch):
-    """OVK_ATT_V2=1 selects the round-1 pair kernel (attention2.cu) for A/B measurements; both must pass the same bar."""
+@pytest.mark.parametrize("B,L,H", [(2, 257, 4), (40, 256, 8), (1, 200, 2), (1, 513, 1), (30, 385, 7), (300, 129, 1)])
+@pytest.mark.parametrize("mode", ["0", "1", "2", "3"])
+def test_attention_round1_pair_kernel_still_agrees(ops, B, L, H, mode, monkeypatch):
+    """OVK_ATT_V2=1 selects the round-1 pair kernel (attention2.cu) for A/B measurements, OVK_ATT3_MODE the variants of the
+    current one; all must pass the same bar.  (385 / 129 tokens: an odd number of query tiles only reaches these kernels when
+    the caller forces it; kept as the one-tile-per-item cases of the dual-issuer K / V ring protocol.)"""
     hd = 64
     qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16()
+    monkeypatch.setenv("OVK_ATT_PAIR_ODD", "1")
+    monkeypatch.setenv("OVK_ATT_VER", "3")
+    monkeypatch.setenv("OVK_ATT3_MODE", mode)
     out3, lse3 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
-    monkeypatch.setenv("OVK_ATT_V2", "1")
+    monkeypatch.setenv("OVK_ATT_VER", "2")
     out2, lse2 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    monkeypatch.setenv("OVK_ATT_VER", "4")
+    out4, lse4 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
     ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
-    assert_close(out2, ref, 2e-2, "attention v2")
-    assert_close(out3, ref, 2e-2, "attention v3")
-    assert_close(lse2, lse_ref, 1e-3, "lse v2")
-    assert_close(lse3, lse_ref, 1e-3, "lse v3")
+    for o, l, what in ((out2, lse2, "v2"), (out3, lse3, "v3"), (out4, lse4, "v4")):
+        assert_close(o, ref, 2e-2, f"attention {what}")
+        assert_close(l, lse_ref, 1e-3, f"lse {what}")
 
 
 def test_attention_large_scores_and_batch_independence(ops):

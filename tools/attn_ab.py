@@ -18,13 +18,16 @@ def t(fn, iters=20):
     return s.elapsed_time(e) / iters
 
 
-for (B, H, L, hd) in ((1024, 16, 257, 64), (1024, 16, 256, 64), (512, 12, 577, 64), (256, 16, 513, 64), (256, 16, 1025, 64)):
+for (B, H, L, hd) in ((1024, 16, 257, 64), (1024, 16, 256, 64), (256, 16, 513, 64), (256, 16, 1025, 64), (2048, 12, 80, 64), (64, 16, 257, 64)):
     qkv = torch.randn(B * L, 3 * H * hd, device="cuda").bfloat16()
     fl = 4.0 * B * H * L * L * hd
     res = {}
-    for name, env in (("v3", "0"), ("v2", "1"), ("v3", "0"), ("v2", "1")):
-        os.environ["OVK_ATT_V2"] = env
-        ms = t(lambda: ops.attention(qkv, B, L, H, hd))
-        res.setdefault(name, []).append(ms)
-    os.environ["OVK_ATT_V2"] = "0"
+    for rep in range(2):
+        for name, ver, mode in (("v4", "4", "0"), ("v3", "3", "0"), ("v3dual", "3", "1"), ("v2", "2", "0")):
+            os.environ["OVK_ATT_VER"] = ver
+            os.environ["OVK_ATT3_MODE"] = mode
+            ms = t(lambda: ops.attention(qkv, B, L, H, hd))
+            res.setdefault(name, []).append(ms)
+    os.environ["OVK_ATT_VER"] = "4"
+    os.environ["OVK_ATT3_MODE"] = "0"
     print(f"B{B} H{H} L{L}: " + "  ".join(f"{k} {min(v):.3f} ms {fl / min(v) / 1e9:.0f} TF/s" for k, v in res.items()), flush=True)
