@@ -150,6 +150,24 @@ int ovk_im2col_patches(const void* images, int img_is_f32, void* cols, long long
                        int lead_rows, void* stream);
 int ovk_embed_assemble(const void* patch, int patch_lead_rows, const float* cls, const float* pos, void* tokens, int B,
                        int N, int D, void* stream);
+/* conv1 + token assembly as ONE kernel (transformer.py:469,610-617; north-star kernel (1): "TMA-staged im2col GEMM fused with
+ * the position-embedding add"): raw pixel rows are fetched by TMA boxes straight out of the NCHW image, converted to the bf16
+ * K-major A tile in shared memory and multiplied on tcgen05; no im2col buffer exists in memory.
+ *   tokens[b, 0, :]     = pos_table[0, :]                         (class_embedding + positional_embedding[0], or 0)
+ *   tokens[b, 1 + p, :] = patch(b, p) . w_packed^T + pos_table[1 + p, :]
+ *   images    : [B,3,H,W] NCHW contiguous, f32 (img_is_f32) or bf16
+ *   w_packed  : bf16 [D, K'], K' = ovk_patch_embed_kdim(P); column ((c*PG + phg)*R + phl)*PW + pw holds
+ *               conv1.weight[d, c, phg*R + phl, pw] (zero where pw >= P or phg*R + phl >= P), PW = 16 (P <= 16) or 32,
+ *               R = 64 / PW, PG = ceil(P / R)
+ *   pos_table : bf16 [N+1, D] or NULL (plain conv tokens with a zero class-token row: the training path, where
+ *               ovk_embed_assemble's autograd owns the add)
+ *   tokens    : bf16 [B, N+1, D]
+ * ovk_patch_embed_supported: 1 when the geometry fits the kernel (P in {14,16,32}, image rows fit the staging ring);
+ * callers use ovk_im2col_patches + ovk_gemm_bf16_rowadd otherwise. */
+int ovk_patch_embed_kdim(int P);
+int ovk_patch_embed_supported(int img_is_f32, int H, int W, int P, int D);
+int ovk_patch_embed(const void* images, int img_is_f32, const void* w_packed, const void* pos_table, void* tokens, int B,
+                    int H, int W, int P, int D, void* stream);
 /* Backward of the patch embedding w.r.t. the input image (the ov-* scripts optimise the image through the tower):
  * dimages[b,c,y,x] = dcols[row(b,y/P,x/P), (c*P + y%P)*P + x%P]  (f32 or bf16 out), dcols = dtokens · conv1.weight. */
 int ovk_col2im_patches(const void* dcols, long long ldc, void* dimages, int img_is_f32, int B, int H, int W, int P,

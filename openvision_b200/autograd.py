@@ -173,43 +173,108 @@ def act_fn(x: torch.Tensor, kind: str) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 # patch embedding, cls / pos assembly
 # ----------------------------------------------------------------------------------------------------------------
+def _pos_table(owner, cls, pos):
+    """bf16 [L, D] table the patch-embedding epilogue adds: positional_embedding with class_embedding folded into row 0
+    (transformer.py:615-617); cached on the versions of the two parameters."""
+    cache = owner.__dict__.setdefault("_ovk_cache", {})
+    tag = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in (pos, cls))
+    hit = cache.get("pos_cls")
+    if hit is None or hit[0] != tag:
+        with torch.no_grad():
+            table = pos.detach().float().clone()
+            table[0] += cls.detach().float()
+            hit = (tag, table.to(torch.bfloat16).contiguous())
+        cache["pos_cls"] = hit
+    return hit[1]
+
+
+def _patch_embed_backward(ctx, dtok):
+    """shared by the two patch-embedding nodes: dtok bf16 [B*(N+1), D] (class-token rows included; the im2col matrix has a
+    zero row there, so they contribute nothing to dW).  The im2col matrix is rebuilt here (the forward never made one)."""
+    (images,) = ctx.saved_tensors
+    conv, conv_weight, P = ctx.conv, ctx.conv_weight, ctx.P
+    w, kpad = conv.packed_weight()
+    dw = dimg = None
+    if ctx.needs_input_grad[1]:
+        k = conv_weight[0].numel()
+        cols = ops.im2col_patches(images, P, kpad, lead_rows=1)
+        dwp = ops.gemm_tn(dtok, cols, out_dtype=_grad_dtype(conv_weight))          # [D, Kpad]
+        dw = _like_param(dwp[:, :k].contiguous(), conv_weight)
+        del cols
+    if ctx.needs_input_grad[0]:
+        dcols = ops.gemm_nn(dtok, w)                                                # [B*(N+1), Kpad]
+        B, _, H, W = images.shape
+        dimg = ops.col2im_patches(dcols, B, H, W, P, 1, torch.float32 if images.dtype == torch.float32 else torch.bfloat16)
+    return dimg, dw
+
+
 class _PatchEmbed(torch.autograd.Function):
+    """conv1 alone: tokens with a zero row in every image's class-token slot."""
+
     @staticmethod
     def forward(ctx, images, conv_weight, conv):
-        w, kpad = conv.packed_weight()
         P = conv.kernel_size[0]
-        cols = ops.im2col_patches(images, P, kpad, lead_rows=1)
-        tok = ops.gemm(cols, w)                      # [B*(N+1), D]; row 0 of every image is 0 (the cls slot)
+        if ops.patch_embed_supported(images, P, conv.out_channels):
+            tok = ops.patch_embed(images, conv.packed_weight_fused(), P, None)
+            tok = tok.view(-1, tok.shape[-1])
+        else:
+            w, kpad = conv.packed_weight()
+            tok = ops.gemm(ops.im2col_patches(images, P, kpad, lead_rows=1), w)
         if any(ctx.needs_input_grad):
-            ctx.save_for_backward(cols, w)
-            ctx.meta = (conv_weight, tuple(images.shape), images.dtype, P)
+            ctx.save_for_backward(images)
+            ctx.conv, ctx.conv_weight, ctx.P = conv, conv_weight, P
         return tok
 
     @staticmethod
     def backward(ctx, dtok):
-        cols, w = ctx.saved_tensors
-        conv_weight, ishape, idtype, P = ctx.meta
-        dtok = _c(dtok)
-        dw = dimg = None
-        if ctx.needs_input_grad[1]:
-            k = conv_weight[0].numel()
-            dwp = ops.gemm_tn(dtok, cols, out_dtype=_grad_dtype(conv_weight))          # [D, Kpad]
-            dw = _like_param(dwp[:, :k].contiguous(), conv_weight)
-        if ctx.needs_input_grad[0]:
-            dcols = ops.gemm_nn(dtok, w)                                                # [B*(N+1), Kpad]
-            B, _, H, W = ishape
-            dimg = ops.col2im_patches(dcols, B, H, W, P, 1, torch.float32 if idtype == torch.float32 else torch.bfloat16)
-            if dimg.dtype != idtype:
-                dimg = dimg.to(idtype)
+        dimg, dw = _patch_embed_backward(ctx, _c(dtok))
         return dimg, dw, None
 
 
 def patch_embed_fn(images, conv_weight, conv):
     """images [B,3,H,W] -> bf16 [B*(N+1), D] patch tokens with a zero row in every image's cls slot."""
     if not _needs_grad(images, conv_weight):
+        P = conv.kernel_size[0]
+        if ops.patch_embed_supported(images, P, conv.out_channels):
+            tok = ops.patch_embed(images, conv.packed_weight_fused(), P, None)
+            return tok.view(-1, tok.shape[-1])
         w, kpad = conv.packed_weight()
-        return ops.gemm(ops.im2col_patches(images, conv.kernel_size[0], kpad, lead_rows=1), w)
+        return ops.gemm(ops.im2col_patches(images, P, kpad, lead_rows=1), w)
     return _PatchEmbed.apply(images, conv_weight, conv)
+
+
+class _PatchEmbedTokens(torch.autograd.Function):
+    """transformer.py:610-617 as one kernel: conv1, reshape / permute, cat(class token), + positional embedding."""
+
+    @staticmethod
+    def forward(ctx, images, conv_weight, cls, pos, conv, owner):
+        P = conv.kernel_size[0]
+        tok = ops.patch_embed(images, conv.packed_weight_fused(), P, _pos_table(owner, cls, pos))
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(images)
+            ctx.conv, ctx.conv_weight, ctx.P = conv, conv_weight, P
+            ctx.cls, ctx.pos = cls, pos
+        return tok.view(-1, tok.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dx):
+        dx = _c(dx)
+        dimg, dw = _patch_embed_backward(ctx, dx)
+        dcls = dpos = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            L, D = ctx.pos.shape
+            s = ops.colsum(dx.view(-1, L * D)).view(L, D)       # sum over images
+            dpos = _like_param(s, ctx.pos) if ctx.needs_input_grad[3] else None
+            dcls = _like_param(s[0].clone(), ctx.cls) if ctx.needs_input_grad[2] else None
+        return dimg, dw, dcls, dpos, None, None
+
+
+def patch_embed_tokens_fn(images, conv, cls, pos, owner):
+    """-> bf16 [B*(N+1), D] finished token buffer (class token and positional embedding added in the GEMM epilogue)."""
+    if not _needs_grad(images, conv.weight, cls, pos):
+        tok = ops.patch_embed(images, conv.packed_weight_fused(), conv.kernel_size[0], _pos_table(owner, cls, pos))
+        return tok.view(-1, tok.shape[-1])
+    return _PatchEmbedTokens.apply(images, conv.weight, cls, pos, conv, owner)
 
 
 class _EmbedAssemble(torch.autograd.Function):

@@ -59,6 +59,11 @@ int make_tmap_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64
   return make_tmap_nd(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle);
 }
 
+int make_tmap_nd_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  return make_tmap_nd(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);
+}
+
 int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                      uint32_t box_inner, uint32_t box_outer) {
   uint64_t dims[2] = {inner, outer};

@@ -43,4 +43,8 @@ int make_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t inner, uint64_
 int make_tmap_nd_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// Generic N-d (<=5) fp32 map, same conventions.
+int make_tmap_nd_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 }  // namespace ovk

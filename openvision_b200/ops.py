@@ -358,6 +358,58 @@ def im2col_patches(images: torch.Tensor, patch: int, ldc: int, lead_rows: int = 
     return cols
 
 
+def patch_embed_supported(images: torch.Tensor, patch: int, D: int) -> bool:
+    """True when the one-kernel patch embedding (patch_embed_kernel) handles this geometry."""
+    if images.dim() != 4 or images.shape[1] != 3 or images.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return bool(_lib.load().ovk_patch_embed_supported(int(images.dtype == torch.float32), images.shape[2], images.shape[3],
+                                                      int(patch), int(D)))
+
+
+def pack_patch_weight(w: torch.Tensor, patch: int) -> torch.Tensor:
+    """conv1.weight [D,3,P,P] -> bf16 [D, K'] in the k-order of patch_embed_kernel (include/ovk.h, ovk_patch_embed):
+    (channel, row group, row in group, pixel padded to PW), zero in the padding columns.  Layout plumbing on torch."""
+    D = w.shape[0]
+    P = int(patch)
+    PW = 16 if P <= 16 else 32
+    R = 64 // PW
+    PG = (P + R - 1) // R
+    out = torch.zeros((D, 3, PG * R, PW), dtype=torch.bfloat16, device=w.device)
+    out[:, :, :P, :P] = w.detach().to(torch.bfloat16)
+    out = out.reshape(D, 3 * PG * R * PW)
+    assert out.shape[1] == _lib.load().ovk_patch_embed_kdim(P)
+    return out.contiguous()
+
+
+def patch_embed(images: torch.Tensor, w_packed: torch.Tensor, patch: int, table: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """images [B,3,H,W] (fp32 / bf16 NCHW) -> tokens bf16 [B, N+1, D]: conv1 as a TMA-staged im2col GEMM with the
+    class-token / positional-embedding add in its epilogue (table bf16 [N+1, D]; None: plain conv tokens, zero class row).
+    Kernel: patch_embed_kernel."""
+    if images.dtype not in (torch.float32, torch.bfloat16):
+        raise OvkError(f"patch_embed: images must be fp32 or bf16, got {images.dtype}")
+    _require(images, images.dtype, "patch_embed.images", 4)
+    _require(w_packed, torch.bfloat16, "patch_embed.w_packed", 2)
+    if not images.is_contiguous() or not w_packed.is_contiguous():
+        raise OvkError("patch_embed: images must be NCHW-contiguous and the packed weight contiguous")
+    B, C, H, W = images.shape
+    D = w_packed.shape[0]
+    if C != 3 or not patch_embed_supported(images, patch, D):
+        raise OvkError(f"patch_embed: unsupported geometry {tuple(images.shape)} patch {patch} width {D}")
+    if w_packed.shape[1] != _lib.load().ovk_patch_embed_kdim(int(patch)):
+        raise OvkError("patch_embed: w_packed must come from pack_patch_weight")
+    N = (H // patch) * (W // patch)
+    if table is not None:
+        _require(table, torch.bfloat16, "patch_embed.table", 2)
+        if tuple(table.shape) != (N + 1, D) or not table.is_contiguous():
+            raise OvkError("patch_embed: table must be contiguous [N+1, D]")
+    tokens = torch.empty((B, N + 1, D), dtype=torch.bfloat16, device=images.device)
+    with _timed("gemm", 2.0 * B * N * D * 3 * patch * patch):
+        _lib.call("ovk_patch_embed", _p(images), int(images.dtype == torch.float32), _p(w_packed), _p(table), _p(tokens),
+                  B, H, W, int(patch), D, _stream())
+    _count()
+    return tokens
+
+
 def embed_assemble(patch_tokens: torch.Tensor, cls: torch.Tensor, pos: torch.Tensor, B: int, N: int,
                    inplace: bool = False) -> torch.Tensor:
     """tokens[b,0]=cls+pos[0]; tokens[b,1+n]=patch[b,n]+pos[1+n]  -> bf16 [B, N+1, D]. patch_tokens is [B*N, D] or, with

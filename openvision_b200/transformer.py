@@ -196,6 +196,11 @@ class PatchEmbedConv(nn.Conv2d):
 
         return _packed(self, "w", self.weight, torch.bfloat16, pack), kpad
 
+    def packed_weight_fused(self):
+        """bf16 [D, K'] in the k-order of patch_embed_kernel (ops.pack_patch_weight)"""
+        P = self.kernel_size[0]
+        return _packed(self, "w_fused", self.weight, torch.bfloat16, lambda w: ops.pack_patch_weight(w, P))
+
     def tokens(self, images: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
         """images [B,3,H,W] -> patch tokens bf16 [B*(N+1), width]: per image one zero row (the cls slot) followed by the
         N patches row-major over the grid; returns (tokens, B, N)."""
@@ -482,37 +487,30 @@ class VisionTransformer(nn.Module):
         return pooled, tokens
 
     def _embed_fused(self, images: torch.Tensor):
-        """Inference path of transformer.py:610-617: patch GEMM whose epilogue adds the positional embedding (class token
-        folded into row 0 of the table; the im2col buffer has a zero row in every image's cls slot), so the GEMM output IS
-        the [B, L, D] token buffer.  Returns None when gradients are needed or the shapes do not fit (then the stand-alone
-        embed_assemble kernel runs)."""
-        from .autograd import _needs_grad
+        """transformer.py:610-617 in ONE kernel (patch_embed_kernel: TMA-staged im2col GEMM whose epilogue adds the positional
+        embedding, class token folded into row 0 of the table), forward and backward.  Returns None when the geometry does
+        not fit (then im2col + GEMM + embed_assemble run)."""
+        from .autograd import patch_embed_tokens_fn
         conv = self.conv1
-        if _needs_grad(images, conv.weight, self.class_embedding, self.positional_embedding) or not images.is_cuda:
+        if not images.is_cuda:
             return None
         if conv.kernel_size != conv.stride or conv.kernel_size[0] != conv.kernel_size[1] or conv.bias is not None:
             return None
         P = conv.kernel_size[0]
+        if images.dtype not in (torch.float32, torch.bfloat16):
+            images = images.to(torch.float32)
+        images = images.contiguous()
         B, _, H, W = images.shape
+        if H % P or W % P:
+            return None
         N = (H // P) * (W // P)
         D = conv.out_channels
         pos, cls = self.positional_embedding, self.class_embedding
-        if D % 64 or pos.dim() != 2 or pos.shape[0] != N + 1 or os.environ.get("OVK_EMBED_FUSE", "1") == "0":
+        if pos.dim() != 2 or pos.shape[0] != N + 1 or os.environ.get("OVK_EMBED_FUSE", "1") == "0":
             return None
-        cache = self.__dict__.setdefault("_ovk_cache", {})
-        tag = tuple((t.data_ptr(), t._version, t.dtype, t.device) for t in (pos, cls))
-        hit = cache.get("pos_cls")
-        if hit is None or hit[0] != tag:
-            with torch.no_grad():
-                table = pos.detach().float().clone()
-                table[0] += cls.detach().float()
-                hit = (tag, table.to(torch.bfloat16).contiguous())
-            cache["pos_cls"] = hit
-        if images.dtype not in (torch.float32, torch.bfloat16):
-            images = images.to(torch.float32)
-        w, kpad = conv.packed_weight()
-        cols = ops.im2col_patches(images.contiguous(), P, kpad, lead_rows=1)
-        return ops.gemm_rowadd(cols, w, hit[1]), B, N
+        if not ops.patch_embed_supported(images, P, D):
+            return None
+        return patch_embed_tokens_fn(images, conv, cls, pos, self), B, N
 
     def _forward_modules(self, x: torch.Tensor):
         """transformer.py:609-651 line by line, every sub-module invoked through __call__ (forward / backward hooks on conv1,

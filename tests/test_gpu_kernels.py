@@ -427,3 +427,56 @@ def test_patch_embed_gemm_with_fused_positional_add(ops, B, H, P, D):
     ref = O.patch_embed(img.bfloat16().float(), wconv.bfloat16().float())
     ref = torch.cat([cls.expand(B, 1, D), ref], 1) + pos
     assert_close(x.view(B, N + 1, D), ref, 1e-2, "patch embed + positional add")
+
+
+@pytest.mark.parametrize("B,H,P,D,dtype,with_table", [
+    (2, 224, 14, 1024, torch.float32, True),      # L/14@224: two 128-patch tiles per image, K' = 768 with padded columns
+    (5, 160, 16, 192, torch.float32, True),       # Ti/16@160: one ragged tile per image (100 patches), D < one column tile
+    (3, 384, 16, 768, torch.float32, True),       # B/16@384: 576 patches = 4.5 tiles, image rows fetched as two TMA boxes
+    (2, 224, 14, 1280, torch.bfloat16, True),     # H/14 width, bf16 pixels
+    (3, 224, 32, 768, torch.float32, False),      # B/32: 32-pixel rows (two image rows per k-block), plain conv tokens
+    (80, 224, 14, 512, torch.bfloat16, False),    # more tiles than SMs: persistent CTAs walk several tiles
+    (2, 336, 14, 1024, torch.float32, True),      # L/14@336: 24 x 24 grid, two boxes of 168 pixels
+])
+def test_patch_embed_one_kernel(ops, B, H, P, D, dtype, with_table):
+    """transformer.py:610-617 as ONE kernel (patch_embed_kernel): raw pixel rows by TMA -> bf16 A tile in shared memory ->
+    tcgen05 GEMM -> + positional-embedding table -> [B, L, D] tokens; against the fp32 conv of the oracle on bf16-rounded
+    operands.  No im2col buffer exists."""
+    gh = H // P
+    N = gh * gh
+    img = rnd(B, 3, H, H, seed=1)
+    wconv = rnd(D, 3, P, P, seed=2, scale=0.05)
+    cls, pos = rnd(D, seed=3), rnd(N + 1, D, seed=4)
+    assert ops.patch_embed_supported(img.to(dtype).cuda(), P, D)
+    table = pos.clone()
+    table[0] += cls
+    wk = ops.pack_patch_weight(wconv.cuda(), P)
+    x = ops.patch_embed(img.to(dtype).cuda(), wk, P, table.bfloat16().cuda() if with_table else None)
+    assert tuple(x.shape) == (B, N + 1, D)
+    ref = O.patch_embed(img.bfloat16().float(), wconv.bfloat16().float())
+    if with_table:
+        ref = torch.cat([cls.expand(B, 1, D), ref], 1) + pos.bfloat16().float()
+        ref[:, 0] = table.bfloat16().float()[0]
+    else:
+        ref = torch.cat([torch.zeros(B, 1, D), ref], 1)
+    assert_close(x, ref, 1e-2, "one-kernel patch embedding")
+    if not with_table:
+        assert (x[:, 0] == 0).all().item(), "class-token slot of the plain conv tokens must be zero"
+
+
+def test_patch_embed_agrees_with_the_im2col_path(ops):
+    """same operands through im2col + GEMM (+ row add): the two paths round the same bf16 products, so they agree to
+    accumulation order."""
+    B, H, P, D = 4, 224, 14, 1024
+    gh = H // P
+    N = gh * gh
+    img = rnd(B, 3, H, H, seed=5).cuda()
+    wconv = rnd(D, 3, P, P, seed=6, scale=0.05).cuda()
+    table = rnd(N + 1, D, seed=7).bfloat16().cuda()
+    K = 3 * P * P
+    kpad = (K + 7) // 8 * 8
+    wp = torch.zeros(D, kpad, dtype=torch.bfloat16, device="cuda")
+    wp[:, :K] = wconv.reshape(D, K).bfloat16()
+    a = ops.gemm_rowadd(ops.im2col_patches(img, P, kpad, lead_rows=1), wp, table).view(B, N + 1, D)
+    b = ops.patch_embed(img, ops.pack_patch_weight(wconv, P), P, table)
+    assert_close(b, a.float().cpu(), 4e-3, "patch_embed vs im2col + GEMM")
