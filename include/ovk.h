@@ -168,6 +168,16 @@ int ovk_patch_embed_kdim(int P);
 int ovk_patch_embed_supported(int img_is_f32, int H, int W, int P, int D);
 int ovk_patch_embed(const void* images, int img_is_f32, const void* w_packed, const void* pos_table, void* tokens, int B,
                     int H, int W, int P, int D, void* stream);
+/* The tail of the image tower as ONE kernel (transformer.py:599-607 _global_pool, :638-640 ln_post after pooling,
+ * :645-646 pooled @ proj; model.py:267 F.normalize; north-star kernel (5) "pooling head and L2-normalise"):
+ *   pooled = mean(x[b, 1:, :]) (mode 0, 'avg'), x[b, 0, :] (mode 1, 'tok') or x[b, L-1, :] (mode 2, the text tower's 'last',
+ *            model.py:278-284 via text_global_pool)
+ *   h      = LayerNorm(pooled; gamma, beta, ln_eps)                (gamma == NULL: skipped)
+ *   y      = h @ proj                 proj bf16 [D, E] row-major   (proj == NULL: y = h, E ignored)
+ *   out[b] = normalize ? y / max(||y||, norm_eps) : y              (f32 when out_is_f32, else bf16)
+ * x bf16 [B, L, D] contiguous, D % 8 == 0, E % 8 == 0.  fp32 between the token load and the output store. */
+int ovk_pool_head(const void* x, int B, int L, int D, int mode, const float* gamma, const float* beta, float ln_eps,
+                  const void* proj, int E, int normalize, float norm_eps, void* out, int out_is_f32, void* stream);
 /* Backward of the patch embedding w.r.t. the input image (the ov-* scripts optimise the image through the tower):
  * dimages[b,c,y,x] = dcols[row(b,y/P,x/P), (c*P + y%P)*P + x%P]  (f32 or bf16 out), dcols = dtokens · conv1.weight. */
 int ovk_col2im_patches(const void* dcols, long long ldc, void* dimages, int img_is_f32, int B, int H, int W, int P,

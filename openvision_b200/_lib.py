@@ -65,6 +65,8 @@ _PROTOTYPES = {
     "ovk_patch_embed_kdim": (c_int, [c_int]),
     "ovk_patch_embed_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "ovk_patch_embed": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ovk_pool_head": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_float,
+                              c_void_p, c_int, c_void_p]),
     "ovk_embed_assemble": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "ovk_col2im_patches": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ovk_colsum_bf16": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),

@@ -6,6 +6,7 @@ arguments, attributes, methods and state_dict keys.  timm / ResNet / HF towers a
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from functools import partial
 from typing import Optional, Tuple, Union
@@ -16,6 +17,7 @@ from torch import nn
 
 from . import ops
 from ._lib import OvkError
+from .transformer import to_2tuple  # noqa: E402
 from .transformer import (GELU, LayerNorm, LayerNormFp32, Linear, MultiheadSelfAttention, QuickGELU, Transformer, VisionTransformer,
                           _as_bf16_2d, _global_hooks, _out_dtype, _own_hooks)
 
@@ -297,12 +299,16 @@ class CLIP(nn.Module):
         self.transformer.recompute_mlp_hidden = enable == 'mlp'
 
     def encode_image(self, image, normalize: bool = False):
+        """model.py:265-267.  With nothing hooked on the tower, F.normalize rides in the pooling-head kernel."""
+        if normalize and isinstance(self.visual, VisionTransformer) and not self.visual.output_tokens \
+                and not _own_hooks(self.visual) and not _global_hooks():
+            return self.visual(image, _normalize=True)
         features = self.visual(image)
         return _normalize(features) if normalize else features
 
     def encode_text(self, text, normalize: bool = False):
         """model.py:269-284: embedding gather + positional add -> transformer -> ln_final -> pool -> projection."""
-        from .autograd import layer_norm_fn, linear_fn
+        from .autograd import _needs_grad, layer_norm_fn, linear_fn
         if self.attn_mask is not None:
             raise OvkError("causal text towers are not on the B200 hot path of this build "
                            "(OpenVision text configs set no_causal_mask=True)")
@@ -316,6 +322,17 @@ class CLIP(nn.Module):
         else:
             x2 = self.transformer.forward_tokens(_as_bf16_2d(x), B, L, owned=True)
             D = x2.shape[-1]
+            proj = self.text_projection
+            if (self.text_pool_type in ('first', 'last') and D % 8 == 0 and not isinstance(proj, nn.Module)
+                    and (proj is None or proj.shape[1] % 8 == 0)
+                    and not _needs_grad(x2, self.ln_final.weight, self.ln_final.bias, proj)):
+                # inference: pool -> ln_final -> @ text_projection (-> F.normalize) in one launch (pool_head_kernel)
+                from .autograd import _v_f32, _w_bf16
+                pj = _w_bf16(self, "text_proj_bf16", proj) if proj is not None else None
+                return ops.pool_head(x2.view(B, L, D), self.text_pool_type, _v_f32(self.ln_final, "ln_w", self.ln_final.weight),
+                                     _v_f32(self.ln_final, "ln_b", self.ln_final.bias), self.ln_final.eps, pj,
+                                     normalize=normalize,
+                                     out_dtype=torch.float32 if out_dtype == torch.float32 else torch.bfloat16).to(out_dtype)
             # LayerNorm is per token, so ln_final(x)[pool] == ln_final(x[pool]): pool first, normalise B rows instead of B*L
             x3 = x2.view(B, L, D)
         if self.text_pool_type == 'last':
@@ -392,3 +409,92 @@ def convert_weights_to_lp(model: nn.Module, dtype=torch.float16):
 
 
 convert_weights_to_fp16 = convert_weights_to_lp
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# checkpoint interchange: positional-embedding resizing at load time (model.py:523-592 of the reference; called by
+# factory.py:178-179 before load_state_dict).  Host-side, one-off work on a [L, D] table: the resampling is written here as
+# two small interpolation matrices (rows = output positions, columns = input positions) applied along each grid axis,
+# with the filter taps F.interpolate uses (align_corners=False): cubic convolution a = -0.75 on 4 clamped taps without
+# antialiasing, the area-scaled a = -0.5 cubic / triangle filter with it.
+# ----------------------------------------------------------------------------------------------------------------
+def _cubic(x: torch.Tensor, a: float) -> torch.Tensor:
+    x = x.abs()
+    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0
+    far = (((x - 5.0) * x + 8.0) * x - 4.0) * a
+    return torch.where(x < 1.0, near, torch.where(x < 2.0, far, torch.zeros_like(x)))
+
+
+def _resample_matrix(n_in: int, n_out: int, mode: str, antialias: bool) -> torch.Tensor:
+    """fp64 [n_out, n_in] matrix R with  out = R @ in  reproducing F.interpolate(mode, antialias, align_corners=False)
+    along one axis."""
+    if mode in ("linear", "bilinear"):
+        taps, cubic = 2, False
+    elif mode == "bicubic":
+        taps, cubic = 4, True
+    else:
+        raise ValueError(f"unsupported interpolation {mode!r}")
+    scale = n_in / n_out
+    R = torch.zeros(n_out, n_in, dtype=torch.float64)
+    idx = torch.arange(n_in, dtype=torch.float64)
+    for i in range(n_out):
+        if antialias:
+            # filter footprint widened by the scale when shrinking (area-style), taps normalised to unit sum
+            support = (taps / 2.0) * scale if scale >= 1.0 else taps / 2.0
+            inv = 1.0 / scale if scale >= 1.0 else 1.0
+            center = scale * (i + 0.5)
+            lo = max(0, int(center - support + 0.5))
+            hi = min(n_in, int(center + support + 0.5))
+            x = (idx[lo:hi] - center + 0.5) * inv
+            w = _cubic(x, -0.5) if cubic else (1.0 - x.abs()).clamp_min(0.0)
+            R[i, lo:hi] = w / w.sum()
+        else:
+            src = scale * (i + 0.5) - 0.5
+            if not cubic:
+                src = max(src, 0.0)
+            f = math.floor(src)
+            t = src - f
+            if cubic:
+                w = _cubic(torch.tensor([t + 1.0, t, 1.0 - t, 2.0 - t], dtype=torch.float64), -0.75)
+                pos = [f - 1, f, f + 1, f + 2]
+            else:
+                w = torch.tensor([1.0 - t, t], dtype=torch.float64)
+                pos = [f, f + 1]
+            for wj, pj in zip(w.tolist(), pos):
+                R[i, min(max(pj, 0), n_in - 1)] += wj      # border taps are clamped (replicated edge)
+    return R
+
+
+def resize_pos_embed(state_dict, model, interpolation: str = 'bicubic', antialias: bool = True):
+    """model.py:523-554: resample the image grid of `visual.positional_embedding` in a checkpoint's state_dict to the
+    model's grid (class-token row kept), in place in the dict."""
+    old = state_dict.get('visual.positional_embedding', None)
+    if old is None or not hasattr(model.visual, 'grid_size'):
+        return
+    gh, gw = to_2tuple(model.visual.grid_size)
+    extra = 1
+    if gh * gw + extra == old.shape[0]:
+        return
+    tok, img = old[:extra], old[extra:]
+    og = int(math.sqrt(img.shape[0]))
+    grid = img.reshape(og, og, -1).to(torch.float64)
+    ry = _resample_matrix(og, gh, interpolation, antialias).to(grid.device)
+    rx = _resample_matrix(og, gw, interpolation, antialias).to(grid.device)
+    new = torch.einsum('yi,ijd->yjd', ry, grid)
+    new = torch.einsum('xj,yjd->yxd', rx, new).reshape(gh * gw, -1).to(old.dtype)
+    state_dict['visual.positional_embedding'] = torch.cat([tok, new], dim=0)
+
+
+def resize_text_pos_embed(state_dict, model, interpolation: str = 'linear', antialias: bool = False):
+    """model.py:557-592: resample the text `positional_embedding` of a checkpoint to the model's context length."""
+    old = state_dict.get('positional_embedding', None)
+    if old is None:
+        return
+    target = getattr(model, 'positional_embedding', None)
+    if target is None:
+        target = getattr(model.text, 'positional_embedding', None)
+    assert old.shape[1] == target.shape[1], 'text pos_embed width changed!'
+    if old.shape[0] == target.shape[0]:
+        return
+    r = _resample_matrix(old.shape[0], target.shape[0], interpolation, antialias).to(old.device)
+    state_dict['positional_embedding'] = (r @ old.to(torch.float64)).to(old.dtype)

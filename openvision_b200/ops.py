@@ -462,6 +462,38 @@ def pool_tokens(x: torch.Tensor, mode: str) -> torch.Tensor:
     return pooled
 
 
+def pool_head(x: torch.Tensor, mode: str, gamma: Optional[torch.Tensor], beta: Optional[torch.Tensor], eps: float,
+              proj: Optional[torch.Tensor], normalize: bool = False, out_dtype=torch.bfloat16,
+              norm_eps: float = 1e-12) -> torch.Tensor:
+    """x bf16 [B,L,D] -> [B,E]: token pooling ('avg' over tokens 1.. / 'tok' = 'first' / 'last'), LayerNorm (gamma / beta fp32, or None),
+    @ proj (bf16 [D,E], or None), optional F.normalize, in one launch.  Kernel: pool_head_kernel."""
+    _require(x, torch.bfloat16, "pool_head.x", 3)
+    if not x.is_contiguous():
+        raise OvkError("pool_head: x must be contiguous")
+    B, L, D = x.shape
+    if (gamma is None) != (beta is None):
+        raise OvkError("pool_head: gamma and beta come together")
+    if gamma is not None:
+        _require(gamma, torch.float32, "pool_head.gamma", 1)
+        _require(beta, torch.float32, "pool_head.beta", 1)
+        if gamma.numel() != D or beta.numel() != D:
+            raise OvkError("pool_head: gamma / beta must have D entries")
+    E = D
+    if proj is not None:
+        _require(proj, torch.bfloat16, "pool_head.proj", 2)
+        if proj.shape[0] != D or not proj.is_contiguous():
+            raise OvkError("pool_head: proj must be contiguous [D, E]")
+        E = proj.shape[1]
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise OvkError("pool_head: output dtype must be fp32 or bf16")
+    out = torch.empty((B, E), dtype=out_dtype, device=x.device)
+    with _timed("pool_head", 2.0 * B * L * D):
+        _lib.call("ovk_pool_head", _p(x), B, L, D, {"avg": 0, "tok": 1, "first": 1, "last": 2}[mode], _p(gamma), _p(beta), float(eps), _p(proj), E,
+                  int(bool(normalize)), float(norm_eps), _p(out), int(out_dtype == torch.float32), _stream())
+    _count()
+    return out
+
+
 def l2_normalize(x: torch.Tensor, out_dtype=torch.float32, eps: float = 1e-12, return_norms: bool = False):
     """F.normalize(x, dim=-1) for x bf16 [rows,E]; output fp32 or bf16. Kernel: l2_normalize_kernel."""
     _require(x, torch.bfloat16, "l2_normalize.x", 2)

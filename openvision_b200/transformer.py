@@ -543,11 +543,16 @@ class VisionTransformer(nn.Module):
             return pooled, x2.reshape(B, L, D)[:, 1:].to(out_dtype)
         return pooled
 
-    def forward(self, x: torch.Tensor):
-        from .autograd import embed_assemble_fn, layer_norm_fn, linear_fn, pool_fn
+    def forward(self, x: torch.Tensor, _normalize: bool = False):
+        """transformer.py:609-651.  `_normalize` (private, used by CLIP.encode_image when nothing is hooked) folds
+        model.py:267's F.normalize into the pooling-head kernel."""
+        from .autograd import _needs_grad, _v_f32, _w_bf16, embed_assemble_fn, layer_norm_fn, linear_fn, normalize_fn, pool_fn
         if _global_hooks() or any(_own_hooks(m) for m in (self.conv1, self.patch_dropout, self.ln_pre, self.transformer,
                                                           self.ln_post)):
-            return self._forward_modules(x)
+            y = self._forward_modules(x)
+            if _normalize:
+                y = (normalize_fn(y[0]), y[1]) if isinstance(y, tuple) else normalize_fn(y)
+            return y
         images = x
         out_dtype = _out_dtype(images)
         x2 = self._embed_fused(images)                                          # :610-617 in one GEMM (inference)
@@ -569,6 +574,17 @@ class VisionTransformer(nn.Module):
 
         if self.pool_type == 'none':
             raise OvkError("pool_type='none' is outside the hot path of this build")
+        # inference: pool -> ln_post -> @ proj (-> F.normalize) in one launch (pool_head_kernel).  LayerNorm is per token, so
+        # with 'tok' pooling ln_post(x)[:, 0] == ln_post(x[:, 0]) and the kernel covers final_ln_after_pool=False as well.
+        if (not self.output_tokens and (self.final_ln_after_pool or self.pool_type == 'tok') and x2.shape[1] % 8 == 0
+                and (self.proj is None or self.proj.shape[1] % 8 == 0)
+                and not _needs_grad(x2, self.ln_post.weight, self.ln_post.bias, self.proj)
+                and os.environ.get("OVK_POOL_HEAD_FUSE", "1") != "0"):
+            proj = _w_bf16(self, "proj_bf16", self.proj) if self.proj is not None else None
+            return ops.pool_head(x2.view(B, L, D), self.pool_type, _v_f32(self.ln_post, "ln_w", self.ln_post.weight),
+                                 _v_f32(self.ln_post, "ln_b", self.ln_post.bias), self.ln_post.eps, proj,
+                                 normalize=_normalize, out_dtype=torch.float32 if out_dtype == torch.float32 else torch.bfloat16
+                                 ).to(out_dtype)
         if self.final_ln_after_pool:                                            # :638-640
             pooled = pool_fn(x2, B, L, self.pool_type)
             pooled = layer_norm_fn(pooled, self.ln_post.weight, self.ln_post.bias, self.ln_post.eps, self.ln_post)
@@ -580,6 +596,8 @@ class VisionTransformer(nn.Module):
         if self.proj is not None:                                               # :645-646  pooled @ proj
             pooled = linear_fn(pooled, self.proj, None, None, None, self, transpose_weight=True)
         pooled = pooled.to(out_dtype)
+        if _normalize:
+            pooled = normalize_fn(pooled)
         if self.output_tokens:
             return pooled, tokens_src.reshape(B, L, D)[:, 1:].to(out_dtype)
         return pooled

@@ -169,10 +169,45 @@ def dist_case(n, e, scale, world, local_loss, gather_with_grad, port):
     print(f"[dist {tag}] per-rank losses {[float(x['loss']) for x in res]}")
 
 
+class _Grid:
+    """the two attributes model.py:523-592 read from the model"""
+
+    def __init__(self, grid, ctx, width):
+        self.visual = type("V", (), {})()
+        self.visual.grid_size = grid
+        self.positional_embedding = torch.zeros(ctx, width)
+
+
+POS_CASES = [(16, 24, "bicubic", True), (24, 16, "bicubic", True), (16, 27, "bicubic", False), (14, 10, "bilinear", False)]
+TEXT_POS_CASES = [(77, 80, "linear", False), (80, 32, "linear", False)]
+
+
+def pos_embed_case(mdl):
+    """the reference's checkpoint-load resampling of positional embeddings (model.py:523-592) on seeded tables"""
+    out = {}
+    for (og, ng, mode, aa) in POS_CASES:
+        g = torch.Generator().manual_seed(1000 + og * 37 + ng)
+        table = torch.randn(og * og + 1, 48, generator=g, dtype=torch.float64)
+        sd = {"visual.positional_embedding": table.clone()}
+        mdl.resize_pos_embed(sd, _Grid((ng, ng), 8, 48), interpolation=mode, antialias=aa)
+        out[f"img_{og}_{ng}_{mode}_{int(aa)}"] = sd["visual.positional_embedding"].numpy()
+    for (oc, nc, mode, aa) in TEXT_POS_CASES:
+        g = torch.Generator().manual_seed(2000 + oc * 37 + nc)
+        table = torch.randn(oc, 40, generator=g, dtype=torch.float64)
+        sd = {"positional_embedding": table.clone()}
+        mdl.resize_text_pos_embed(sd, _Grid((4, 4), nc, 40), interpolation=mode, antialias=aa)
+        out[f"txt_{oc}_{nc}_{mode}_{int(aa)}"] = sd["positional_embedding"].numpy()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "pos_embed_resize.npz"), **out)
+    print(f"  wrote pos_embed_resize.npz ({len(out)} arrays)")
+
+
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     tr, mdl, lossm = ref_loader.load()
+    pos_embed_case(mdl)
+    if "--only-pos" in sys.argv:
+        return
     for cfg_name, batch in TOWER_CASES:
         tower_case(tr, mdl, lossm, cfg_name, batch)
     for n, e, s in LOSS_CASES:

@@ -480,3 +480,33 @@ def test_patch_embed_agrees_with_the_im2col_path(ops):
     a = ops.gemm_rowadd(ops.im2col_patches(img, P, kpad, lead_rows=1), wp, table).view(B, N + 1, D)
     b = ops.patch_embed(img, ops.pack_patch_weight(wconv, P), P, table)
     assert_close(b, a.float().cpu(), 4e-3, "patch_embed vs im2col + GEMM")
+
+
+@pytest.mark.parametrize("B,L,D,E,mode,ln,normalize,out_dtype", [
+    (9, 257, 1024, 768, "avg", True, True, torch.float32),     # L/14 head; B not a multiple of the images per CTA
+    (4, 101, 192, 192, "avg", True, False, torch.bfloat16),    # Ti/16
+    (6, 577, 768, 512, "avg", True, True, torch.bfloat16),     # B/16@384
+    (5, 257, 1280, 1024, "avg", True, True, torch.float32),    # H/14: 160 column vectors (one row group)
+    (7, 17, 128, 64, "tok", True, True, torch.float32),        # class-token pooling
+    (3, 80, 768, 768, "last", True, True, torch.float32),      # text tower: last token
+    (8, 50, 256, 0, "avg", False, False, torch.float32),       # pooling only (no LayerNorm, no projection)
+    (600, 10, 64, 32, "avg", True, True, torch.float32),       # more CTAs than SMs
+])
+def test_pool_head_one_kernel(ops, B, L, D, E, mode, ln, normalize, out_dtype):
+    """transformer.py:599-607,638-646 + model.py:267 in one launch (pool_head_kernel) against fp32 torch math on the same
+    bf16 tokens / projection."""
+    x = rnd(B, L, D, seed=1).bfloat16()
+    gamma = 1.0 + 0.1 * rnd(D, seed=2)
+    beta = 0.1 * rnd(D, seed=3)
+    proj = (rnd(D, E, seed=4) * D ** -0.5).bfloat16() if E else None
+    got = ops.pool_head(x.cuda(), mode, gamma.cuda() if ln else None, beta.cuda() if ln else None, 1e-6,
+                        proj.cuda() if proj is not None else None, normalize=normalize, out_dtype=out_dtype)
+    xf = x.float()
+    pooled = {"avg": xf[:, 1:].mean(1), "tok": xf[:, 0], "last": xf[:, -1]}[mode]
+    if ln:
+        pooled = torch.nn.functional.layer_norm(pooled, (D,), gamma, beta, 1e-6)
+    y = pooled @ proj.float() if proj is not None else pooled
+    if normalize:
+        y = torch.nn.functional.normalize(y, dim=-1)
+    assert got.dtype == out_dtype and tuple(got.shape) == tuple(y.shape)
+    assert_close(got, y, 1e-2 if out_dtype == torch.bfloat16 else 2e-4, f"pool head {mode}")

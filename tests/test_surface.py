@@ -138,3 +138,47 @@ def test_decay_mask_is_the_reference_kernel_rule():
             want |= {f"{pre}{i}.attn.in_proj_weight", f"{pre}{i}.attn.out_proj.weight", f"{pre}{i}.mlp.c_fc.weight",
                      f"{pre}{i}.mlp.c_proj.weight"}
     assert decayed == want
+
+
+def test_resize_pos_embed_matches_reference_golden(golden):
+    """checkpoint interchange (reference model.py:523-592): positional-embedding resampling at load
+    time against tables the reference's own resize_pos_embed / resize_text_pos_embed produced (oracle/make_golden.py)."""
+    import numpy as np
+    import torch
+    import openvision_b200 as ovb
+    from oracle.make_golden import POS_CASES, TEXT_POS_CASES, _Grid
+    g = golden("pos_embed_resize.npz")
+    for (og, ng, mode, aa) in POS_CASES:
+        gen = torch.Generator().manual_seed(1000 + og * 37 + ng)
+        table = torch.randn(og * og + 1, 48, generator=gen, dtype=torch.float64)
+        sd = {"visual.positional_embedding": table.clone()}
+        ovb.resize_pos_embed(sd, _Grid((ng, ng), 8, 48), interpolation=mode, antialias=aa)
+        ref = g[f"img_{og}_{ng}_{mode}_{int(aa)}"]
+        got = sd["visual.positional_embedding"].numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-12, (og, ng, mode, aa)
+        assert np.array_equal(got[0], table[0].numpy()), "class-token row must pass through"
+    for (oc, nc, mode, aa) in TEXT_POS_CASES:
+        gen = torch.Generator().manual_seed(2000 + oc * 37 + nc)
+        table = torch.randn(oc, 40, generator=gen, dtype=torch.float64)
+        sd = {"positional_embedding": table.clone()}
+        ovb.resize_text_pos_embed(sd, _Grid((4, 4), nc, 40), interpolation=mode, antialias=aa)
+        assert np.abs(sd["positional_embedding"].numpy() - g[f"txt_{oc}_{nc}_{mode}_{int(aa)}"]).max() < 1e-12
+
+
+def test_resize_pos_embed_then_strict_load():
+    """a checkpoint trained at another resolution loads strictly after the resize (factory.py:178-179 order)."""
+    import torch
+    import openvision_b200 as ovb
+    from oracle import synth
+    cfg = synth.CONFIGS["mini-ov"]                      # 48 px / patch 16: 3 x 3 grid
+    model = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    sd = synth.make_state_dict("mini-ov", seed=0)
+    width = sd["visual.positional_embedding"].shape[1]
+    sd["visual.positional_embedding"] = torch.randn(5 * 5 + 1, width)      # as if trained at 80 px
+    sd["positional_embedding"] = torch.randn(12, sd["positional_embedding"].shape[1])
+    ovb.resize_pos_embed(sd, model)
+    ovb.resize_text_pos_embed(sd, model)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    assert tuple(model.visual.positional_embedding.shape) == (3 * 3 + 1, width)
