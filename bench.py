@@ -555,6 +555,9 @@ def train_workload(torch, ovb, ops, rec, name, batch, world, rank, steps, warmup
     named = list(tower.named_parameters()) + [("logit_scale", log_scale)]
     opt = ovb.FlatAdamW(named, lr=1e-4, b1=0.9, b2=0.95, weight_decay=0.2, grad_clip_norm=1.0)
     step_no = [0]
+    # DP gradient sum over NVLink: buckets of the flat gradient buffers, each all-reduced (NCCL, async) from a
+    # post-accumulate-grad hook as soon as its last gradient is in, i.e. under the rest of the backward pass
+    reducer = opt.overlap_all_reduce(bucket_bytes=64 << 20) if world > 1 else None
 
     def step():
         opt.zero_grad()
@@ -562,8 +565,8 @@ def train_workload(torch, ovb, ops, rec, name, batch, world, rank, steps, warmup
         feats = ovb.model._normalize(feats)
         loss = crit(feats, txt, log_scale.exp())
         loss.backward()
-        if world > 1:
-            opt.all_reduce_grads()          # DP gradient sum over NVLink (bucketed NCCL calls on the flat buffers)
+        if reducer is not None:
+            reducer.finish()
         step_no[0] += 1
         opt.step(lr_mult=ovb.cosine_schedule(step_no[0], 10000, 100), grad_scale=1.0 / world)
         return loss
@@ -609,6 +612,9 @@ def train_workload(torch, ovb, ops, rec, name, batch, world, rank, steps, warmup
                         "peak_source": f"{peaks['src']} sustained cuBLAS bf16"},
            "kernels": kernels, "loss": float(loss.detach()), "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30,
            "gpu_launches": ops.launch_count - n0}
+    if reducer is not None:
+        reducer.remove()
+        out["config"]["gradient_all_reduce"] = f"{len(reducer.buckets)} buckets of <= 64 MiB launched from backward hooks (overlapped)"
     del tower, opt, images
     torch.cuda.empty_cache()
     return out

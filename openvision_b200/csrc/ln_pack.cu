@@ -62,25 +62,48 @@ __global__ void __launch_bounds__(128) ln_pack_kernel(const TW* __restrict__ W, 
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   __syncwarp();
-  // pass 3 (lane 0, serial): cancel the residual with one-ulp moves
-  if (lane == 0) {
-    for (int k = 0; k < K && r != 0.f; ++k) {
-      const uint32_t b = q[k];
-      if ((b & 0x7FFFu) == 0 || (b & 0x7F80u) == 0x7F80u) continue;   // zero, inf / nan: leave alone
-      const float qv = bf16_bits_to_float(b);
-      // the adjacent value in the direction that reduces r: down (towards -inf) if r > 0, up if r < 0
+  // pass 3: cancel the residual with one-ulp moves, entries visited in ascending k exactly as a serial walk would.  Each
+  // lane prepares its entry of a 32-entry chunk for both directions (coalesced loads, no dependence on r); the warp then
+  // steps through the chunk's candidates in lane order with the running residual r kept identical in every lane, so the
+  // only serial part is two shuffles per candidate instead of a dependent global load per entry.
+  for (int k0 = 0; k0 < K && r != 0.f; k0 += 32) {
+    const int k = k0 + lane;
+    uint32_t b = 0;
+    float delta_dn = 0.f, delta_up = 0.f;
+    bool ok_dn = false, ok_up = false;
+    if (k < K) {
+      b = q[k];
+      if (!((b & 0x7FFFu) == 0 || (b & 0x7F80u) == 0x7F80u)) {   // zero, inf / nan: leave alone
+        const float qv = bf16_bits_to_float(b);
+        const float v = fmaf(ldw<TW>(w + k), gamma[k], -mean);
+        const float e = v - qv;                                     // rounding error of this entry
+        // the adjacent value towards -inf (used when r > 0) and towards +inf (r < 0)
+        const uint32_t nb_dn = (qv > 0.f) ? b - 1 : b + 1;
+        const uint32_t nb_up = (qv > 0.f) ? b + 1 : b - 1;
+        if ((nb_dn & 0x7F80u) != 0x7F80u) {
+          delta_dn = bf16_bits_to_float(nb_dn) - qv;
+          ok_dn = !(e * delta_dn < 0.25f * delta_dn * delta_dn);    // only entries already off in that direction
+        }
+        if ((nb_up & 0x7F80u) != 0x7F80u) {
+          delta_up = bf16_bits_to_float(nb_up) - qv;
+          ok_up = !(e * delta_up < 0.25f * delta_up * delta_up);
+        }
+      }
+    }
+    unsigned rem = __ballot_sync(0xffffffffu, ok_dn || ok_up);
+    while (rem != 0u && r != 0.f) {
+      const int j = __ffs(rem) - 1;
+      rem &= rem - 1;
       const bool down = r > 0.f;
-      const bool shrink = (qv > 0.f) == down;                          // magnitude decreases
-      const uint32_t nb = shrink ? b - 1 : b + 1;
-      if ((nb & 0x7F80u) == 0x7F80u) continue;
-      const float nv = bf16_bits_to_float(nb);
-      const float delta = nv - qv;                                     // sign opposite to r
-      if (fabsf(delta) >= 2.f * fabsf(r)) continue;                    // the move would overshoot
-      const float v = fmaf(ldw<TW>(w + k), gamma[k], -mean);
-      const float e = v - qv;                                          // rounding error of this entry
-      if (e * delta < 0.25f * delta * delta) continue;                 // only entries already off in that direction
-      q[k] = static_cast<unsigned short>(nb);
-      r += delta;
+      const float dj = __shfl_sync(0xffffffffu, down ? delta_dn : delta_up, j);
+      const bool okj = __shfl_sync(0xffffffffu, static_cast<int>(down ? ok_dn : ok_up), j) != 0;
+      if (!okj || fabsf(dj) >= 2.f * fabsf(r)) continue;            // not off in that direction / the move would overshoot
+      if (lane == j) {
+        const float qv = bf16_bits_to_float(b);
+        const uint32_t nb = ((qv > 0.f) == down) ? b - 1 : b + 1;
+        q[k] = static_cast<unsigned short>(nb);
+      }
+      r += dj;
     }
   }
 }

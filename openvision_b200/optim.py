@@ -80,6 +80,69 @@ class _Group:
             off += sz
 
 
+class BucketedGradReducer:
+    """Data-parallel gradient SUM overlapped with the backward pass (the reference averages the gradients inside its jitted
+    step, main_clip.py:480-483, where XLA overlaps the collective with the remaining backward; on the PyTorch surface that is
+    DDP's job).  The flat gradient buffer of every parameter group is cut into buckets of whole parameters; a
+    post-accumulate-grad hook per parameter counts its bucket down, and the bucket's NCCL all-reduce is enqueued (async, on
+    NCCL's own stream) the moment its last gradient has been accumulated - parameters are laid out in registration order
+    and gradients arrive roughly in reverse, so the buckets of the last layers are already on the wire while the first
+    layers are still in backward.  finish() launches whatever never fired (parameters without a gradient this step) and
+    waits for everything.  Works on any backend (tests run it under gloo on CPU buffers)."""
+
+    class _Bucket:
+        __slots__ = ("flat", "lo", "hi", "n", "pending", "work")
+
+    def __init__(self, groups, bucket_bytes: int = 64 << 20, group=None):
+        self.process_group = group
+        self.buckets = []
+        self._handles = []
+        for g in groups:
+            per = max(1, bucket_bytes // g.flat_g.element_size())
+            cur = None
+            base = g.flat_g.data_ptr()
+            for p in g.params:
+                lo = (p.grad.data_ptr() - base) // g.flat_g.element_size()
+                hi = lo + p.numel()
+                if cur is None or hi - cur.lo > per and cur.n > 0:
+                    cur = self._Bucket()
+                    cur.flat, cur.lo, cur.hi, cur.n, cur.pending, cur.work = g.flat_g, lo, hi, 0, 0, None
+                    self.buckets.append(cur)
+                cur.hi = hi
+                cur.n += 1
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(cur)))
+        self.reset()
+
+    def _make_hook(self, bucket):
+        def hook(_param):
+            bucket.pending -= 1
+            if bucket.pending == 0 and bucket.work is None:
+                self._launch(bucket)
+        return hook
+
+    def _launch(self, b):
+        import torch.distributed as dist
+        b.work = dist.all_reduce(b.flat[b.lo:b.hi], group=self.process_group, async_op=True)
+
+    def reset(self) -> None:
+        for b in self.buckets:
+            b.pending, b.work = b.n, None
+
+    def finish(self) -> None:
+        """call after backward(): every bucket reduced and visible to the current stream; re-armed for the next step"""
+        for b in self.buckets:
+            if b.work is None:
+                self._launch(b)
+        for b in self.buckets:
+            b.work.wait()
+        self.reset()
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 class FlatAdamW:
     """scale_by_adam (bf16 first moment) + decoupled weight decay + lr schedule + optional global-norm clipping, on libovk
     kernels (ops.adamw_step / ops.sumsq).  `named_params`: iterable of (name, parameter) with requires_grad."""
@@ -123,6 +186,12 @@ class FlatAdamW:
                 works.append(dist.all_reduce(g.flat_g[off:off + per], group=group, async_op=True))
         for w in works:
             w.wait()
+
+    def overlap_all_reduce(self, bucket_bytes: int = 64 << 20, group=None) -> BucketedGradReducer:
+        """Arm the overlapped, bucketed gradient all-reduce (BucketedGradReducer): call once after construction, then
+        `reducer.finish()` after every backward() instead of all_reduce_grads()."""
+        self.reducer = BucketedGradReducer(self.groups, bucket_bytes, group)
+        return self.reducer
 
     def step(self, lr_mult: float = 1.0, grad_scale: float = 1.0) -> None:
         self.step_count += 1

@@ -119,3 +119,62 @@ def test_gather_features_semantics(local_loss, gwg):
             assert torch.allclose(x["gi"], w[sl]) and torch.allclose(x["gt"], 2.0 * w[sl])
         else:            # no gradient reaches the local features through the gathered copies
             assert x["gi"] is None and x["gt"] is None
+
+
+def _reducer_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from openvision_b200.optim import BucketedGradReducer, _Group
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.GELU(),
+                                torch.nn.Linear(40, 8))
+    unused = torch.nn.Parameter(torch.zeros(16))          # never receives a gradient: its bucket is launched by finish()
+    named = list(model.named_parameters()) + [("unused", unused)]
+    group = _Group(named, decay=False)
+    red = BucketedGradReducer([group], bucket_bytes=4 * 1000)      # ~1000 floats per bucket -> several buckets
+    assert len(red.buckets) >= 3
+    launched_early = []
+    out = {}
+    for step in range(2):                                  # two steps: the reducer re-arms itself
+        group.flat_g.zero_()
+        g = torch.Generator().manual_seed(100 * step + rank)
+        x = torch.randn(16, 24, generator=g)
+        model(x).square().sum().backward()
+        launched_early.append(sum(b.work is not None for b in red.buckets))
+        red.finish()
+        out[step] = group.flat_g.clone()
+    out["early"] = launched_early
+    out["nbuckets"] = len(red.buckets)
+    torch.save(out, os.path.join(outdir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_gradient_all_reduce_overlaps_and_sums():
+    """SURVEY.md §8f rank 2 (main_clip.py:480-483): the DP gradient sum is bucketed and launched from
+    post-accumulate-grad hooks while backward is still running; result = sum of the ranks' gradients, on every rank."""
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_reducer_worker, args=(world, 29791, d), nprocs=world, join=True)
+        res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.GELU(),
+                                torch.nn.Linear(40, 8))
+    for step in range(2):
+        total = None
+        for rank in range(world):
+            model.zero_grad()
+            g = torch.Generator().manual_seed(100 * step + rank)
+            model(torch.randn(16, 24, generator=g)).square().sum().backward()
+            flat = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 8)) for p in model.parameters()])
+            total = flat if total is None else total + flat
+        for rank in range(world):
+            got = res[rank][step]
+            assert torch.allclose(got[:total.numel()], total, rtol=1e-5, atol=1e-6), (step, rank)
+            assert torch.equal(got[total.numel():], torch.zeros_like(got[total.numel():])), "unused parameter's slice stays zero"
+    # every bucket except the one holding the gradient-less parameter was already on the wire when backward returned
+    for rank in range(world):
+        assert all(e >= res[rank]["nbuckets"] - 1 for e in res[rank]["early"]), res[rank]["early"]
