@@ -201,6 +201,14 @@ int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int 
  * Scores are recomputed tile by tile; two launches (dQ, then dK/dV), no atomics. */
 int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                       int B, int L, int H, int hd, float scale, void* stream);
+/* The same two with the additive CAUSAL mask of the stock text tower (transformer.py:757-763 build_causal_mask, applied
+ * at model.py:276 `self.transformer(x, attn_mask=self.attn_mask)`): flags = OVK_ATT_CAUSAL masks every key j > query i
+ * (-inf before the softmax, so P and dS are exactly zero there).  flags = 0 is the unmasked call above. */
+#define OVK_ATT_CAUSAL 1
+int ovk_attention_fwd_ex(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, int flags,
+                         void* stream);
+int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                         int B, int L, int H, int hd, float scale, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Pooling head, transformer.py:599-607,638-646.

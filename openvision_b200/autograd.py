@@ -360,35 +360,36 @@ def normalize_fn(features: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 class _AttentionCore(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, B, L, H, hd):
+    def forward(ctx, qkv, B, L, H, hd, causal):
         if any(ctx.needs_input_grad):
-            out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+            out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True, causal=causal)
             ctx.save_for_backward(qkv, out, lse)
-            ctx.meta = (B, L, H, hd)
+            ctx.meta = (B, L, H, hd, causal)
             return out
-        return ops.attention(qkv, B, L, H, hd)
+        return ops.attention(qkv, B, L, H, hd, causal=causal)
 
     @staticmethod
     def backward(ctx, dout):
         qkv, out, lse = ctx.saved_tensors
-        B, L, H, hd = ctx.meta
-        return ops.attention_bwd(qkv, out, _c(dout), lse, B, L, H, hd), None, None, None, None
+        B, L, H, hd, causal = ctx.meta
+        return ops.attention_bwd(qkv, out, _c(dout), lse, B, L, H, hd, causal=causal), None, None, None, None, None
 
 
-def attention_block_fn(x2, attn, B, L, residual: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+def attention_block_fn(x2, attn, B, L, residual: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                       causal: bool = False):
     """in_proj GEMM (+bias) -> flash attention -> out_proj GEMM (+bias, +residual)  (module-by-module path)."""
     H = attn.num_heads
     hd = attn.embed_dim // H
     if _needs_grad(x2, attn.in_proj_weight, attn.out_proj.weight, residual):
         qkv = _Linear.apply(x2, attn.in_proj_weight, attn.in_proj_bias, None, _Sub(attn, "in"), False)
-        a = _AttentionCore.apply(qkv, B, L, H, hd)
+        a = _AttentionCore.apply(qkv, B, L, H, hd, causal)
         return _Linear.apply(a, attn.out_proj.weight, attn.out_proj.bias, residual, _Sub(attn, "out"), False)
     wqkv = _w_bf16(attn, "in_w", attn.in_proj_weight)
     bqkv = _v_f32(attn, "in_b", attn.in_proj_bias) if attn.in_proj_bias is not None else None
     wo = _w_bf16(attn, "out_w", attn.out_proj.weight)
     bo = _v_f32(attn, "out_b", attn.out_proj.bias) if attn.out_proj.bias is not None else None
     qkv = ops.gemm(x2, wqkv, bias=bqkv)
-    a = ops.attention(qkv, B, L, H, hd)
+    a = ops.attention(qkv, B, L, H, hd, causal=causal)
     return ops.gemm(a, wo, bias=bo, residual=residual, out=out)
 
 
@@ -445,7 +446,7 @@ def _ln_folded(owner, key, w, b, ln, gamma_f32, beta_f32, b_f32):
     return packed
 
 
-def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
+def _block_forward(x2, p, blk, B, L, inplace, save, stats=None, causal=False):
     """-> (y, saved tensors or None, row statistics of y or None).  `stats` are the partial (sum, sum sq) of the rows of
     x2 when the producer of x2 already had them (the previous block's last GEMM)."""
     H = blk.attn.num_heads
@@ -461,9 +462,9 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
         parts = (D + 127) // 128
         qkv = ops.gemm_ln(x2, wq, bias=dq, row_stats=stats, eps=blk.ln_1.eps)
         if save:
-            a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+            a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True, causal=causal)
         else:
-            a = ops.attention(qkv, B, L, H, hd)
+            a = ops.attention(qkv, B, L, H, hd, causal=causal)
         st_mid = torch.empty((parts, M, 2), dtype=torch.float32, device=x2.device)
         x_mid = ops.gemm_ln(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None, stats_out=st_mid)
         remlp = getattr(blk, "_recompute_mlp_hidden", False)   # selective recompute: u / f are rebuilt in backward
@@ -482,9 +483,9 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
         h = ops.layernorm(x2, p["g1"], p["b1"], blk.ln_1.eps)
     qkv = ops.gemm(h, p["wqkv"], bias=p["bqkv"])
     if save:
-        a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+        a, lse = ops.attention(qkv, B, L, H, hd, save_lse=True, causal=causal)
     else:
-        a = ops.attention(qkv, B, L, H, hd)
+        a = ops.attention(qkv, B, L, H, hd, causal=causal)
     x_mid = ops.gemm(a, p["wo"], bias=p["bo"], residual=x2, out=x2 if inplace else None)
     if save:
         h, mean2, rstd2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps, save_stats=True, out=h)
@@ -502,11 +503,11 @@ def _block_forward(x2, p, blk, B, L, inplace, save, stats=None):
 
 class _Block(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x2, stats, blk, B, L, *params):
+    def forward(ctx, x2, stats, blk, B, L, causal, *params):
         p = _block_packed(blk)
-        y, saved, st_y = _block_forward(x2, p, blk, B, L, inplace=False, save=True, stats=stats)
+        y, saved, st_y = _block_forward(x2, p, blk, B, L, inplace=False, save=True, stats=stats, causal=causal)
         ctx.save_for_backward(*saved)
-        ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params = blk, B, L, p, params
+        ctx.blk, ctx.B, ctx.L, ctx.p, ctx.params, ctx.causal = blk, B, L, p, params, causal
         if st_y is None:
             return y, None
         ctx.mark_non_differentiable(st_y)
@@ -521,7 +522,7 @@ class _Block(torch.autograd.Function):
         hd = blk.attn.embed_dim // H
         act = blk._act_kind()
         dy = _c(dy)
-        need_w = any(ctx.needs_input_grad[5:])
+        need_w = any(ctx.needs_input_grad[6:])
         # ---- MLP branch
         h2 = None
         if u is None:   # selective recompute: ln_2 output, then fc1 + GELU with the pre-activation saved
@@ -551,7 +552,7 @@ class _Block(torch.autograd.Function):
         da = ops.gemm_nn(dxm, p["wo"])
         g_out_w = ops.gemm_tn(dxm, a, out_dtype=_grad_dtype(out_w)) if need_w else None
         g_out_b = ops.colsum(dxm) if need_w and out_b is not None else None
-        dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, hd)
+        dqkv = ops.attention_bwd(qkv, a, da, lse, B, L, H, hd, causal=ctx.causal)
         del da
         if mean1 is None:
             h1, mean1, rstd1 = ops.layernorm(x_in, p["g1"], p["b1"], blk.ln_1.eps, save_stats=True)
@@ -567,16 +568,16 @@ class _Block(torch.autograd.Function):
                  _like_param(g_out_w, out_w), _like_param(g_out_b, out_b), _like_param(dg2, ln2_w),
                  _like_param(db2, ln2_b), _like_param(g_fc_w, fc_w), _like_param(g_fc_b, fc_b),
                  _like_param(g_pj_w, pj_w), _like_param(g_pj_b, pj_b))
-        return (dx, None, None, None, None) + grads
+        return (dx, None, None, None, None, None) + grads
 
 
-def block_fn(x2, blk, B, L, inplace, stats=None):
+def block_fn(x2, blk, B, L, inplace, stats=None, causal=False):
     """One ResidualAttentionBlock on a bf16 [B*L, D] residual stream -> (y, row statistics of y or None).
     5 kernels forward with LayerNorm folded into the GEMMs (QKV GEMM, attention, out-proj GEMM+residual, fc1 GEMM+GELU,
     fc2 GEMM+residual; +1 row-statistics kernel in the first block), 7 with the stand-alone LayerNorm kernels.
     `stats`: the statistics the previous block returned for x2, if any."""
     params = _block_params(blk)
     if _needs_grad(x2, *params):
-        return _Block.apply(x2, stats, blk, B, L, *params)
-    y, _, st_y = _block_forward(x2, _block_packed(blk), blk, B, L, inplace=inplace, save=False, stats=stats)
+        return _Block.apply(x2, stats, blk, B, L, causal, *params)
+    y, _, st_y = _block_forward(x2, _block_packed(blk), blk, B, L, inplace=inplace, save=False, stats=stats, causal=causal)
     return y, st_y

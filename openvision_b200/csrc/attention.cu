@@ -70,7 +70,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      const __grid_constant__ CUtensorMap tmTail, const __grid_constant__ CUtensorMap tmQKVb,
                      const __grid_constant__ CUtensorMap tmOb, float* __restrict__ lse_out,
                      __nv_bfloat16* __restrict__ out, int tail_row_fused, int L, int Lm, int H, int nq, int total_items,
-                     float scale_log2) {
+                     float scale_log2, int causal) {
   // PERSISTENT: each CTA walks work items (query tile, head, image) with stride gridDim.x, keeping its TMEM allocation,
   // barriers and the K/V TMA ring alive across items, so the next item's Q/K/V loads run under the current item's
   // softmax.  Query rows [0, nq * 128) are handled here; a short remainder of rows goes to attention_tail_kernel.
@@ -298,7 +298,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (lane == 0) mbar_arrive(q_empty);
       }
       for (int j = 0; j < nkv; ++j, ++g) {
-        const int valid = min(ATT_BKV, Lm - j * ATT_BKV) - 64 * half;   // valid columns of this half (may be <= 0)
+        // valid columns of this half (may be <= 0).  Causal (the text tower's additive mask, transformer.py:757-763: -inf
+        // above the diagonal): row q0 + r sees keys <= q0 + r, i.e. a per-thread column count; masked columns contribute 0
+        // to P and to the row sum exactly like the columns past the end of the sequence.
+        const int valid_u = min(ATT_BKV, Lm - j * ATT_BKV) - 64 * half;
+        const int valid = causal ? min(valid_u, q0 + r - j * ATT_BKV - 64 * half + 1) : valid_u;
         const int nblk = ((min(ATT_BKV, Lm - j * ATT_BKV) + 15) & ~15) - 64 * half;
         mbar_wait(s_full, g & 1, 16);
         tc_fence_after();
@@ -652,7 +656,14 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
 
 extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
                                  void* stream) {
+  return ovk_attention_fwd_ex(qkv, out, lse, B, L, H, hd, scale, 0, stream);
+}
+
+extern "C" int ovk_attention_fwd_ex(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale,
+                                    int flags, void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention: empty problem");
+  if (flags & ~OVK_ATT_CAUSAL) return set_error(OVK_ERR_SHAPE, "attention: unknown flags 0x%x", flags);
+  const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
   if (hd < 64 || hd > 80 || (hd % 8))
     return set_error(OVK_ERR_SHAPE, "attention: head dim %d not supported (64, 72 or 80)", hd);
   const bool ext = hd > ATT_HD;   // 64 < hd <= 80: extra 16-dim operand block (zero-filled past hd by TMA)
@@ -668,7 +679,7 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
     const int nq2 = (L - t2 + ATT_BQ - 1) / ATT_BQ;
     const char* odd_env = getenv("OVK_ATT_PAIR_ODD");   // =1: the pair kernels also for an odd tile count (tests of that path)
     const bool pair_odd = odd_env != nullptr && odd_env[0] == '1';
-    if (!ext && !force_v1 && L <= 4096 && (nq2 % 2 == 0 || pair_odd)) {
+    if (!ext && !force_v1 && !causal && L <= 4096 && (nq2 % 2 == 0 || pair_odd)) {
       // attention4.cu (half-block double buffering, one MMA warp per tile slot, cross-item prefetch, deferred epilogue) by
       // default; OVK_ATT_VER=3 / 2 (or the older OVK_ATT_V2=1) select the earlier generations for A/B measurements
       const char* ver = getenv("OVK_ATT_VER");
@@ -708,7 +719,7 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   }
   // a short remainder of query rows goes to the FMA-pipe tail kernel instead of a padded 128-row tile (hd = 64 only)
   int tail = L % ATT_BQ;
-  if (ext || L <= ATT_BQ || tail > ATT_MAX_TAIL || L > ATT_TAIL_MAX_L) tail = 0;
+  if (ext || causal || L <= ATT_BQ || tail > ATT_MAX_TAIL || L > ATT_TAIL_MAX_L) tail = 0;   // (the remainder-token paths are unmasked)
   const int l_main = L - tail;
   const int nq = (l_main + ATT_BQ - 1) / ATT_BQ;
   const long long items = static_cast<long long>(nq) * H * B;
@@ -721,11 +732,11 @@ extern "C" int ovk_attention_fwd(const void* qkv, void* out, float* lse, int B, 
   if (ext)
     attention_fwd_kernel<16><<<grid, ATT_THREADS, AttL<16>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse,
                                                                           reinterpret_cast<__nv_bfloat16*>(out), 0, L, l_main, H, nq,
-                                                                          static_cast<int>(items), scale * 1.4426950408889634f);
+                                                                          static_cast<int>(items), scale * 1.4426950408889634f, causal);
   else
     attention_fwd_kernel<0><<<grid, ATT_THREADS, AttL<0>::SMEM_BYTES, s>>>(tmQKV, tmO, tmTail, tmQKVb, tmOb, lse,
                                                                       reinterpret_cast<__nv_bfloat16*>(out), fused_tail, L, l_main, H, nq,
-                                                                      static_cast<int>(items), scale * 1.4426950408889634f);
+                                                                      static_cast<int>(items), scale * 1.4426950408889634f, causal);
   if ((rc = check_launch("attention_fwd_kernel"))) return rc;
   if (tail && !fused_tail) {
     dim3 tgrid((tail * H + 3) / 4, B);

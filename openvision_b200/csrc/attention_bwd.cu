@@ -61,7 +61,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQKV,
                      const __grid_constant__ CUtensorMap tmQKVb, const __grid_constant__ CUtensorMap tmOb,
                      const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
-                     const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale, int total_items) {
+                     const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale, int total_items,
+                     int causal) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention_bwd: dynamic smem base not 1024-byte aligned\n");
@@ -307,6 +308,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     for (int it = 0; it < nt; ++it, ++g) {
       const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
       const int valid_kv = min(AB_T, L - kv0);
+      // causal mask (transformer.py:757-763): query row qrow sees keys <= qrow; P and dS are zero above the diagonal, which
+      // is the same per-element masking as the columns past the end of the sequence, with a per-thread column count
+      const int qrow = ((MODE == MODE_DQ) ? t0 : it * AB_T) + r;
+      const int kmax = causal ? min(valid_kv, qrow - kv0 + 1) : valid_kv;
       if (MODE == MODE_DKV) {
         const int row = it * AB_T + r;
         lse2 = row < L ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
@@ -330,7 +335,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_x32(tmem_base + t_lane + AB_TM_DP + col, dv);
         tmem_ld_wait();
         uint32_t pp[16], dd[16];
-        if (col + 32 <= valid_kv) {   // full chunk (the common case): no per-element masking
+        if (col + 32 <= kmax) {   // full chunk (the common case): no per-element masking
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
@@ -343,10 +348,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           for (int j = 0; j < 16; ++j) {
             float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
             float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
-            p0 = (col + 2 * j < valid_kv) ? p0 : 0.f;
-            p1 = (col + 2 * j + 1 < valid_kv) ? p1 : 0.f;
-            const float d0 = (col + 2 * j < valid_kv) ? p0 * (__uint_as_float(dv[2 * j]) - dlt) : 0.f;
-            const float d1 = (col + 2 * j + 1 < valid_kv) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dlt) : 0.f;
+            p0 = (col + 2 * j < kmax) ? p0 : 0.f;
+            p1 = (col + 2 * j + 1 < kmax) ? p1 : 0.f;
+            const float d0 = (col + 2 * j < kmax) ? p0 * (__uint_as_float(dv[2 * j]) - dlt) : 0.f;
+            const float d1 = (col + 2 * j + 1 < kmax) ? p1 * (__uint_as_float(dv[2 * j + 1]) - dlt) : 0.f;
             pp[j] = pack_bf16x2(p0, p1);
             dd[j] = pack_bf16x2(d0, d1);
           }
@@ -448,7 +453,14 @@ using namespace ovk;
 
 extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                  float* delta, int B, int L, int H, int hd, float scale, void* stream) {
+  return ovk_attention_bwd_ex(qkv, out, dout, lse, dqkv, delta, B, L, H, hd, scale, 0, stream);
+}
+
+extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                    float* delta, int B, int L, int H, int hd, float scale, int flags, void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
+  if (flags & ~OVK_ATT_CAUSAL) return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
+  const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
   if (hd < 64 || hd > 80 || (hd % 8))
     return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (64, 72 or 80)", hd);
   const bool ext = hd > AB_HD;
@@ -494,16 +506,16 @@ extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* d
   const int grid = items < num_sms() ? items : num_sms();   // persistent: one CTA per SM (512 TMEM columns each)
   if (ext) {
     attention_bwd_kernel<MODE_DQ, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                 tmDQKVb, lse, delta, L, H, scale, items);
+                                                                                 tmDQKVb, lse, delta, L, H, scale, items, causal);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                  tmDQKVb, lse, delta, L, H, scale, items);
+                                                                                  tmDQKVb, lse, delta, L, H, scale, items, causal);
   } else {
     attention_bwd_kernel<MODE_DQ, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                             tmDQKVb, lse, delta, L, H, scale, items);
+                                                                             tmDQKVb, lse, delta, L, H, scale, items, causal);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                              tmDQKVb, lse, delta, L, H, scale, items);
+                                                                              tmDQKVb, lse, delta, L, H, scale, items, causal);
   }
   return check_launch("attention_bwd_kernel<dKdV>");
 }

@@ -150,8 +150,8 @@ def text_global_pool(x, text: Optional[torch.Tensor] = None, pool_type: str = 'a
 
 
 class TextTransformer(nn.Module):
-    """transformer.py:669-816. The OpenVision text towers are non-causal (no_causal_mask=True) and run on the same
-    libovk block kernels as the image tower; a causal additive mask is not on the hot path of this build."""
+    """transformer.py:669-816. Runs on the same libovk block kernels as the image tower: non-causal for the OpenVision text
+    configs (no_causal_mask=True), with the causal flag of the attention kernels for the stock ones."""
 
     def __init__(self, context_length: int = 77, vocab_size: int = 49408, width: int = 512, heads: int = 8,
                  layers: int = 12, mlp_ratio: float = 4.0, ls_init_value: float = None, output_dim: int = 512,
@@ -309,18 +309,15 @@ class CLIP(nn.Module):
     def encode_text(self, text, normalize: bool = False):
         """model.py:269-284: embedding gather + positional add -> transformer -> ln_final -> pool -> projection."""
         from .autograd import _needs_grad, layer_norm_fn, linear_fn
-        if self.attn_mask is not None:
-            raise OvkError("causal text towers are not on the B200 hot path of this build "
-                           "(OpenVision text configs set no_causal_mask=True)")
         B, L = text.shape
         x = self.token_embedding(text) + self.positional_embedding[:L]          # gather + add (index plumbing)
         out_dtype = _out_dtype(x)
         hooked = _global_hooks() or _own_hooks(self.transformer) or _own_hooks(self.ln_final)
         if hooked:   # model.py:276-277 through __call__, so hooks on the text transformer / ln_final see the stock tensors
-            x3 = self.ln_final(self.transformer(x.to(torch.bfloat16)))
+            x3 = self.ln_final(self.transformer(x.to(torch.bfloat16), attn_mask=self.attn_mask))
             D = x3.shape[-1]
         else:
-            x2 = self.transformer.forward_tokens(_as_bf16_2d(x), B, L, owned=True)
+            x2 = self.transformer.forward_tokens(_as_bf16_2d(x), B, L, owned=True, attn_mask=self.attn_mask)
             D = x2.shape[-1]
             proj = self.text_projection
             if (self.text_pool_type in ('first', 'last') and D % 8 == 0 and not isinstance(proj, nn.Module)

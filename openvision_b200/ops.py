@@ -434,7 +434,7 @@ def embed_assemble(patch_tokens: torch.Tensor, cls: torch.Tensor, pos: torch.Ten
 
 
 def attention(qkv: torch.Tensor, B: int, L: int, H: int, hd: int, scale: Optional[float] = None,
-              save_lse: bool = False):
+              save_lse: bool = False, causal: bool = False):
     """qkv bf16 [B*L, 3*H*hd] (in_proj output) -> bf16 [B*L, H*hd]; optional lse fp32 [B,H,L].
     Kernel: attention_fwd_kernel (tcgen05 flash attention)."""
     _require(qkv, torch.bfloat16, "attention.qkv", 2)
@@ -445,7 +445,7 @@ def attention(qkv: torch.Tensor, B: int, L: int, H: int, hd: int, scale: Optiona
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
     with _timed("attention", 4.0 * B * H * L * L * hd):
-        _lib.call("ovk_attention_fwd", _p(qkv), _p(out), _p(lse), B, L, H, hd, float(scale), _stream())
+        _lib.call("ovk_attention_fwd_ex", _p(qkv), _p(out), _p(lse), B, L, H, hd, float(scale), int(bool(causal)), _stream())
     _count()
     return (out, lse) if save_lse else out
 
@@ -613,7 +613,8 @@ def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale, row_lse, col_lse
 # ----------------------------------------------------------------------------------------------------------------
 # backward kernels of the image tower
 # ----------------------------------------------------------------------------------------------------------------
-def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: Optional[float] = None) -> torch.Tensor:
+def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: Optional[float] = None,
+                  causal: bool = False) -> torch.Tensor:
     """dqkv bf16 [B*L, 3*H*hd] from qkv, the forward output, its gradient and the saved lse.
     Kernels: attention_bwd_kernel<dQ>, attention_bwd_kernel<dKdV>."""
     for t, name, cols in ((qkv, "qkv", 3 * H * hd), (out, "out", H * hd), (dout, "dout", H * hd)):
@@ -626,8 +627,8 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
     with _timed("attention_bwd", 14.0 * B * H * L * L * hd):
-        _lib.call("ovk_attention_bwd", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), B, L, H, hd,
-                  float(scale), _stream())
+        _lib.call("ovk_attention_bwd_ex", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), B, L, H, hd,
+                  float(scale), int(bool(causal)), _stream())
     _count(2)
     return dqkv
 

@@ -94,6 +94,33 @@ def _tree_hooks(m: nn.Module, include_self: bool = True) -> bool:
     return any(_own_hooks(x) for x in it)
 
 
+_MASK_KINDS = {}
+
+
+def _mask_is_causal(attn_mask: Optional[torch.Tensor], L: int) -> bool:
+    """None -> False; the additive causal mask of transformer.py:757-763 (0 on / below the diagonal, -inf above; any size
+    >= L, of which the leading [L, L] block applies) -> True; anything else is not on this path.  The kernels take a FLAG, not
+    the tensor, so the mask is inspected once per (storage, version) — one small device read-back — and cached."""
+    if attn_mask is None:
+        return False
+    key = (attn_mask.data_ptr(), attn_mask._version, tuple(attn_mask.shape), attn_mask.dtype, str(attn_mask.device), L)
+    kind = _MASK_KINDS.get(key)
+    if kind is None:
+        ok = attn_mask.dim() == 2 and attn_mask.shape[0] >= L and attn_mask.shape[1] >= L and attn_mask.is_floating_point()
+        if ok:
+            m = attn_mask[:L, :L].float()
+            upper = torch.ones(L, L, dtype=torch.bool, device=m.device).triu(1)
+            ok = bool(torch.isneginf(m[upper]).all()) and bool((m[~upper] == 0).all())
+        kind = "causal" if ok else "other"
+        if len(_MASK_KINDS) > 64:
+            _MASK_KINDS.clear()
+        _MASK_KINDS[key] = kind
+    if kind != "causal":
+        raise OvkError("attention masks other than the causal mask of the text tower (transformer.py:757-763) are outside "
+                       "the B200 hot path of this build")
+    return True
+
+
 def _residual_add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     from .autograd import add_fn
     shape = a.shape
@@ -237,12 +264,13 @@ class MultiheadSelfAttention(nn.MultiheadAttention):
         if value is None:
             value = query
         if (key is not query) or (value is not query) or key_padding_mask is not None or need_weights or \
-                attn_mask is not None or is_causal or not self.batch_first:
-            raise OvkError("MultiheadSelfAttention: only batch-first self-attention without masks / weights is on the "
-                           "B200 hot path (the configuration the OpenVision towers use)")
+                not self.batch_first:
+            raise OvkError("MultiheadSelfAttention: only batch-first self-attention without padding masks / weights is on "
+                           "the B200 hot path (the configuration the OpenVision towers use)")
         from .autograd import attention_block_fn
         B, L, D = query.shape
-        y = attention_block_fn(_as_bf16_2d(query), self, B, L, residual=None)
+        causal = _mask_is_causal(attn_mask, L) or (bool(is_causal) and attn_mask is None)
+        y = attention_block_fn(_as_bf16_2d(query), self, B, L, residual=None, causal=causal)
         y = y.reshape(B, L, D).to(_out_dtype(query) if query.dtype != torch.bfloat16 else torch.bfloat16)
         return y, None
 
@@ -294,26 +322,25 @@ class ResidualAttentionBlock(nn.Module):
     def attention(self, q_x, k_x=None, v_x=None, attn_mask=None):
         return self.attn(q_x, k_x, v_x, need_weights=False, attn_mask=attn_mask)[0]
 
-    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, inplace: bool, stats: Optional[torch.Tensor] = None):
+    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, inplace: bool, stats: Optional[torch.Tensor] = None,
+                       causal: bool = False):
         """Fast path on a bf16 [B*L, D] residual stream -> (y, row statistics of y or None). When `inplace`, x2 is
         updated in place (it is ours). `stats` are the LayerNorm statistics of x2 handed over by the previous block."""
         from .autograd import block_fn
-        return block_fn(x2, self, B, L, inplace, stats)
+        return block_fn(x2, self, B, L, inplace, stats, causal)
 
     def forward(self, q_x: torch.Tensor, k_x=None, v_x=None, attn_mask=None):
         if k_x is not None or v_x is not None:
             raise OvkError("cross-attention inputs are outside the hot path of this build")
-        if attn_mask is not None:
-            raise OvkError("additive attention masks (causal text tower) are not on the B200 hot path; "
-                           "OpenVision text towers use no_causal_mask=True")
         B, L, D = q_x.shape
+        causal = _mask_is_causal(attn_mask, L)
         if self._fusable():
-            y, _ = self.forward_tokens(_as_bf16_2d(q_x), B, L, inplace=False)
+            y, _ = self.forward_tokens(_as_bf16_2d(q_x), B, L, inplace=False, causal=causal)
             return y.reshape(B, L, D).to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
         # module-by-module path (hooks on any sub-module, LayerScale, unknown activation): the reference's forward
         # (transformer.py:254-265) with every sub-module invoked through __call__ so its hooks fire, all on libovk kernels
         x = q_x if q_x.dtype == torch.bfloat16 else q_x.to(torch.bfloat16)
-        x = _residual_add(x, _as_bf16_2d(self.ls_1(self.attention(q_x=self.ln_1(x)))).reshape(B, L, D))
+        x = _residual_add(x, _as_bf16_2d(self.ls_1(self.attention(q_x=self.ln_1(x), attn_mask=attn_mask))).reshape(B, L, D))
         x = _residual_add(x, _as_bf16_2d(self.ls_2(self.mlp(self.ln_2(x)))).reshape(B, L, D))
         return x.to(_out_dtype(q_x) if q_x.dtype != torch.bfloat16 else torch.bfloat16)
 
@@ -352,29 +379,30 @@ class Transformer(nn.Module):
             return self.resblocks[0].mlp.c_fc.int8_original_dtype
         return self.resblocks[0].mlp.c_fc.weight.dtype
 
-    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, owned: bool) -> torch.Tensor:
-        """bf16 [B*L, D] -> bf16 [B*L, D]; `owned` says whether x2 may be overwritten."""
+    def forward_tokens(self, x2: torch.Tensor, B: int, L: int, owned: bool, attn_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bf16 [B*L, D] -> bf16 [B*L, D]; `owned` says whether x2 may be overwritten; attn_mask: None or the causal mask."""
+        causal = _mask_is_causal(attn_mask, L)
         stats = None   # LayerNorm statistics of x2, produced by the epilogue of the GEMM that wrote it
         for r in self.resblocks:
             if r._fusable() and not _own_hooks(r):
                 r._recompute_mlp_hidden = self.recompute_mlp_hidden
                 if self.grad_checkpointing and torch.is_grad_enabled() and x2.requires_grad:
-                    x2, stats = checkpoint(r.forward_tokens, x2, B, L, False, stats, use_reentrant=False)
+                    x2, stats = checkpoint(r.forward_tokens, x2, B, L, False, stats, causal, use_reentrant=False)
                 else:
-                    x2, stats = r.forward_tokens(x2, B, L, inplace=owned and not torch.is_grad_enabled(), stats=stats)
+                    x2, stats = r.forward_tokens(x2, B, L, inplace=owned and not torch.is_grad_enabled(), stats=stats,
+                                                 causal=causal)
                 owned = True
             else:
-                x2 = _as_bf16_2d(r(x2.reshape(B, L, -1)))
+                x2 = _as_bf16_2d(r(x2.reshape(B, L, -1), attn_mask=attn_mask))
                 owned, stats = True, None
         return x2
 
     def forward(self, x: torch.Tensor, attn_mask: Optional[torch.Tensor] = None):
-        if attn_mask is not None:
-            raise OvkError("additive attention masks are not on the B200 hot path (see ResidualAttentionBlock)")
         if not self.batch_first:
             x = x.transpose(0, 1)
         B, L, D = x.shape
-        y = self.forward_tokens(_as_bf16_2d(x), B, L, owned=x.dtype != torch.bfloat16 or not x.is_contiguous())
+        y = self.forward_tokens(_as_bf16_2d(x), B, L, owned=x.dtype != torch.bfloat16 or not x.is_contiguous(),
+                                attn_mask=attn_mask)
         y = y.reshape(B, L, D).to(_out_dtype(x) if x.dtype != torch.bfloat16 else torch.bfloat16)
         if not self.batch_first:
             y = y.transpose(0, 1)

@@ -172,12 +172,7 @@ def test_tower_and_loss_gradients_match_reference(golden, cfg_name, batch):
     m = m.cuda().train()
     images = synth.make_images(cfg_name, batch, 0).cuda().requires_grad_(True)
     text = synth.make_text(cfg_name, batch, 0).cuda()
-    if cfg["text"].get("no_causal_mask", False):
-        img_n, txt_n, scale = m(images, text)
-    else:   # stock config has a causal text tower (outside the hot path): feed the reference's text features
-        img_n = m.encode_image(images, normalize=True)
-        txt_n = torch.as_tensor(g["text_features_norm"]).float().cuda()
-        scale = m.logit_scale.exp()
+    img_n, txt_n, scale = m(images, text)      # mini-stock: causal text tower (attention kernels' causal flag, fwd + bwd)
     loss = ovb.ClipLoss()(img_n, txt_n, scale)
     loss.backward()
     ref_loss = float(g["loss"])
@@ -186,7 +181,7 @@ def test_tower_and_loss_gradients_match_reference(golden, cfg_name, batch):
     checked = 0
     for name, p in m.named_parameters():
         key = "grad/" + name
-        if key not in g or not name.startswith(("visual.", "logit_scale")):
+        if key not in g:
             continue
         assert p.grad is not None, name
         ref = g[key]
@@ -196,7 +191,7 @@ def test_tower_and_loss_gradients_match_reference(golden, cfg_name, batch):
         tol = 6e-2 if "ln_" not in name else 8e-2
         assert_grad(got, ref, name, tol)
         checked += 1
-    assert checked >= 25, checked
+    assert checked >= 50, checked
 
 
 def test_ti16_image_gradient_and_checkpointing(golden):

@@ -510,3 +510,29 @@ def test_pool_head_one_kernel(ops, B, L, D, E, mode, ln, normalize, out_dtype):
         y = torch.nn.functional.normalize(y, dim=-1)
     assert got.dtype == out_dtype and tuple(got.shape) == tuple(y.shape)
     assert_close(got, y, 1e-2 if out_dtype == torch.bfloat16 else 2e-4, f"pool head {mode}")
+
+
+@pytest.mark.parametrize("B,L,H,hd", [(3, 77, 2, 64), (2, 128, 1, 64), (2, 80, 3, 64), (2, 200, 2, 64), (1, 257, 2, 64),
+                                      (2, 300, 1, 64), (2, 77, 2, 80), (1, 130, 1, 80), (40, 77, 8, 64)])
+def test_attention_causal_forward_and_backward(ops, B, L, H, hd):
+    """The stock text tower's additive causal mask (transformer.py:757-763) as a kernel flag: forward, lse and all three
+    gradients against fp32 torch math with an explicit -inf mask."""
+    qkv = rnd(B * L, 3 * H * hd, seed=L + hd).bfloat16()
+    dout = rnd(B * L, H * hd, seed=L + hd + 1).bfloat16()
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True, causal=True)
+    x = qkv.float().view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)
+    mask = torch.full((L, L), float("-inf")).triu(1)
+    s = (x[0] @ x[1].transpose(-1, -2)) / math.sqrt(hd) + mask
+    ref = (torch.softmax(s, -1) @ x[2]).permute(0, 2, 1, 3).reshape(B * L, H * hd)
+    assert_close(out, ref, 2e-2, f"causal attention L{L}")
+    assert_close(lse, torch.logsumexp(s, -1), 1e-3, "causal attention lse")
+    ref.backward(dout.float())
+    dqkv = ops.attention_bwd(qkv.cuda(), out, dout.cuda(), lse, B, L, H, hd, causal=True)
+    dref = x.grad.permute(1, 3, 0, 2, 4).reshape(B * L, 3 * H * hd)
+    got = dqkv.float().cpu().view(B * L, 3, H * hd)
+    want = dref.view(B * L, 3, H * hd)
+    for i, name in enumerate("qkv"):
+        assert_close(got[:, i], want[:, i], 3e-2, f"causal attention d{name} L{L}")
+    # the flag matters: the unmasked call must differ
+    out0 = ops.attention(qkv.cuda(), B, L, H, hd)
+    assert (out0.float() - out.float()).abs().max().item() > 1e-2

@@ -38,13 +38,13 @@ def test_encode_image_and_text_match_reference_golden(golden, cfg_name, batch):
         check_embeddings(img_n, g["image_features_norm"], f"{cfg_name} image")
         ref_raw = torch.as_tensor(g["image_features"]).float()
         assert (raw.float().cpu() - ref_raw).abs().max().item() <= 3e-2 * ref_raw.abs().max().item()
-        if synth.CONFIGS[cfg_name]["text"].get("no_causal_mask", False):
-            txt_n = m.encode_text(text, normalize=True)
-            check_embeddings(txt_n, g["text_features_norm"], f"{cfg_name} text")
-            i2, t2, s = m(images, text)
-            assert abs(float(s) - float(g["logit_scale_exp"])) < 1e-4
-            check_embeddings(i2, g["image_features_norm"], "forward image")
-            check_embeddings(t2, g["text_features_norm"], "forward text")
+        # (mini-stock: the stock text tower with its causal mask, transformer.py:757-763 — the causal flag of the attention kernels)
+        txt_n = m.encode_text(text, normalize=True)
+        check_embeddings(txt_n, g["text_features_norm"], f"{cfg_name} text")
+        i2, t2, s = m(images, text)
+        assert abs(float(s) - float(g["logit_scale_exp"])) < 1e-4
+        check_embeddings(i2, g["image_features_norm"], "forward image")
+        check_embeddings(t2, g["text_features_norm"], "forward text")
 
 
 def test_piecewise_calls_like_ov_zero_shot(golden):
