@@ -4,8 +4,8 @@
 //
 // forward  (clip_loss_fwd_kernel): per 128 x 256 tile, each epilogue thread owns one row x 128 columns of the fp32
 //   accumulator.  One exponential per logit serves BOTH directions: e = 2^(z2 - c) with c the maximum of the warp's
-//   32 x 32 sub-block; row sums are thread-local (online-softmax recurrence, src/models/bpt.py:105-124), column sums are
-//   a 5-step shuffle butterfly (31 SHFL for 32 columns).  Rows / columns whose own maximum lies more than 2^100 below
+//   32 x 32 sub-block; row sums are thread-local (online-softmax recurrence, src/models/bpt.py:105-124), column sums go
+//   through a per-warp shared-memory transposition (warp_column_sums).  Rows / columns whose own maximum lies more than 2^100 below
 //   c (so that e would lose them) take an exact slow path, so the result does not depend on how well-scaled the
 //   features are.  Partials (max, sum) per (row, column-half of a tile) and per (row-tile, column) go to a workspace;
 //   clip_loss_finalize_kernel merges them into row_lse, col_max / col_sum (a rank's partial column statistics).
@@ -33,24 +33,34 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 
-// Transposing reduction: lane l holds e[0..31] (32 columns of its row); returns, in lane j, sum over lanes of e[j].
-__device__ __forceinline__ float warp_column_sums(float (&e)[32], uint32_t lane) {
+// Transposing reduction through shared memory: lane l holds e[0..31] (32 columns of its row); returns, in lane j, the sum
+// over the warp's 32 rows of column j.  Column-major scratch with a pitch of 36 floats: the 32 scalar stores of a column
+// are one conflict-free wavefront each (lanes = rows = consecutive words), and lane j reads its column back as eight
+// 16-byte loads (144-byte pitch: the 8 lanes of a quarter-warp phase cover all 32 banks).  73 instructions per 32 x 32 block
+// against 124 for the shuffle butterfly this replaces (31 SHFL + 31 FADD + 62 FSEL); the kernel is epilogue-bound.
+constexpr int CL_TP = 36;                         // scratch pitch (floats)
+constexpr int CL_T_BYTES = 32 * CL_TP * 4;        // per warp
+__device__ __forceinline__ float warp_column_sums(const float (&e)[32], uint32_t lane, uint32_t scratch) {
 #pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool up = (lane & half) != 0;
+  for (int c = 0; c < 32; ++c) sts_f32(scratch + (c * CL_TP + lane) * 4, e[c]);
+  __syncwarp();
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < half; ++k) {
-      const float send = up ? e[k] : e[k + half];
-      const float keep = up ? e[k + half] : e[k];
-      e[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
+  for (int q = 0; q < 8; ++q) {
+    const float4 v = lds_f32x4(scratch + (lane * CL_TP + 4 * q) * 4);
+    s[0] += v.x;
+    s[1] += v.y;
+    s[2] += v.z;
+    s[3] += v.w;
   }
-  return e[0];
+  __syncwarp();   // the scratch is rewritten by the next chunk
+  return (s[0] + s[1]) + (s[2] + s[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// epilogue scratch: [4 quads][256 cols] (ref, sum) + one transposition block per epilogue warp; the ring gives up a stage for it
 template <bool PAIR>
-using FwdLayout = GemmSmemLayout<CL_BN, 0, 4 * CL_BN * 8, PAIR>;  // epilogue scratch: [4 quads][256 cols] (ref, sum)
+using FwdLayout = GemmSmemLayout<CL_BN, 0, 4 * CL_BN * 8 + GEMM_EPI_WARPS * CL_T_BYTES, PAIR, PAIR ? 5 : 3>;
 
 template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -75,6 +85,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int et = quad * 32 + lane;
     const uint32_t bar_id = 1 + grp;
     const uint32_t scol = smem_u32(cx.epi_scratch());  // float2 [4][256]
+    const uint32_t tscr = scol + 4 * CL_BN * 8 + ew * CL_T_BYTES;   // this warp's transposition block
     const float scale = __ldg(scale_ptr);              // the temperature lives on the device (no host read-back)
     const float s2 = scale * LOG2E;
     GemmSched sched(n_loc, n_cols, CL_BN, E, 1, PAIR, cx.rank);
@@ -146,7 +157,7 @@ clip_loss_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           l_row = fmaf(l_row, fast_exp2(m_row - m_new), add);
           m_row = m_new;
         }
-        float cs = warp_column_sums(e, lane);  // lane j: sum over the warp's 32 rows of column col0 + j
+        float cs = warp_column_sums(e, lane, tscr);  // lane j: sum over the warp's 32 rows of column col0 + j
         float cref_out = c_ref;
         unsigned need = __ballot_sync(0xffffffffu, cs < 7.8886e-31f /* 2^-100 */ && col0 + (int)lane < n_cols);
         while (need) {  // columns far below the sub-block maximum: exact path, one column at a time

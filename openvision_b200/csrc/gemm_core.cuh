@@ -31,10 +31,10 @@ constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_PANEL_BYTES = 64 * 128;                 // MN-major panel: 64 k-rows x 128 B
 
 // C_BYTES: output staging area (TMA store), EPI_BYTES: epilogue scratch (bias tile, column statistics, ...).
-template <int BN, int C_BYTES = 2 * GEMM_BM * 128, int EPI_BYTES = 2 * BN * 4, bool PAIR = false>
+template <int BN, int C_BYTES = 2 * GEMM_BM * 128, int EPI_BYTES = 2 * BN * 4, bool PAIR = false, int STAGES_ = 0>
 struct GemmSmemLayout {
   static constexpr bool kPair = PAIR;
-  static constexpr int STAGES = PAIR ? 6 : 4;
+  static constexpr int STAGES = STAGES_ > 0 ? STAGES_ : (PAIR ? 6 : 4);   // ring depth (kernels with a big epilogue scratch ask for fewer)
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of the B tile staged by THIS CTA
   static constexpr int B_STAGE_BYTES = B_ROWS * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = GEMM_A_STAGE_BYTES + B_STAGE_BYTES;
