@@ -13,6 +13,8 @@ embeddings inside the timed region.  Prints ONE JSON line on rank 0.  Besides th
   clip_loss        : BASELINE's second metric (configs[3]) with its own roofline / cpu_baseline, and at N > 1 a parity
                      check of the NCCL path against the single-GPU fused loss on the SAME global feature set
   reference_gpu    : the UNMODIFIED reference modules (baseline/_ref, see oracle/ref_loader.py) on the same GPU in bf16
+  small_batch_latency (inside extra_workloads): ms per encode_image call at batch 1 / 8, eager vs one CUDA-graph launch vs the
+                     reference modules on the same GPU (the ov-* scripts' regime)
   extra_workloads  : BASELINE configs[2] (B/16@384 fwd+bwd, batch 512) and configs[4] (H/14 training step, 1024 / GPU)
 
 --impl reference times the reference's own CPU implementation of the path: the unmodified reference modules when
@@ -491,6 +493,55 @@ def reference_on_gpu(torch, cfg, batch: int, iters: int, loss_n: int, embed: int
     return out
 
 
+def small_batch_latency(torch, ovb, cfg, batches=(1, 8), iters=30):
+    """The ov-* scripts' regime (batch 1-8): ms per CLIP.encode_image(normalize=True) call, launch-bound.  Eager libovk path,
+    the same kernels replayed from one CUDA graph (openvision_b200.graphed_encode_image), and the unmodified reference
+    modules (bf16, PyTorch eager) on the same GPU when baseline/_ref is present."""
+    torch.manual_seed(0)
+    model = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    del model.transformer, model.token_embedding
+    model = model.cuda().eval()
+    ovb.convert_weights_to_lp(model, torch.bfloat16)
+    ref = None
+    if _reference_available():
+        from oracle import ref_loader
+        _, mdl, _ = ref_loader.load()
+        ref = mdl.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]),
+                       cast_dtype=torch.bfloat16)
+        del ref.transformer, ref.token_embedding
+        ref = ref.cuda().eval()
+        mdl.convert_weights_to_lp(ref, dtype=torch.bfloat16)
+
+    def t(fn):
+        with torch.no_grad():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+        return s.elapsed_time(e) / iters
+
+    side = cfg["vision"]["image_size"]
+    rows = []
+    for b in batches:
+        img = torch.randn(b, 3, side, side, device="cuda")
+        graphed = ovb.graphed_encode_image(model, img, normalize=True)
+        row = {"batch": b, "eager_ms": t(lambda: model.encode_image(img, normalize=True)), "cuda_graph_ms": t(lambda: graphed(img))}
+        if ref is not None:
+            img16 = img.to(torch.bfloat16)
+            row["reference_gpu_eager_ms"] = t(lambda: ref.encode_image(img16, normalize=True))
+            row["reference_over_graph"] = row["reference_gpu_eager_ms"] / row["cuda_graph_ms"]
+        rows.append(row)
+        del graphed
+    del model, ref
+    torch.cuda.empty_cache()
+    return rows
+
+
 def attention_vs_sdpa(torch, ops, peaks, iters=10):
     """Head-to-head of ovk_attention_fwd against F.scaled_dot_product_attention (cuDNN and flash backends) on the tower's
     attention shapes (transformer.py:225,250-252), same GPU, bf16, CUDA events, burst (kernel timed alone)."""
@@ -777,6 +828,7 @@ def run_ours(args):
     if not args.no_extras:
         if rank == 0:
             leg("attention_vs_sdpa", lambda: attention_vs_sdpa(torch, ops, peaks))
+            leg("small_batch_latency", lambda: small_batch_latency(torch, ovb, cfg))
         del model
         torch.cuda.empty_cache()
         w_steps = max(2, min(args.steps, 4))

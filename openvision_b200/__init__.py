@@ -9,6 +9,7 @@ from ._lib import OvkError, load as load_library  # noqa: F401
 from .loss import ClipLoss, DualCaptionClipLoss, gather_features  # noqa: F401
 from .optim import FlatAdamW, cosine_schedule, decay_mask_from_modules  # noqa: F401
 from .configs import CONFIGS  # noqa: F401
+from .graphs import GraphedCall, graphed_encode_image, graphed_encode_text  # noqa: F401
 from .model import (CLIP, CLIPTextCfg, CLIPVisionCfg, TextTransformer, convert_weights_to_lp,  # noqa: F401
                     get_cast_dtype, get_input_dtype, resize_pos_embed, resize_text_pos_embed)
 from .transformer import (LayerNorm, LayerNormFp32, QuickGELU, ResidualAttentionBlock, Transformer,  # noqa: F401

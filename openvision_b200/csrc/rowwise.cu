@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   // Persistent: a warp walks rows with stride (warps in the grid) and keeps the gamma / beta of its own columns in
   // registers for all of them (re-reading them per row costs four L1 loads per 16 bytes of data, which is what limited
   // the first version).  MAXV <= 4: RPW = 2 rows are loaded before either is touched (more bytes in flight per SM).
-  constexpr int RPW = MAXV >= 8 ? 1 : 2;
-  constexpr bool GB_IN_REGS = MAXV <= 4;   // 16 * MAXV registers; wider rows read gamma / beta through L1 as before
+  constexpr int RPW = MAXV >= 8 ? 1 : 2;   // (host: rows per block = 8 * RPW)
+  constexpr bool GB_IN_REGS = MAXV <= 6;   // 16 * MAXV registers; wider rows read gamma / beta through L1 as before
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
                                                                const __nv_bfloat16* dres, long long lddres,
                                                                __nv_bfloat16* dx, long long lddx, int rows, int D) {
   // persistent like the forward: a warp walks rows with a grid stride and keeps gamma of its columns in registers
-  constexpr bool G_IN_REGS = MAXV <= 4;
+  constexpr bool G_IN_REGS = MAXV <= 6;
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_dx_kernel(const __nv_bfloat
   }
 }
 
-// One-pass variant for D <= 1024 (MAXV <= 4): the same persistent row walk also accumulates this lane's columns of
+// One-pass variant for D <= 1536 (MAXV <= 6): the same persistent row walk also accumulates this lane's columns of
 // dgamma = sum dy * xhat and dbeta = sum dy in registers over all the rows of the warp, then the block reduces its eight
 // warps through shared memory and issues one atomicAdd per column.  Saves the second pass over dy and x that the separate
 // column-sum kernel needs (6 -> 4 passes over [rows, D] with the residual gradient).
@@ -245,22 +245,43 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
                                                                   const __nv_bfloat16* dres, long long lddres,
                                                                   __nv_bfloat16* dx, long long lddx, float* __restrict__ dgamma,
                                                                   float* __restrict__ dbeta, int rows, int D) {
-  extern __shared__ float red[];   // [8 warps][2][MAXV * 256]
+  extern __shared__ float red[];   // [8 warps][2][MAXV * 256] (+ [MAXV * 256] gamma when G_SMEM)
+  // rows wider than 1024 (H/14: 1280): the 2 x 8 x MAXV column accumulators plus three row buffers leave no registers for
+  // gamma, which then lives in shared memory (two 16-byte loads per vector and pass) instead
+  constexpr bool G_SMEM = MAXV > 4;
+  constexpr int DP = MAXV * 256;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const int nvec = D >> 3;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
-  float gm[MAXV][8], dg[MAXV][8], db[MAXV][8];
+  float gm[G_SMEM ? 1 : MAXV][8], dg[MAXV][8], db[MAXV][8];
+  float* gs = red + 16 * DP;
+  if (G_SMEM) {
+    for (int c = threadIdx.x; c < DP; c += blockDim.x) gs[c] = c < D ? gamma[c] : 0.f;
+    __syncthreads();
+  }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    const float4 g0 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 g1 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-    gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
-    gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+    if (!G_SMEM) {
+      const int v = lane + i * 32;
+      const float4 g0 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 g1 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
+      gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
   }
+  auto gamma_of = [&](int i, float (&g)[8]) {
+    if (G_SMEM) {
+      const float4 a = *reinterpret_cast<const float4*>(gs + (lane + i * 32) * 8);
+      const float4 b = *reinterpret_cast<const float4*>(gs + (lane + i * 32) * 8 + 4);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = gm[G_SMEM ? 0 : i][j];
+    }
+  };
   for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + static_cast<long long>(row) * lddy);
@@ -278,13 +299,14 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      float fx[8], fd[8];
+      float fx[8], fd[8], gv[8];
       unpack8(rx[i], fx);
       unpack8(rd[i], fd);
+      gamma_of(i, gv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (fx[j] - mu) * rs;
-        const float g = fd[j] * gm[i][j];
+        const float g = fd[j] * gv[j];
         s1 += g;
         s2 = fmaf(g, xh, s2);
         dg[i][j] = fmaf(fd[j], xh, dg[i][j]);
@@ -298,18 +320,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float fx[8], fd[8], fr[8], o[8];
+        float fx[8], fd[8], fr[8], o[8], gv[8];
         unpack8(rx[i], fx);
         unpack8(rd[i], fd);
         unpack8(rr[i], fr);
+        gamma_of(i, gv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gm[i][j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gv[j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
         dxr[v] = pack8(o);
       }
     }
   }
   // block reduction of the column sums, then one atomicAdd per column and block
-  const int DP = MAXV * 256;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
 #pragma unroll
@@ -536,7 +558,7 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   if ((D % 8) || (ldx % 8) || (ldy % 8)) return set_error(OVK_ERR_ALIGN, "layernorm: D, ldx, ldy must be multiples of 8");
   if (D > 2048) return set_error(OVK_ERR_SHAPE, "layernorm: D=%d > 2048 not supported", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int rpb = 8 * (D > 1024 ? 1 : 2);  // 8 warps x rows per warp (layernorm_fwd_kernel::RPW)
+  const int rpb = 8 * (D > 1536 ? 1 : 2);  // 8 warps x rows per warp (layernorm_fwd_kernel::RPW)
   const int need = (rows + rpb - 1) / rpb;
   const int cap = 4 * num_sms();           // persistent: CTAs walk the rows with a grid stride
   const int grid = need < cap ? need : cap;
@@ -545,6 +567,8 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   if (D <= 256) layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else if (D <= 512) layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else if (D <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  else if (D <= 1280) layernorm_fwd_kernel<5><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);   // H/14
+  else if (D <= 1536) layernorm_fwd_kernel<6><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else layernorm_fwd_kernel<8><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   return check_launch("layernorm_fwd_kernel");
 }
@@ -569,14 +593,14 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
   auto xp = reinterpret_cast<const __nv_bfloat16*>(x);
   auto dxp = reinterpret_cast<__nv_bfloat16*>(dx);
   auto drp = reinterpret_cast<const __nv_bfloat16*>(dres);
-  if (dgamma != nullptr && dbeta != nullptr && D <= 1024) {   // one pass: dx and the parameter gradients together
+  if (dgamma != nullptr && dbeta != nullptr && D <= 1536) {   // one pass: dx and the parameter gradients together
     const int need = (rows + 7) / 8;
     const int cap = (D <= 512 ? 2 : 1) * num_sms();   // D > 512: 213 registers per thread, one CTA per SM
     const int grid = need < cap ? need : cap;
     int rc;
 #define OVK_LNB_FUSED(MV)                                                                                                     \
     {                                                                                                                         \
-      const size_t sm = 8 * 2 * (MV) * 256 * sizeof(float);                                                                   \
+      const size_t sm = (8 * 2 + ((MV) > 4 ? 1 : 0)) * (MV) * 256 * sizeof(float);                                            \
       static PerDeviceOnce attr_##MV;                                                                                         \
       if (attr_##MV.need()) {                                                                                                 \
         cudaFuncSetAttribute(layernorm_bwd_fused_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)); \
@@ -587,7 +611,9 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
     }
     if (D <= 256) OVK_LNB_FUSED(1)
     else if (D <= 512) OVK_LNB_FUSED(2)
-    else OVK_LNB_FUSED(4)
+    else if (D <= 1024) OVK_LNB_FUSED(4)
+    else if (D <= 1280) OVK_LNB_FUSED(5)   // H/14: gamma in shared memory (see the kernel)
+    else OVK_LNB_FUSED(6)
 #undef OVK_LNB_FUSED
     rc = check_launch("layernorm_bwd_fused_kernel");
     return rc;
@@ -608,6 +634,7 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
   if (D <= 256) layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 512) layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  else if (D <= 1536) layernorm_bwd_dx_kernel<6><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   return check_launch("layernorm_bwd_dx_kernel");
 }

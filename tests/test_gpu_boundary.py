@@ -187,3 +187,30 @@ def test_tensor_on_another_device_is_rejected():
         torch.cuda.synchronize()
     assert torch.isfinite(y.float()).all()
     assert (z.float() - a.float() @ w.float().t()).abs().max().item() <= 0.5
+
+
+def test_cuda_graph_replay_matches_eager_bit_for_bit():
+    """Small-batch latency path (the ov-* scripts run batch 1-8): encode_image / encode_text captured once into a CUDA graph
+    and replayed — the same libovk kernels, so the results are bitwise those of the eager call, for new inputs too."""
+    from oracle import synth
+    cfg_name = "Ti16-160"
+    cfg = synth.CONFIGS[cfg_name]
+    m = ovb.CLIP(embed_dim=cfg["embed_dim"], vision_cfg=dict(cfg["vision"]), text_cfg=dict(cfg["text"]))
+    m.load_state_dict(synth.make_state_dict(cfg_name, 0), strict=True)
+    m = m.cuda().eval()
+    a = synth.make_images(cfg_name, 2, 0).cuda()
+    b = synth.make_images(cfg_name, 2, 1).cuda()
+    g = ovb.graphed_encode_image(m, a, normalize=True)
+    with torch.no_grad():
+        for x in (a, b, a):
+            got = g(x).clone()
+            ref = m.encode_image(x, normalize=True)
+            assert torch.equal(got, ref)
+    t = synth.make_text(cfg_name, 2, 0).cuda()
+    gt = ovb.graphed_encode_text(m, t, normalize=True)
+    with torch.no_grad():
+        assert torch.equal(gt(t).clone(), m.encode_text(t, normalize=True))
+    with torch.no_grad():   # a changed weight invalidates the captured packed copies: loud, not stale
+        m.visual.proj.mul_(1.0)
+    with pytest.raises(OvkError):
+        g(a)

@@ -91,7 +91,8 @@ def test_gemm_linearity_at_full_size(ops):
     assert_close(c3, c1.float() * 2, 1e-2, "scaling linearity")
 
 
-@pytest.mark.parametrize("rows,D", [(808, 192), (1000, 768), (4096, 1024), (777, 1280), (64, 1152), (1, 8), (33, 2048)])
+@pytest.mark.parametrize("rows,D", [(808, 192), (1000, 768), (4096, 1024), (777, 1280), (64, 1152), (1, 8), (33, 2048), (999, 1536),
+                                    (5001, 1280)])
 def test_layernorm_fwd(ops, rows, D):
     x = (rnd(rows, D, seed=0) * 2 + 0.5).bfloat16()
     g, b = rnd(D, seed=1), rnd(D, seed=2)
@@ -103,7 +104,8 @@ def test_layernorm_fwd(ops, rows, D):
     assert_close(rstd, torch.rsqrt(var + 1e-6), 1e-3, "layernorm rstd")
 
 
-@pytest.mark.parametrize("rows,D", [(808, 192), (3000, 768), (4096, 1024), (500, 1280)])
+@pytest.mark.parametrize("rows,D", [(808, 192), (3000, 768), (4096, 1024), (500, 1280), (5000, 1280), (700, 1152), (900, 1536),
+                                    (300, 2048)])
 def test_layernorm_bwd(ops, rows, D):
     x = (rnd(rows, D, seed=0) * 2 + 0.5).bfloat16()
     dy = rnd(rows, D, seed=5).bfloat16()
