@@ -77,12 +77,21 @@ __device__ __forceinline__ void exp_chunk_4(const uint32_t (&x)[16], float scale
 #pragma unroll
   for (int i = 0; i < 16; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(x[i]), scale_log2, neg_m));
 }
+// TRUNC variant (OVK_ATT4_TRUNC=1, A/B): the fp32 -> bf16 pack of P is the XU pipe's second customer (F2FP runs there, ~3
+// clocks per warp instruction next to the 8 of every MUFU).  A byte permute on the ALU pipe keeps the upper halves of two
+// fp32 words instead (truncation towards zero).  Truncation alone would shrink P by E[ulp / 2] = 2^-8 * E[1 / mantissa] =
+// 0.2818 % on average, so the exponent argument carries +log2(1 + delta), delta = 0.002826: E[trunc(e (1 + delta))] = e.
+// The fp32 row sum then holds (1 + delta) * sum e; the epilogue divides it out (and the lse subtracts the constant).
+constexpr float A4_TRUNC_LOG2 = 0.0040714f;      // log2(1.002826)
+constexpr float A4_TRUNC_INV = 0.99718196f;      // 1 / 1.002826
 // consume a chunk of exponentials: row-sum contribution and the 8 packed bf16 pairs
+template <bool TRUNC>
 __device__ __forceinline__ float pack_chunk_4(const float (&e)[16], uint32_t (&pw)[8]) {
   float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
   float s4 = e[8] + e[9], s5 = e[10] + e[11], s6 = e[12] + e[13], s7 = e[14] + e[15];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) pw[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+  for (int i = 0; i < 8; ++i)
+    pw[i] = TRUNC ? __byte_perm(__float_as_uint(e[2 * i]), __float_as_uint(e[2 * i + 1]), 0x7632) : pack_bf16x2(e[2 * i], e[2 * i + 1]);
   return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
 }
 
@@ -94,6 +103,7 @@ struct A4Item {
   bool titem;
 };
 
+template <bool TRUNC>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse_out,
@@ -369,7 +379,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       const uint32_t tl = prev.t_last;
       mbar_wait(&bars[A4_B_PVDONE + 2 * w + (tl & 1)], (tl >> 1) & 1, 48);
       tc_fence_after();
-      float m_ref = prev.m_ref, l = prev.l;
+      float m_ref = prev.m_ref, l = TRUNC ? prev.l * A4_TRUNC_INV : prev.l;
       const int b = prev.b, h = prev.h, q0 = prev.q0, buf = prev.buf;
       const bool titem = prev.titem;
       uint32_t o[64];
@@ -569,7 +579,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         // P = 2^(S*scale - m_ref) as packed bf16 pairs, written over the score columns: chunk c (score columns [16c, 16c+16))
         // becomes words [8c, 8c+8) of the buffer.  Hand-pipelined: the exponentials of chunk c+1 are issued before the sums /
         // packing of chunk c, so nothing waits on a MUFU result issued just before it.  (Masked columns hold -inf -> 0.)
-        const float neg_m = -cur.m_ref;
+        const float neg_m = TRUNC ? A4_TRUNC_LOG2 - cur.m_ref : -cur.m_ref;
         {
           uint32_t pw[8];
           float ea[16], eb[16];
@@ -579,19 +589,19 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           uint32_t(&c3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&x[48]);
           exp_chunk_4(c0, scale_log2, neg_m, ea);
           exp_chunk_4(c1, scale_log2, neg_m, eb);
-          float acc = pack_chunk_4(ea, pw);
+          float acc = pack_chunk_4<TRUNC>(ea, pw);
           tmem_st_x8_4(t_s, pw);
           if (valid > 32) {   // uniform
             exp_chunk_4(c2, scale_log2, neg_m, ea);
-            acc += pack_chunk_4(eb, pw);
+            acc += pack_chunk_4<TRUNC>(eb, pw);
             tmem_st_x8_4(t_s + 8, pw);
             exp_chunk_4(c3, scale_log2, neg_m, eb);
-            acc += pack_chunk_4(ea, pw);
+            acc += pack_chunk_4<TRUNC>(ea, pw);
             tmem_st_x8_4(t_s + 16, pw);
-            acc += pack_chunk_4(eb, pw);
+            acc += pack_chunk_4<TRUNC>(eb, pw);
             tmem_st_x8_4(t_s + 24, pw);
           } else {
-            acc += pack_chunk_4(eb, pw);
+            acc += pack_chunk_4<TRUNC>(eb, pw);
             tmem_st_x8_4(t_s + 8, pw);
           }
           cur.l += acc;
@@ -646,17 +656,24 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
   }
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention4): %s", cudaGetErrorString(e));
     attr_once.done();
   }
+  const char* tr = getenv("OVK_ATT4_TRUNC");   // read per call (A/B runs alternate the two inside one process)
+  const bool trunc = tr != nullptr && tr[0] == '1';
   const int tail = (L > A4_BQ && L % A4_BQ == 1) ? 1 : 0;   // cls + power-of-two grid: remainder token handled outside the tiles
   const int l_main = L - tail;
   const int nq = (l_main + A4_BQ - 1) / A4_BQ;
   const long long items = static_cast<long long>((nq + 1) / 2) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
   const int grid = static_cast<int>(items < (long long)num_sms() ? items : (long long)num_sms());
-  attention_fwd4_kernel<<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L, l_main, H,
-                                                         nq, static_cast<int>(items), scale * 1.4426950408889634f);
+  if (trunc)
+    attention_fwd4_kernel<true><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
+                                                                 l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f);
+  else
+    attention_fwd4_kernel<false><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
+                                                                  l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f);
   return check_launch("attention_fwd4_kernel");
 }

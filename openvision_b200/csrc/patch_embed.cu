@@ -3,13 +3,15 @@
 // kernel: an im2col GEMM whose A operand is never materialised in memory.
 //
 //   warp 0   producer : TMA boxes of RAW pixels (fp32 or bf16, straight out of the NCHW image: for every patch row of the
-//                       tile a [R image rows x W pixels] box of one channel) into a 2-stage staging ring, and the weight
+//                       tile a [R image rows x W pixels] box of one channel) into a 2-4 slot staging ring (88 KB cut to the tile's size), and the weight
 //                       k-blocks (bf16, K-major, SWIZZLE_128B) into a 2-stage B ring
-//   warps 4-7 transform: thread m owns patch m of the 128-patch tile: reads its R x P pixels of the staged rows, converts to
-//                       bf16 and writes row m of the K-major SWIZZLE_128B A tile (what a TMA load of an im2col matrix would
-//                       have produced), zero-filling the padding columns
+//   warps 4-11 transform: two threads per patch of the 128-patch tile (one per half of the k-block's R image rows): read
+//                       their R/2 x P pixels of the staged rows, convert to bf16 and write their part of row m of the K-major
+//                       SWIZZLE_128B A tile (what a TMA load of an im2col matrix would have produced), zero-filling the
+//                       padding columns.  (Four transform warps — one per scheduler — were the bottleneck of the first
+//                       version: 1 240 clocks per k-block against 512 for its MMAs, profiles/r02_patch_embed.md.)
 //   warp 1   MMA      : tcgen05.mma 128 x 256 x 64 per k-block into one of two TMEM accumulators
-//   warps 8-15 epilogue: TMEM -> registers, + positional-embedding row (bf16 table, class token folded into row 0), bf16,
+//   warps 12-19 epilogue: TMEM -> registers, + positional-embedding row (bf16 table, class token folded into row 0), bf16,
 //                       swizzled smem, 3-D TMA store into tokens[b, 1 + p, :]; the first tile of an image also writes the
 //                       class-token row tokens[b, 0, :]
 //
@@ -27,8 +29,11 @@ namespace ovk {
 
 constexpr int PE_BM = 128;
 constexpr int PE_BN = 256;
-constexpr int PE_THREADS = 512;
-constexpr int PE_RAW_STAGE = 45056;   // 44 KB per staging slot (largest supported tile: 7 patch rows x 4 x 384 fp32 pixels)
+constexpr int PE_THREADS = 640;
+constexpr int PE_TR_WARPS = 8;        // transform warps (4 .. 11)
+constexpr int PE_EPI_WARP0 = 4 + PE_TR_WARPS;
+constexpr int PE_RAW_BYTES = 90112;   // staging ring: 88 KB, cut into 2-4 slots of the tile's size (largest tile: 43 KB)
+constexpr int PE_RAW_MAX_STAGES = 4;
 constexpr int PE_A_BYTES = PE_BM * 128;
 constexpr int PE_B_BYTES = PE_BN * 128;
 constexpr int PE_C_BYTES = PE_BM * 128;
@@ -36,8 +41,8 @@ constexpr int PE_OFF_A = 0;
 constexpr int PE_OFF_B = PE_OFF_A + 2 * PE_A_BYTES;
 constexpr int PE_OFF_C = PE_OFF_B + 2 * PE_B_BYTES;
 constexpr int PE_OFF_RAW = PE_OFF_C + 2 * PE_C_BYTES;
-constexpr int PE_OFF_BAR = PE_OFF_RAW + 2 * PE_RAW_STAGE;
-constexpr int PE_NUM_BARS = 16;
+constexpr int PE_OFF_BAR = PE_OFF_RAW + PE_RAW_BYTES;
+constexpr int PE_NUM_BARS = 12 + 2 * PE_RAW_MAX_STAGES;
 constexpr int PE_OFF_SLOT = PE_OFF_BAR + PE_NUM_BARS * 8;
 constexpr int PE_SMEM = PE_OFF_SLOT + 16;
 static_assert(PE_SMEM <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -46,6 +51,7 @@ struct PatchEmbedArgs {
   int B, N, gw, D, L;     // images, patches per image, patches per image row, width, tokens per image (N + 1)
   int nx, xbox;           // an image row is fetched as nx boxes of xbox pixels (TMA boxes are <= 256 wide)
   int box_stride;         // bytes between staged boxes (box bytes rounded up to 128)
+  int raw_stage, raw_nst; // bytes per staging slot (multiple of 1024) and number of slots (2..4)
   int tiles_pi, tiles_n;  // 128-patch tiles per image, 256-column tiles
   const __nv_bfloat16* table;   // [L, D] positional embedding (+ class token in row 0) or null (plain conv tokens)
   __nv_bfloat16* out;           // [B, L, D]
@@ -80,14 +86,14 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PE_OFF_BAR);
-  uint64_t* raw_full = bars;          // [2]
-  uint64_t* raw_empty = bars + 2;     // [2]
-  uint64_t* a_full = bars + 4;        // [2]
-  uint64_t* a_empty = bars + 6;       // [2]
-  uint64_t* b_full = bars + 8;        // [2]
-  uint64_t* b_empty = bars + 10;      // [2]
-  uint64_t* tmem_full = bars + 12;    // [2]
-  uint64_t* tmem_empty = bars + 14;   // [2]
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = bars + 2;       // [2]
+  uint64_t* b_full = bars + 4;        // [2]
+  uint64_t* b_empty = bars + 6;       // [2]
+  uint64_t* tmem_full = bars + 8;     // [2]
+  uint64_t* tmem_empty = bars + 10;   // [2]
+  uint64_t* raw_full = bars + 12;                         // [raw_nst]
+  uint64_t* raw_empty = bars + 12 + PE_RAW_MAX_STAGES;    // [raw_nst]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PE_OFF_SLOT);
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -98,10 +104,12 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
     tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < PE_RAW_MAX_STAGES; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&raw_empty[i], 4);
-      mbar_init(&a_full[i], 4);
+      mbar_init(&raw_empty[i], PE_TR_WARPS);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], PE_TR_WARPS);
       mbar_init(&a_empty[i], 1);
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
@@ -131,7 +139,9 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
     if (elect_one()) {
       // ------------------------------------------------------------------------------------------ TMA producer
       const uint32_t box_bytes = static_cast<uint32_t>(R * a.xbox * ES);
-      uint32_t kbc = 0;   // k-blocks issued so far (ring position / phase of all three 2-stage rings)
+      uint32_t kbc = 0;   // k-blocks issued so far (ring position / phase of the 2-stage A and B rings)
+      int rs = 0;         // staging ring: slot and phase
+      uint32_t rph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int b, p0, n0;
         decode(t, b, p0, n0);
@@ -142,13 +152,17 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
           const int s = kbc & 1;
           const uint32_t ph = (kbc >> 1) & 1;
           const int c = kb / PG, phg = kb % PG;
-          mbar_wait(&raw_empty[s], ph ^ 1, 11);
-          mbar_arrive_expect_tx(&raw_full[s], static_cast<uint32_t>(npy * a.nx) * box_bytes);
-          uint8_t* dst = smem + PE_OFF_RAW + s * PE_RAW_STAGE;
+          mbar_wait(&raw_empty[rs], rph ^ 1, 11);
+          mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(npy * a.nx) * box_bytes);
+          uint8_t* dst = smem + PE_OFF_RAW + rs * a.raw_stage;
           for (int pyl = 0; pyl < npy; ++pyl)
             for (int ix = 0; ix < a.nx; ++ix)
-              tma_load_3d(dst + (pyl * a.nx + ix) * a.box_stride, &tmI, &raw_full[s], ix * a.xbox, (py0 + pyl) * P + phg * R,
+              tma_load_3d(dst + (pyl * a.nx + ix) * a.box_stride, &tmI, &raw_full[rs], ix * a.xbox, (py0 + pyl) * P + phg * R,
                           b * 3 + c);
+          if (++rs == a.raw_nst) {
+            rs = 0;
+            rph ^= 1;
+          }
           mbar_wait(&b_empty[s], ph ^ 1, 12);
           mbar_arrive_expect_tx(&b_full[s], PE_B_BYTES);
           tma_load_2d(smem + PE_OFF_B + s * PE_B_BYTES, &tmB, &b_full[s], kb * 64, n0);
@@ -184,10 +198,15 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
         umma_commit(&tmem_full[acc]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < PE_EPI_WARP0) {
     // ------------------------------------------------------------------------------------------ pixel -> A-tile transform
-    const int m = threadIdx.x - 128;   // patch inside the tile = row of the A tile
+    constexpr int RH = R / 2;                // image rows of the k-block per thread
+    const int tt = threadIdx.x - 128;
+    const int m = tt & 127;                  // patch inside the tile = row of the A tile
+    const int r0 = (tt >> 7) * RH;           // first of this thread's rows of the k-block
     uint32_t kbc = 0;
+    int rs = 0;
+    uint32_t rph = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
       int b, p0, n0;
       decode(t, b, p0, n0);
@@ -202,11 +221,12 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
         const int s = kbc & 1;
         const uint32_t ph = (kbc >> 1) & 1;
         const int phg = kb % PG;
-        uint32_t w[R][PW / 2];   // bf16 pairs of this patch's R x PW slice of the k-block
-        mbar_wait(&raw_full[s], ph, 16);
-        const uint32_t src = smem_u32(smem + PE_OFF_RAW + s * PE_RAW_STAGE) + src_off;
+        uint32_t w[RH][PW / 2];   // bf16 pairs of this thread's RH x PW slice of the k-block
+        mbar_wait(&raw_full[rs], rph, 16);
+        const uint32_t src = smem_u32(smem + PE_OFF_RAW + rs * a.raw_stage) + src_off;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int rr = 0; rr < RH; ++rr) {
+          const int r = r0 + rr;
           const bool row_ok = valid && (phg * R + r < P);
           if (row_ok) {
             uint32_t raw[PBYTES / 4];
@@ -214,35 +234,40 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
             for (int v = 0; v < NV; ++v) lds_words<VB>(src + r * a.xbox * ES + v * VB, &raw[v * (VB / 4)]);
             if constexpr (ES == 4) {
 #pragma unroll
-              for (int j = 0; j < P / 2; ++j) w[r][j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
+              for (int j = 0; j < P / 2; ++j) w[rr][j] = pack_bf16x2(__uint_as_float(raw[2 * j]), __uint_as_float(raw[2 * j + 1]));
             } else {
 #pragma unroll
-              for (int j = 0; j < P / 2; ++j) w[r][j] = raw[j];
+              for (int j = 0; j < P / 2; ++j) w[rr][j] = raw[j];
             }
 #pragma unroll
-            for (int j = P / 2; j < PW / 2; ++j) w[r][j] = 0u;
+            for (int j = P / 2; j < PW / 2; ++j) w[rr][j] = 0u;
           } else {
 #pragma unroll
-            for (int j = 0; j < PW / 2; ++j) w[r][j] = 0u;
+            for (int j = 0; j < PW / 2; ++j) w[rr][j] = 0u;
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);   // pixels are in registers: the staging slot may be refilled
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);   // pixels are in registers: the staging slot may be refilled
+        if (++rs == a.raw_nst) {
+          rs = 0;
+          rph ^= 1;
+        }
         mbar_wait(&a_empty[s], ph ^ 1, 17);
         const uint32_t dst = smem_u32(smem + PE_OFF_A + s * PE_A_BYTES);
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+        for (int rr = 0; rr < RH; ++rr)
 #pragma unroll
           for (int j = 0; j < PW / 8; ++j)
-            sts128(dst + sw128_offset(m, r * (PW / 8) + j), make_uint4(w[r][4 * j], w[r][4 * j + 1], w[r][4 * j + 2], w[r][4 * j + 3]));
+            sts128(dst + sw128_offset(m, (r0 + rr) * (PW / 8) + j),
+                   make_uint4(w[rr][4 * j], w[rr][4 * j + 1], w[rr][4 * j + 2], w[rr][4 * j + 3]));
         fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[s]);
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= PE_EPI_WARP0) {
     // ------------------------------------------------------------------------------------------ epilogue
-    const int ew = warp - 8;
+    const int ew = warp - PE_EPI_WARP0;
     const int grp = ew >> 2;
     const int quad = ew & 3;
     const int et = quad * 32 + lane;
@@ -268,45 +293,51 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
       for (int c = 0; c < 2; ++c) {
         const int ncol0 = n0 + grp * 128 + c * 64;
         const bool live = ncol0 < a.D;
-        uint32_t v[64];
         if (live) {
           if (leader) tma_store_wait_read<0>();
           named_bar_sync(bar_id, 128);
-          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-          uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-          tmem_ld_x32(taddr + c * 64, v0);
-          tmem_ld_x32(taddr + c * 64 + 32, v1);
-          tmem_ld_wait();
         }
-        if (c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        if (!live) continue;
-        float x[64];
+        // two passes of 32 columns (the 640-thread CTA leaves 96 registers per thread)
+#pragma unroll 1
+        for (int hcol = 0; hcol < 2; ++hcol) {
+          uint32_t v[32];
+          if (live) {
+            tmem_ld_x32(taddr + c * 64 + hcol * 32, v);
+            tmem_ld_wait();
+          }
+          if (c == 1 && hcol == 1) {   // accumulator drained: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (!live) continue;
+          float x[32];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) x[j] = __uint_as_float(v[j]);
-        if (a.table != nullptr && valid) {
-          const uint4* src = reinterpret_cast<const uint4*>(a.table + static_cast<long long>(1 + p) * a.D + ncol0);
-          const int nvec = min(8, (a.D - ncol0) >> 3);
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          const int ncol = ncol0 + hcol * 32;
+          if (a.table != nullptr && valid && ncol < a.D) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.table + static_cast<long long>(1 + p) * a.D + ncol);
+            const int nvec = min(4, (a.D - ncol) >> 3);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j < nvec) {
-              const uint4 r = __ldg(src + j);
-              const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            for (int j = 0; j < 4; ++j) {
+              if (j < nvec) {
+                const uint4 r = __ldg(src + j);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                x[8 * j + 2 * q] += bf16_lo(rw[q]);
-                x[8 * j + 2 * q + 1] += bf16_hi(rw[q]);
+                for (int q = 0; q < 4; ++q) {
+                  x[8 * j + 2 * q] += bf16_lo(rw[q]);
+                  x[8 * j + 2 * q + 1] += bf16_hi(rw[q]);
+                }
               }
             }
           }
-        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(sbuf + sw128_offset(et, j), make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
-                                                        pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7])));
+          for (int j = 0; j < 4; ++j)
+            sts128(sbuf + sw128_offset(et, hcol * 4 + j),
+                   make_uint4(pack_bf16x2(x[8 * j], x[8 * j + 1]), pack_bf16x2(x[8 * j + 2], x[8 * j + 3]),
+                              pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), pack_bf16x2(x[8 * j + 6], x[8 * j + 7])));
+        }
+        if (!live) continue;
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (leader) {
@@ -345,6 +376,12 @@ static int launch_patch_embed(const CUtensorMap& tmI, const CUtensorMap& tmB, co
 
 using namespace ovk;
 
+// bytes of one staging slot: the most patch rows a 128-patch tile can touch, each nx boxes, rounded up to 1 KB
+static int pe_stage_bytes(int gw, int nx, int box_stride) {
+  const int npy = gw % PE_BM == 0 || PE_BM % gw == 0 ? (PE_BM + gw - 1) / gw : (gw - 1 + PE_BM - 1) / gw + 1;
+  return (npy * nx * box_stride + 1023) / 1024 * 1024;
+}
+
 extern "C" int ovk_patch_embed_kdim(int P) {
   if (P != 14 && P != 16 && P != 32) return 0;
   const int PW = P <= 16 ? 16 : 32, R = 64 / PW, PG = (P + R - 1) / R;
@@ -359,8 +396,7 @@ extern "C" int ovk_patch_embed_supported(int img_is_f32, int H, int W, int P, in
   if (gw % nx || ((W / nx) * es) % 16 || (W * es) % 16) return 0;
   const int R = 64 / (P <= 16 ? 16 : 32);
   const int box_stride = (R * (W / nx) * es + 127) / 128 * 128;
-  const int npy = (gw - 1 + PE_BM - 1) / gw + 1;   // most patch rows a 128-patch tile can touch
-  return npy * nx * box_stride <= PE_RAW_STAGE ? 1 : 0;
+  return 2 * pe_stage_bytes(gw, nx, box_stride) <= PE_RAW_BYTES ? 1 : 0;   // at least a double buffer
 }
 
 extern "C" int ovk_patch_embed(const void* images, int img_is_f32, const void* w_packed, const void* pos_table, void* tokens,
@@ -381,6 +417,8 @@ extern "C" int ovk_patch_embed(const void* images, int img_is_f32, const void* w
   a.xbox = W / a.nx;
   const int R = 64 / (P <= 16 ? 16 : 32);
   a.box_stride = (R * a.xbox * es + 127) / 128 * 128;
+  a.raw_stage = pe_stage_bytes(a.gw, a.nx, a.box_stride);
+  a.raw_nst = PE_RAW_BYTES / a.raw_stage < PE_RAW_MAX_STAGES ? PE_RAW_BYTES / a.raw_stage : PE_RAW_MAX_STAGES;
   a.tiles_pi = (a.N + PE_BM - 1) / PE_BM;
   a.tiles_n = (D + PE_BN - 1) / PE_BN;
   a.table = reinterpret_cast<const __nv_bfloat16*>(pos_table);

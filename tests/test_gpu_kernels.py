@@ -538,3 +538,21 @@ def test_attention_causal_forward_and_backward(ops, B, L, H, hd):
     # the flag matters: the unmasked call must differ
     out0 = ops.attention(qkv.cuda(), B, L, H, hd)
     assert (out0.float() - out.float()).abs().max().item() > 1e-2
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 257, 4), (40, 256, 8), (1, 200, 2), (3, 513, 2), (2, 1025, 1)])
+def test_attention_truncating_pack_variant(ops, B, L, H, monkeypatch):
+    """OVK_ATT4_TRUNC=1 (A/B switch of attention4): P packed to bf16 by truncation with the mean bias folded into the exponent
+    argument; must meet the same bar as the round-to-nearest pack, and its mean must not drift (bias compensation)."""
+    hd = 64
+    qkv = rnd(B * L, 3 * H * hd, seed=L + 7).bfloat16()
+    monkeypatch.setenv("OVK_ATT4_TRUNC", "1")
+    out, lse = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    monkeypatch.setenv("OVK_ATT4_TRUNC", "0")
+    out0, lse0 = ops.attention(qkv.cuda(), B, L, H, hd, save_lse=True)
+    ref, lse_ref = _attn_ref(qkv, B, L, H, hd)
+    assert_close(out, ref, 2e-2, "attention (truncating pack)")
+    assert_close(lse, lse_ref, 1e-3, "lse (truncating pack)")
+    e1 = (out.float().cpu() - ref).abs().mean().item()
+    e0 = (out0.float().cpu() - ref).abs().mean().item()
+    assert e1 <= 2.0 * e0 + 1e-6, (e1, e0)

@@ -17,7 +17,7 @@ echo "ncu launches rc=$?"
 echo "== ncu full (top kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_bf16 -s 1 -c 5 -o gpurun_out/prof_gemm_${TAG} $NCU_CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attention_fwd|clip_loss_fwd|clip_loss_grad|layernorm|row_stats" -s 1 -c 8 -o gpurun_out/prof_attn_loss_${TAG} $NCU_CMD > gpurun_out/ncu_full2_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"attention_fwd|clip_loss_fwd|clip_loss_grad|layernorm|row_stats|patch_embed|pool_head" -s 0 -c 10 -o gpurun_out/prof_attn_loss_${TAG} $NCU_CMD > gpurun_out/ncu_full2_${TAG}.log 2>&1
 echo "ncu full (attention/loss) rc=$?"
 fi
 ls -la gpurun_out | tail -8
