@@ -35,7 +35,10 @@ constexpr int A4_HD = 64;
 constexpr int A4_THREADS = 352;       // 8 softmax warps + producer + 2 MMA issuers
 constexpr int A4_TILE = 128 * 128;    // [128 rows x 64 bf16], SWIZZLE_128B
 constexpr int A4_HALF = 64 * 128;     // byte offset of rows 64.. inside a tile
-constexpr int A4_NS = 3;              // K / V ring depth (tiles)
+#ifndef OVK_A4_NS
+#define OVK_A4_NS 3
+#endif
+constexpr int A4_NS = OVK_A4_NS;      // K / V ring depth (tiles); 5 (all of shared memory) measured equal to 3
 constexpr int A4_OFF_Q = 0;                               // [2 item buffers][2 tiles]
 constexpr int A4_OFF_V = A4_OFF_Q + 4 * A4_TILE;          // V before K (the O_t^T MMA over-reads one tile past V)
 constexpr int A4_OFF_K = A4_OFF_V + A4_NS * A4_TILE;
@@ -45,15 +48,16 @@ constexpr int A4_OFF_RED = A4_OFF_PT + 384;               // remainder-row scrat
 constexpr int A4_OFF_BAR = A4_OFF_RED + 64;
 constexpr int A4_B_QFULL = 0;     // [2]
 constexpr int A4_B_QFREE = 2;     // [2]
-constexpr int A4_B_KFULL = 4;     // [NS]
-constexpr int A4_B_KEMPTY = 7;    // [NS]  two arrivals
-constexpr int A4_B_VFULL = 10;    // [NS]
-constexpr int A4_B_VEMPTY = 13;   // [NS]  two arrivals
-constexpr int A4_B_SFULL = 16;    // [2 slots][2]
-constexpr int A4_B_PREADY = 20;   // [2 slots][2]
-constexpr int A4_B_PVDONE = 24;   // [2 slots][2]
-constexpr int A4_NUM_BARS = 28;
+constexpr int A4_B_KFULL = 4;                       // [NS]
+constexpr int A4_B_KEMPTY = A4_B_KFULL + A4_NS;     // [NS]  two arrivals
+constexpr int A4_B_VFULL = A4_B_KEMPTY + A4_NS;     // [NS]
+constexpr int A4_B_VEMPTY = A4_B_VFULL + A4_NS;     // [NS]  two arrivals
+constexpr int A4_B_SFULL = A4_B_VEMPTY + A4_NS;     // [2 slots][2]
+constexpr int A4_B_PREADY = A4_B_SFULL + 4;         // [2 slots][2]
+constexpr int A4_B_PVDONE = A4_B_PREADY + 4;        // [2 slots][2]
+constexpr int A4_NUM_BARS = A4_B_PVDONE + 4;
 constexpr int A4_SMEM = A4_OFF_BAR + A4_NUM_BARS * 8 + 16;
+static_assert(A4_SMEM <= 232448, "attention4: shared memory");
 constexpr uint32_t A4_T_S = 0, A4_T_O = 256, A4_T_SK = 384, A4_T_ST = 416, A4_T_OT = 432, A4_T_TT = 448;
 
 __device__ __forceinline__ void umma_bf16_ts4(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
@@ -103,7 +107,9 @@ struct A4Item {
   bool titem;
 };
 
-template <bool TRUNC>
+// DBG (only with -DOVK_ATT4_DEBUG_VARIANTS, tools/attn_knockout.py): knock-outs that make the RESULT WRONG but show what a
+// softmax step spends its time on: bit 0 no exponentials / packing, bit 1 no row maximum, bit 2 no P stores, bit 3 no score loads.
+template <bool TRUNC, int DBG = 0>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse_out,
@@ -281,8 +287,10 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           if (hb_s == 0) mbar_wait(&bars[A4_B_QFULL + buf], (cs.n >> 1) & 1, 43);
           if (half == 0) mbar_wait(&bars[A4_B_KFULL + ks], kph, 44);
           tc_fence_after();
+          if constexpr ((DBG & 32) == 0) {
 #pragma unroll
-          for (int k = 0; k < A4_HD / 16; ++k) umma_bf16_ss(d_tmem, a + 2 * k, bd + 2 * k, idesc, k != 0);
+            for (int k = 0; k < A4_HD / 16; ++k) umma_bf16_ss(d_tmem, a + 2 * k, bd + 2 * k, idesc, k != 0);
+          }
           if (tail && hb_s == 0) {   // this tile's rows against the remainder key
 #pragma unroll
             for (int k = 0; k < A4_HD / 16; ++k)
@@ -329,7 +337,8 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           if (half == 0) mbar_wait(&bars[A4_B_VFULL + vs], vph, 46);
           mbar_wait(&bars[A4_B_PREADY + 2 * w + e], (t_p >> 1) & 1, 45);   // P(t) is in TMEM (and the previous O has been read)
           tc_fence_after();
-          if (ksteps == 4) {
+          if constexpr ((DBG & 32) != 0) {
+          } else if (ksteps == 4) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_bf16_ts4(tO, a_tmem + 8 * kk, bd + kk * 128, idesc_pv, (hb_p | kk) != 0);
           } else {
@@ -375,13 +384,18 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     A4Item prev{};
 
     // ---- epilogue of `prev`: O / l -> bf16 -> smem -> TMA store (+ the remainder query row of the head)
+    // (Measured and dropped, tools/attn_ab.py against this version on the same box: handing the staging Q buffer back one
+    // step later instead of waiting for the store's read right here: +2..5 %; pulling O out of TMEM before the p_ready
+    // arrival and normalising / storing after it: +13 % (o[64] then lives across the arrival and spills at the 168-register
+    // cap); polling instead of suspending barrier waits: +9 %; a 5-deep K / V ring: +-0.)
     auto epilogue = [&]() {
       const uint32_t tl = prev.t_last;
       mbar_wait(&bars[A4_B_PVDONE + 2 * w + (tl & 1)], (tl >> 1) & 1, 48);
       tc_fence_after();
-      float m_ref = prev.m_ref, l = TRUNC ? prev.l * A4_TRUNC_INV : prev.l;
-      const int b = prev.b, h = prev.h, q0 = prev.q0, buf = prev.buf;
-      const bool titem = prev.titem;
+      if constexpr ((DBG & 16) != 0) {   // barrier protocol only
+        if (r == 0) mbar_arrive(&bars[A4_B_QFREE + prev.buf]);
+        return;
+      }
       uint32_t o[64];
       {
         uint32_t(&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
@@ -390,8 +404,11 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         tmem_ld_x32(t_o + 32, o1);
       }
       uint32_t u_ot = 0;
-      if (titem && quad < 2) tmem_ld_x1(tmem_base + t_lane + A4_T_OT, u_ot);
+      if (prev.titem && quad < 2) tmem_ld_x1(tmem_base + t_lane + A4_T_OT, u_ot);
       tmem_ld_wait();
+      float m_ref = prev.m_ref, l = TRUNC ? prev.l * A4_TRUNC_INV : prev.l;
+      const int b = prev.b, h = prev.h, q0 = prev.q0, buf = prev.buf;
+      const bool titem = prev.titem;
       const uint32_t rows = smem_u32(smem + A4_OFF_ROWS + buf * 384);
       if (tail) {   // fold the remainder key in: one more online-softmax step, entirely in registers
         const float m_fin = fmaxf(m_ref, prev.s_tail);
@@ -505,12 +522,22 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         {
           uint32_t(&x0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&x[0]);
           uint32_t(&x1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&x[32]);
-          tmem_ld_x32(t_s, x0);
-          if (valid > 32) tmem_ld_x32(t_s + 32, x1);
-          tmem_ld_wait();
+          if constexpr ((DBG & 8) == 0) {
+            tmem_ld_x32(t_s, x0);
+            if (valid > 32) tmem_ld_x32(t_s + 32, x1);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              x[i] = 0x3c000000u + lane + i;
+              asm volatile("" : "+r"(x[i]));
+            }
+          }
         }
         float mx = neg_inf;
-        if (valid == A4_HB) {
+        if constexpr ((DBG & 2) != 0) {
+          mx = __uint_as_float(x[0]);
+        } else if (valid == A4_HB) {
           float m4[4] = {neg_inf, neg_inf, neg_inf, neg_inf};
 #pragma unroll
           for (int i = 0; i < 32; ++i) m4[i & 3] = max3f_4(m4[i & 3], __uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1]));
@@ -587,24 +614,35 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           uint32_t(&c1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&x[16]);
           uint32_t(&c2)[16] = *reinterpret_cast<uint32_t(*)[16]>(&x[32]);
           uint32_t(&c3)[16] = *reinterpret_cast<uint32_t(*)[16]>(&x[48]);
+          if constexpr ((DBG & 1) != 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) pw[i] = x[16 * c + i] ^ x[16 * c + 8 + i];
+              if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s + 8 * c, pw);
+              else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
+            }
+            cur.l += neg_m;
+          } else {
           exp_chunk_4(c0, scale_log2, neg_m, ea);
           exp_chunk_4(c1, scale_log2, neg_m, eb);
           float acc = pack_chunk_4<TRUNC>(ea, pw);
-          tmem_st_x8_4(t_s, pw);
+          if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s, pw); else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
           if (valid > 32) {   // uniform
             exp_chunk_4(c2, scale_log2, neg_m, ea);
             acc += pack_chunk_4<TRUNC>(eb, pw);
-            tmem_st_x8_4(t_s + 8, pw);
+            if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s + 8, pw); else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
             exp_chunk_4(c3, scale_log2, neg_m, eb);
             acc += pack_chunk_4<TRUNC>(ea, pw);
-            tmem_st_x8_4(t_s + 16, pw);
+            if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s + 16, pw); else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
             acc += pack_chunk_4<TRUNC>(eb, pw);
-            tmem_st_x8_4(t_s + 24, pw);
+            if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s + 24, pw); else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
           } else {
             acc += pack_chunk_4<TRUNC>(eb, pw);
-            tmem_st_x8_4(t_s + 8, pw);
+            if constexpr ((DBG & 4) == 0) tmem_st_x8_4(t_s + 8, pw); else asm volatile("" ::"r"(pw[0]), "r"(pw[7]));
           }
           cur.l += acc;
+          }
         }
         tmem_st_wait();
         if (titem && half == 0) fence_proxy_async_smem();
@@ -669,6 +707,23 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
   const long long items = static_cast<long long>((nq + 1) / 2) * H * B;
   if (items > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention: too many work items");
   const int grid = static_cast<int>(items < (long long)num_sms() ? items : (long long)num_sms());
+#ifdef OVK_ATT4_DEBUG_VARIANTS
+  {
+    const char* dbg = getenv("OVK_ATT4_DBG");
+    const int d = dbg != nullptr ? atoi(dbg) : 0;
+#define OVK_A4_DBG_CASE(N)                                                                                                   \
+    if (d == N) {                                                                                                              \
+      cudaFuncSetAttribute(attention_fwd4_kernel<false, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);             \
+      attention_fwd4_kernel<false, N><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), \
+                                                                       L, l_main, H, nq, static_cast<int>(items),              \
+                                                                       scale * 1.4426950408889634f);                          \
+      return check_launch("attention_fwd4_kernel<dbg>");                                                                       \
+    }
+    OVK_A4_DBG_CASE(1) OVK_A4_DBG_CASE(2) OVK_A4_DBG_CASE(4) OVK_A4_DBG_CASE(8) OVK_A4_DBG_CASE(5) OVK_A4_DBG_CASE(7) OVK_A4_DBG_CASE(15)
+    OVK_A4_DBG_CASE(16) OVK_A4_DBG_CASE(31) OVK_A4_DBG_CASE(47) OVK_A4_DBG_CASE(63)
+#undef OVK_A4_DBG_CASE
+  }
+#endif
   if (trunc)
     attention_fwd4_kernel<true><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
                                                                  l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f);
