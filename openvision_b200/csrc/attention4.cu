@@ -108,7 +108,8 @@ struct A4Item {
 };
 
 // DBG (only with -DOVK_ATT4_DEBUG_VARIANTS, tools/attn_knockout.py): knock-outs that make the RESULT WRONG but show what a
-// softmax step spends its time on: bit 0 no exponentials / packing, bit 1 no row maximum, bit 2 no P stores, bit 3 no score loads.
+// softmax step spends its time on: bit 0 no exponentials / packing, bit 1 no row maximum, bit 2 no P stores, bit 3 no score loads,
+// bit 4 no epilogue work, bit 5 no S / P V MMAs, bit 6 no HBM traffic (every item reads and writes head 0 of image 0).
 template <bool TRUNC, int DBG = 0>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
@@ -160,7 +161,9 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       // ------------------------------------------------------------------ TMA producer
       int n = 0, g = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
-        const int pr = item % npair, h = (item / npair) % H, b = item / (npair * H);
+        const int pr = item % npair;
+        // DBG bit 6: every item loads head 0 of image 0 (L2 hits): the kernel without its HBM reads
+        const int h = (DBG & 64) ? 0 : (item / npair) % H, b = (DBG & 64) ? 0 : item / (npair * H);
         const int buf = n & 1;
         const bool has_b = 2 * pr + 1 < nq;
         const bool titem = tail && (2 * pr == nq - 1 || 2 * pr + 1 == nq - 1);
@@ -387,7 +390,11 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     // (Measured and dropped, tools/attn_ab.py against this version on the same box: handing the staging Q buffer back one
     // step later instead of waiting for the store's read right here: +2..5 %; pulling O out of TMEM before the p_ready
     // arrival and normalising / storing after it: +13 % (o[64] then lives across the arrival and spills at the 168-register
-    // cap); polling instead of suspending barrier waits: +9 %; a 5-deep K / V ring: +-0.)
+    // cap); polling instead of suspending barrier waits: +9 %; a 5-deep K / V ring: +-0; every thread storing its 128-byte
+    // output row straight from registers (no staging tile / proxy fence / group barrier / TMA store): +-0.  tools/attn_knockout.py
+    // shows why none of this moves the total: the exponentials run at the XU pipe's rate but nothing else overlaps them - the two
+    // tile slots execute the same step at the same time, so both warps of a scheduler are in their exp phase together and in
+    // their load / max / hand-off phase together.)
     auto epilogue = [&]() {
       const uint32_t tl = prev.t_last;
       mbar_wait(&bars[A4_B_PVDONE + 2 * w + (tl & 1)], (tl >> 1) & 1, 48);
@@ -491,8 +498,8 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         continue;
       }
       A4Item cur;
-      cur.h = (item / npair) % H;
-      cur.b = item / (npair * H);
+      cur.h = (DBG & 64) ? 0 : (item / npair) % H;     // (bit 6: stores go to one place as well)
+      cur.b = (DBG & 64) ? 0 : item / (npair * H);
       cur.buf = n & 1;
       cur.q0 = qt * A4_BQ;
       cur.titem = tail && qt == nq - 1;   // this group also carries the remainder query row
@@ -720,7 +727,7 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
       return check_launch("attention_fwd4_kernel<dbg>");                                                                       \
     }
     OVK_A4_DBG_CASE(1) OVK_A4_DBG_CASE(2) OVK_A4_DBG_CASE(4) OVK_A4_DBG_CASE(8) OVK_A4_DBG_CASE(5) OVK_A4_DBG_CASE(7) OVK_A4_DBG_CASE(15)
-    OVK_A4_DBG_CASE(16) OVK_A4_DBG_CASE(31) OVK_A4_DBG_CASE(47) OVK_A4_DBG_CASE(63)
+    OVK_A4_DBG_CASE(16) OVK_A4_DBG_CASE(31) OVK_A4_DBG_CASE(47) OVK_A4_DBG_CASE(63) OVK_A4_DBG_CASE(64) OVK_A4_DBG_CASE(79) OVK_A4_DBG_CASE(127)
 #undef OVK_A4_DBG_CASE
   }
 #endif
