@@ -882,6 +882,18 @@ def run_ours(args):
             if "clip_loss" in rg and world == 1 and rg["clip_loss"]["global_batch"] == args.loss_batch:
                 rg["clip_loss"]["reference_over_ours"] = rg["clip_loss"]["value"] / loss_line["value"]
             line["reference_gpu"] = rg
+        att = line["kernels"].get("attention")
+        if att and att.get("launches_per_step"):
+            # the attention core at this shape sits BELOW the machine's ridge point (4 L hd FLOP per (3 + 1) * hd * 2 bytes of
+            # q, k, v in and o out = L / 2 FLOP per byte): its binding roofline is HBM, reported next to the tensor one
+            vcfg = cfg["vision"]
+            heads, hd = vcfg["width"] // vcfg["head_width"], vcfg["head_width"]
+            ltok = (vcfg["image_size"] // vcfg["patch_size"]) ** 2 + 1
+            byts = batch * ltok * 4 * heads * hd * 2
+            gbs = byts * att["launches_per_step"] / att["ms_per_step"] / 1e6
+            att.update(hbm_bytes_per_launch=byts, achieved_gbs=gbs, frac_of_measured_hbm=gbs / peaks["hbm"],
+                       flop_per_byte=ltok / 2.0, ridge_flop_per_byte=peaks["tf_sustained"] * 1e3 / peaks["hbm"],
+                       bound="hbm" if ltok / 2.0 < peaks["tf_sustained"] * 1e3 / peaks["hbm"] else "tensor")
         if "attention_vs_sdpa" in extras:
             line["kernels"].setdefault("attention", {})["vs_sdpa"] = extras.pop("attention_vs_sdpa")
         if extras:

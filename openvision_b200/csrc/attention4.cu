@@ -3,7 +3,7 @@
 // (open_clip/transformer.py:225,239-252); online softmax as in src/models/bpt.py:105-124.
 //
 // attention3.cu (64-key half blocks, two score buffers per tile, hand-pipelined exponentials) with the hand-offs that its
-// profile still showed exposed (profiles/r02_attention3_stalls.md: 11 % of a softmax warp's time waiting for the first S of
+// profile still showed exposed (its stall profile: 11 % of a softmax warp's time waiting for the first S of
 // an item, 11 % for the last P V) taken off the critical path:
 //   * every tile slot is an independent pipeline with its OWN MMA-issuing warp (warps 9 and 10): the steps of a slot —
 //     (item, half block) pairs — are numbered t = 0, 1, 2, ... across items; S(t+2) is issued right behind P V(t) whether or

@@ -9,7 +9,7 @@
 //                       their R/2 x P pixels of the staged rows, convert to bf16 and write their part of row m of the K-major
 //                       SWIZZLE_128B A tile (what a TMA load of an im2col matrix would have produced), zero-filling the
 //                       padding columns.  (Four transform warps — one per scheduler — were the bottleneck of the first
-//                       version: 1 240 clocks per k-block against 512 for its MMAs, profiles/r02_patch_embed.md.)
+//                       version: 1 240 clocks per k-block against 512 for its MMAs, ncu source view of profiles/r02 run d.)
 //   warp 1   MMA      : tcgen05.mma 128 x 256 x 64 per k-block into one of two TMEM accumulators
 //   warps 12-19 epilogue: TMEM -> registers, + positional-embedding row (bf16 table, class token folded into row 0), bf16,
 //                       swizzled smem, 3-D TMA store into tokens[b, 1 + p, :]; the first tile of an image also writes the
