@@ -208,7 +208,11 @@ int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const 
 int ovk_attention_fwd_ex(const void* qkv, void* out, float* lse, int B, int L, int H, int hd, float scale, int flags,
                          void* stream);
 int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
-                         int B, int L, int H, int hd, float scale, int flags, void* stream);
+                         float* workspace, int B, int L, int H, int hd, float scale, int flags, void* stream);
+/* workspace: f32[ovk_attention_bwd_workspace_floats(B, L, H, flags)] or NULL.  With it, the remainder token of L = 128 k + 1
+ * (class token + power-of-two grid) is handled outside the 128-wide tiles (attention_bwd_tail_kernel + rank-1 terms in the
+ * tile kernels' epilogues) instead of as a third tile row / column; the function returns 0 when the shape has no such token. */
+long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int flags);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Pooling head, transformer.py:599-607,638-646.

@@ -424,19 +424,28 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             tmem_ld_x32(tmem_base + t_lane + ATT_TMEM_S + 64 * half + c, sv);
             tmem_ld_wait();
             if (c + 32 <= valid) {   // full chunk (the common case): no per-element masking
-              float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+              // packed fp32 pairs (FFMA2 / FADD2): half the FMA-pipe instructions of the chunk
+              const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nm2 = f2_pack(-m_ref, -m_ref);
+              uint64_t rs2[2] = {0ull, 0ull};   // two independent (even, odd) running sums
 #pragma unroll
               for (int cc = 0; cc < 32; cc += 8) {
                 float pv[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  pv[i] = fast_exp2(fmaf(__uint_as_float(sv[cc + i]), scale_log2, -m_ref));
-                  rs4[i & 3] += pv[i];
+                for (int i = 0; i < 4; ++i) {
+                  float lo, hi;
+                  f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[cc + 2 * i]), __uint_as_float(sv[cc + 2 * i + 1])), sc2, nm2), lo, hi);
+                  pv[2 * i] = fast_exp2(lo);
+                  pv[2 * i + 1] = fast_exp2(hi);
+                  rs2[i & 1] = f2_add(rs2[i & 1], f2_pack(pv[2 * i], pv[2 * i + 1]));
                 }
                 sts128(p_base + sw128_offset(r, (c + cc) >> 3),
                        make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7])));
               }
-              rowsum += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+              {
+                float lo, hi;
+                f2_unpack(f2_add(rs2[0], rs2[1]), lo, hi);
+                rowsum += lo + hi;
+              }
             } else {
 #pragma unroll
               for (int cc = 0; cc < 32; cc += 8) {

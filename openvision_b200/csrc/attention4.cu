@@ -78,8 +78,19 @@ __device__ __forceinline__ float max3f_4(float a, float b, float c) { return fma
 
 // 16 exponentials p = 2^(s * scale - m) of one chunk, issued back to back
 __device__ __forceinline__ void exp_chunk_4(const uint32_t (&x)[16], float scale_log2, float neg_m, float (&e)[16]) {
+#ifdef OVK_A4_NO_F32X2
 #pragma unroll
   for (int i = 0; i < 16; ++i) e[i] = fast_exp2(fmaf(__uint_as_float(x[i]), scale_log2, neg_m));
+#else
+  const uint64_t s2 = f2_pack(scale_log2, scale_log2), m2 = f2_pack(neg_m, neg_m);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float lo, hi;
+    f2_unpack(f2_fma(f2_pack(__uint_as_float(x[2 * i]), __uint_as_float(x[2 * i + 1])), s2, m2), lo, hi);
+    e[2 * i] = fast_exp2(lo);
+    e[2 * i + 1] = fast_exp2(hi);
+  }
+#endif
 }
 // TRUNC variant (OVK_ATT4_TRUNC=1, A/B): the fp32 -> bf16 pack of P is the XU pipe's second customer (F2FP runs there, ~3
 // clocks per warp instruction next to the 8 of every MUFU).  A byte permute on the ALU pipe keeps the upper halves of two
@@ -91,12 +102,20 @@ constexpr float A4_TRUNC_INV = 0.99718196f;      // 1 / 1.002826
 // consume a chunk of exponentials: row-sum contribution and the 8 packed bf16 pairs
 template <bool TRUNC>
 __device__ __forceinline__ float pack_chunk_4(const float (&e)[16], uint32_t (&pw)[8]) {
-  float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
-  float s4 = e[8] + e[9], s5 = e[10] + e[11], s6 = e[12] + e[13], s7 = e[14] + e[15];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     pw[i] = TRUNC ? __byte_perm(__float_as_uint(e[2 * i]), __float_as_uint(e[2 * i + 1]), 0x7632) : pack_bf16x2(e[2 * i], e[2 * i + 1]);
+#ifdef OVK_A4_NO_F32X2
+  float s0 = e[0] + e[1], s1 = e[2] + e[3], s2 = e[4] + e[5], s3 = e[6] + e[7];
+  float s4 = e[8] + e[9], s5 = e[10] + e[11], s6 = e[12] + e[13], s7 = e[14] + e[15];
   return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+#else
+  const uint64_t a0 = f2_add(f2_pack(e[0], e[1]), f2_pack(e[2], e[3])), a1 = f2_add(f2_pack(e[4], e[5]), f2_pack(e[6], e[7]));
+  const uint64_t a2 = f2_add(f2_pack(e[8], e[9]), f2_pack(e[10], e[11])), a3 = f2_add(f2_pack(e[12], e[13]), f2_pack(e[14], e[15]));
+  float lo, hi;
+  f2_unpack(f2_add(f2_add(a0, a1), f2_add(a2, a3)), lo, hi);
+  return lo + hi;
+#endif
 }
 
 // what the deferred epilogue of an item needs
@@ -114,7 +133,8 @@ template <bool TRUNC, int DBG = 0>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse_out,
-                      __nv_bfloat16* __restrict__ out, int L, int Lm, int H, int nq, int total_items, float scale_log2) {
+                      __nv_bfloat16* __restrict__ out, int L, int Lm, int H, int nq, int total_items, float scale_log2,
+                      int stagger_ns) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention4: dynamic smem base not 1024-byte aligned\n");
@@ -480,6 +500,9 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       // (the scratch words red+32.. / the staging tile are reused only after the next named barrier / the next TMA load)
     };
 
+    // Start-up stagger of slot B (OVK_ATT4_STAGGER_NS, A/B): the two slots do the same work per step, so left alone both warps
+    // of a scheduler sit in their exp phase (XU contended) and in their load / max / hand-off phase (XU idle) together.
+    if (w == 1 && stagger_ns > 0) __nanosleep(static_cast<unsigned>(stagger_ns));
     for (int n = 0;; ++n) {
       const int item = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
       const bool done = item >= total_items;
@@ -706,6 +729,8 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention4): %s", cudaGetErrorString(e));
     attr_once.done();
   }
+  const char* stg = getenv("OVK_ATT4_STAGGER_NS");
+  const int stagger = stg != nullptr ? atoi(stg) : 0;
   const char* tr = getenv("OVK_ATT4_TRUNC");   // read per call (A/B runs alternate the two inside one process)
   const bool trunc = tr != nullptr && tr[0] == '1';
   const int tail = (L > A4_BQ && L % A4_BQ == 1) ? 1 : 0;   // cls + power-of-two grid: remainder token handled outside the tiles
@@ -723,7 +748,7 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
       cudaFuncSetAttribute(attention_fwd4_kernel<false, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);             \
       attention_fwd4_kernel<false, N><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), \
                                                                        L, l_main, H, nq, static_cast<int>(items),              \
-                                                                       scale * 1.4426950408889634f);                          \
+                                                                       scale * 1.4426950408889634f, stagger);                 \
       return check_launch("attention_fwd4_kernel<dbg>");                                                                       \
     }
     OVK_A4_DBG_CASE(1) OVK_A4_DBG_CASE(2) OVK_A4_DBG_CASE(4) OVK_A4_DBG_CASE(8) OVK_A4_DBG_CASE(5) OVK_A4_DBG_CASE(7) OVK_A4_DBG_CASE(15)
@@ -733,9 +758,9 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
 #endif
   if (trunc)
     attention_fwd4_kernel<true><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
-                                                                 l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f);
+                                                                 l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f, stagger);
   else
     attention_fwd4_kernel<false><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
-                                                                  l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f);
+                                                                  l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f, stagger);
   return check_launch("attention_fwd4_kernel");
 }

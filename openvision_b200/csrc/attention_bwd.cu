@@ -62,7 +62,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      const __grid_constant__ CUtensorMap tmQKVb, const __grid_constant__ CUtensorMap tmOb,
                      const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
                      const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale, int total_items,
-                     int causal) {
+                     int causal, int Lm, const float* __restrict__ ws, const __nv_bfloat16* __restrict__ qkv_g,
+                     const __nv_bfloat16* __restrict__ dout_g, int hd_g) {
+  // Lm < L (= L - 1, remainder token of L = 128 k + 1): the tiles cover tokens [0, Lm) only; the remainder token's query
+  // row and key / value row are computed by attention_bwd_tail_kernel, which also leaves, per (image, head), the three
+  // vectors the epilogues below add as rank-1 terms: ws[0][i] = dS(i, t), ws[1][j] = P(t, j), ws[2][j] = dS(t, j).
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) {
     if (threadIdx.x == 0) printf("[ovk] attention_bwd: dynamic smem base not 1024-byte aligned\n");
@@ -82,7 +86,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
-  const int nt = (L + AB_T - 1) / AB_T;  // tiles per sequence: stationary tiles of an item, streamed tiles per item
+  const int nt = (Lm + AB_T - 1) / AB_T;  // tiles per sequence: stationary tiles of an item, streamed tiles per item
   const float s2 = scale * 1.4426950408889634f;
   // stationary tile `which` (0: ST0, 1: ST1, 2: X) of set `buf`
   auto st_off = [](int buf, int which) { return buf == 0 ? (which == 0 ? AB_OFF_ST0 : which == 1 ? AB_OFF_ST1 : AB_OFF_X)
@@ -178,7 +182,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           const uint32_t sa = smem_u32(smem + AB_OFF_SA + s * AB_TILE), sb = smem_u32(smem + AB_OFF_SB + s * AB_TILE);
           const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
           const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
-          const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
+          const int nkv = (min(AB_T, Lm - kv0) + 15) & ~15;
           const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
           const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
           const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
@@ -209,8 +213,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           const uint32_t sab = smem_u32(smem + AB_OFF_SAB + s * AB_BT), sbb = smem_u32(smem + AB_OFF_SBB + s * AB_BT);
           const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
           const int q0 = (MODE == MODE_DQ) ? t0 : it * AB_T;
-          const int nkv = (min(AB_T, L - kv0) + 15) & ~15;
-          const int nq = (min(AB_T, L - q0) + 15) & ~15;
+          const int nkv = (min(AB_T, Lm - kv0) + 15) & ~15;
+          const int nq = (min(AB_T, Lm - q0) + 15) & ~15;
           const uint32_t q_addr = (MODE == MODE_DQ) ? st0 : sa;
           const uint32_t do_addr = (MODE == MODE_DQ) ? st1 : sb;
           const uint32_t k_addr = (MODE == MODE_DQ) ? sa : st0;
@@ -300,22 +304,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       dlt = d;
       mbar_arrive(&st_empty[buf]);   // this thread is done reading the stationary tiles
       const int row = t0 + r;
-      if (row < L) {
+      if (row < Lm) {
         lse2 = lse[bh * L + row] * 1.4426950408889634f;
         if (hsel == 0) delta[bh * L + row] = d;
       }
     }
     for (int it = 0; it < nt; ++it, ++g) {
       const int kv0 = (MODE == MODE_DQ) ? it * AB_T : t0;
-      const int valid_kv = min(AB_T, L - kv0);
+      const int valid_kv = min(AB_T, Lm - kv0);
       // causal mask (transformer.py:757-763): query row qrow sees keys <= qrow; P and dS are zero above the diagonal, which
       // is the same per-element masking as the columns past the end of the sequence, with a per-thread column count
       const int qrow = ((MODE == MODE_DQ) ? t0 : it * AB_T) + r;
       const int kmax = causal ? min(valid_kv, qrow - kv0 + 1) : valid_kv;
       if (MODE == MODE_DKV) {
         const int row = it * AB_T + r;
-        lse2 = row < L ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
-        dlt = row < L ? delta[bh * L + row] : 0.f;
+        lse2 = row < Lm ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
+        dlt = row < Lm ? delta[bh * L + row] : 0.f;
       }
       mbar_wait(s_full, g & 1, 25);
       tc_fence_after();
@@ -324,7 +328,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // rows that the TMA store clips).  DQ: A = dS[q rows][keys < nkv].  DKV: A = (P | dS)^T, contraction over the first
       // nq query rows, key columns >= valid_kv only feed clipped dK / dV rows.  With L = 128 k + 1 most of the remainder
       // tile's work falls away here.
-      const int rows_read = (MODE == MODE_DQ) ? min(AB_T, L - t0) : ((min(AB_T, L - it * AB_T) + 15) & ~15);
+      const int rows_read = (MODE == MODE_DQ) ? min(AB_T, Lm - t0) : ((min(AB_T, Lm - it * AB_T) + 15) & ~15);
       const int cols_read = (MODE == MODE_DQ) ? ((valid_kv + 15) & ~15) : valid_kv;
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
@@ -336,12 +340,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld_wait();
         uint32_t pp[16], dd[16];
         if (col + 32 <= kmax) {   // full chunk (the common case): no per-element masking
+          // packed fp32 pairs (FFMA2 / FADD2 / FMUL2): 3 instead of 6 FMA-pipe instructions per pair of scores
+          const uint64_t sc2 = f2_pack(s2, s2), nl2 = f2_pack(-lse2, -lse2), nd2 = f2_pack(-dlt, -dlt);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(sv[2 * j]), s2, -lse2));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(sv[2 * j + 1]), s2, -lse2));
+            float x0, x1, d0, d1;
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(sv[2 * j]), __uint_as_float(sv[2 * j + 1])), sc2, nl2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
             pp[j] = pack_bf16x2(p0, p1);
-            dd[j] = pack_bf16x2(p0 * (__uint_as_float(dv[2 * j]) - dlt), p1 * (__uint_as_float(dv[2 * j + 1]) - dlt));
+            f2_unpack(f2_mul(f2_pack(p0, p1), f2_add(f2_pack(__uint_as_float(dv[2 * j]), __uint_as_float(dv[2 * j + 1])), nd2)), d0, d1);
+            dd[j] = pack_bf16x2(d0, d1);
           }
         } else {
 #pragma unroll
@@ -374,10 +382,53 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_wait(mma_done, (g - 1) & 1, 27);
     tc_fence_after();
     // staging reuses the P region: atom 0 <- ACC0 (dQ or dK), atom 1 <- ACC1 (dV)
+    // rank-1 terms of the remainder token (see the kernel header): coefficient of this thread's row, and the row of the
+    // packed qkv / dout tensors that multiplies it
+    const bool tail = ws != nullptr;
+    float tcoef = 0.f;
+    const __nv_bfloat16* tvec = nullptr;
+    if (tail) {
+      const float* wsb = ws + bh * 3 * Lm;
+      const long long trow = static_cast<long long>(b) * L + Lm;   // the remainder token
+      if (MODE == MODE_DQ) {
+        tcoef = wsb[t0 + r];                                                                  // dS(i, t)
+        tvec = qkv_g + (trow * 3 * H + H + h) * hd_g;                                          // k_t
+      } else if (hsel == 0) {
+        tcoef = wsb[2 * Lm + t0 + r];                                                         // dS(t, j)
+        tvec = qkv_g + (trow * 3 * H + h) * hd_g;                                              // q_t
+      } else {
+        tcoef = wsb[Lm + t0 + r];                                                             // P(t, j)
+        tvec = dout_g + (trow * H + h) * hd_g;                                                 // dO_t
+      }
+    }
+    // o[0..n) += tcoef * tvec[col0 .. col0 + n)   (n a multiple of 8)
+    auto add_tail = [&](uint32_t* o, int col0, int n) {
+      for (int v = 0; v < n / 8; ++v) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(tvec + col0) + v);
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          o[8 * v + 2 * q] = __float_as_uint(fmaf(tcoef, bf16_lo(w4[q]), __uint_as_float(o[8 * v + 2 * q])));
+          o[8 * v + 2 * q + 1] = __float_as_uint(fmaf(tcoef, bf16_hi(w4[q]), __uint_as_float(o[8 * v + 2 * q + 1])));
+        }
+      }
+    };
     if (MODE == MODE_DQ) {
       uint32_t o[32];
       tmem_ld_x32(tmem_base + t_lane + AB_TM_ACC0 + hsel * 32, o);
       tmem_ld_wait();
+      if (tail) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const uint4 u = __ldg(reinterpret_cast<const uint4*>(tvec + hsel * 32) + v);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o[8 * v + 2 * q] = __float_as_uint(fmaf(tcoef, bf16_lo(w4[q]), __uint_as_float(o[8 * v + 2 * q])));
+            o[8 * v + 2 * q + 1] = __float_as_uint(fmaf(tcoef, bf16_hi(w4[q]), __uint_as_float(o[8 * v + 2 * q + 1])));
+          }
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         sts128(smem_u32(smem + AB_OFF_P) + sw128_offset(r, hsel * 4 + q),
@@ -393,6 +444,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         uint32_t o[32];
         tmem_ld_x32(tmem_base + t_lane + src + c, o);
         tmem_ld_wait();
+        if (tail) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(tvec + c) + v);
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              o[8 * v + 2 * q] = __float_as_uint(fmaf(tcoef, bf16_lo(w4[q]), __uint_as_float(o[8 * v + 2 * q])));
+              o[8 * v + 2 * q + 1] = __float_as_uint(fmaf(tcoef, bf16_hi(w4[q]), __uint_as_float(o[8 * v + 2 * q + 1])));
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           sts128(smem_u32(smem + AB_OFF_P + hsel * AB_TILE) + sw128_offset(r, (c >> 3) + q),
@@ -409,6 +472,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       uint32_t ob[16];
       tmem_ld_x16(tmem_base + t_lane + srcb, ob);
       tmem_ld_wait();
+      if (tail) add_tail(ob, 64, hd_g - 64 < 16 ? hd_g - 64 : 16);   // dims 64 .. hd (the columns past hd stay zero)
       const uint32_t dst = smem_u32(smem + AB_OFF_OUTB + hsel * AB_BT);
 #pragma unroll
       for (int c = 0; c < 2; ++c)
@@ -447,17 +511,179 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------ remainder token
+// L = 128 k + 1 (class token + a power-of-two patch grid: every L/14 and H/14 training step): as a third row / column of
+// 128-wide tiles the one remainder token t = L - 1 cost the tile kernels +63 % (B = 256, L = 257 vs 256).  Here it is a
+// handful of dot products per (image, head) on the FMA pipe, one thread per token:
+//   row t      : s_j = q_t . k_j, P(t, j), dS(t, j) for every key j  ->  dq_t = scale * sum_j dS(t, j) k_j
+//   column t   : s_i = q_i . k_t, P(i, t), dS(i, t) for every query i ->  dk_t = scale * sum_i dS(i, t) q_i,  dv_t = sum_i P(i, t) dO_i
+// and the vectors dS(., t), P(t, .), dS(t, .) over the tile tokens go to `ws` for the tile kernels' epilogues (rank-1 terms).
+constexpr int ABT_THREADS = 256;
+constexpr int ABT_WARPS = ABT_THREADS / 32;
+constexpr int ABT_MAXV = 10;   // head width <= 80: ten 16-byte vectors per row
+
+// dot product of a global bf16 row (one thread streams the whole row) with an fp32 vector in shared memory
+__device__ __forceinline__ float abt_dot(const __nv_bfloat16* p, int nv, const float* vec) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int v = 0; v < ABT_MAXV; ++v) {
+    if (v < nv) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + v);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a0 = fmaf(bf16_lo(w4[q]), vec[8 * v + 2 * q], a0);
+        a1 = fmaf(bf16_hi(w4[q]), vec[8 * v + 2 * q + 1], a1);
+      }
+    }
+  }
+  return a0 + a1;
+}
+// dot product of two global bf16 rows
+__device__ __forceinline__ float abt_dot2(const __nv_bfloat16* p, const __nv_bfloat16* q, int nv) {
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int v = 0; v < ABT_MAXV; ++v) {
+    if (v < nv) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + v);
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(q) + v);
+      const uint32_t u4[4] = {u.x, u.y, u.z, u.w}, w4[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a0 = fmaf(bf16_lo(u4[k]), bf16_lo(w4[k]), a0);
+        a1 = fmaf(bf16_hi(u4[k]), bf16_hi(w4[k]), a1);
+      }
+    }
+  }
+  return a0 + a1;
+}
+
+__global__ void __launch_bounds__(ABT_THREADS, 4)
+attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                          const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                          float* __restrict__ ws, int L, int H, int hd, float scale) {
+  extern __shared__ float abt_smem[];
+  const int Lm = L - 1, t = L - 1;
+  const int nv = hd >> 3;
+  float* vq = abt_smem;            // q_t, k_t, v_t, dO_t, O_t as fp32 [5][80]
+  float* vk = vq + 80;
+  float* vv = vk + 80;
+  float* vd = vv + 80;
+  float* vo = vd + 80;
+  float* red = vo + 80;            // [ABT_WARPS][96] per-warp partial sums of a weighted row sum
+  float* c1 = red + ABT_WARPS * 96;   // [L] coefficient vectors of the current part
+  float* c2 = c1 + L;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.x;
+  const long long b = blockIdx.y;
+  const long long bh = b * H + h;
+  const long long qtok = 3LL * H * hd;                 // elements per token of qkv / dqkv
+  const long long otok = static_cast<long long>(H) * hd;
+  const __nv_bfloat16* qb = qkv + b * L * qtok + h * hd;                 // q rows of this head (k: + H*hd, v: + 2*H*hd)
+  const __nv_bfloat16* ob = out + b * L * otok + h * hd;
+  const __nv_bfloat16* db = dout + b * L * otok + h * hd;
+  const float s2 = scale * 1.4426950408889634f;
+  for (int d = tid; d < hd; d += ABT_THREADS) {
+    vq[d] = __bfloat162float(qb[t * qtok + d]);
+    vk[d] = __bfloat162float(qb[t * qtok + H * hd + d]);
+    vv[d] = __bfloat162float(qb[t * qtok + 2 * H * hd + d]);
+    vd[d] = __bfloat162float(db[t * otok + d]);
+    vo[d] = __bfloat162float(ob[t * otok + d]);
+  }
+  __syncthreads();
+  float delta_t = 0.f;
+  for (int d = 0; d < hd; ++d) delta_t = fmaf(vd[d], vo[d], delta_t);
+  const float lse_t2 = lse[bh * L + t] * 1.4426950408889634f;
+  float* wsb = ws + bh * 3 * Lm;
+
+  // dst[0..hd) = mul * sum_j coef[j] * row_j[0..hd)  (rows `pitch` elements apart).  Lanes own dimension pairs (one coalesced
+  // 4-byte load per lane and row: 128 contiguous bytes per warp), warps own every ABT_WARPS-th row.
+  auto weighted_row_sum = [&](const __nv_bfloat16* rows, long long pitch, const float* coef, float mul, __nv_bfloat16* dst) {
+    const int np = hd >> 1;                    // dimension pairs (32 for hd = 64, 40 for hd = 80)
+    const bool second = lane + 32 < np;        // lanes 0..7 carry a second pair when hd > 64
+    float a0 = 0.f, a1 = 0.f, e0 = 0.f, e1 = 0.f;
+#pragma unroll 8
+    for (int j = warp; j < L; j += ABT_WARPS) {
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rows + j * pitch);
+      const float cj = coef[j];
+      if (lane < np) {
+        const uint32_t u = __ldg(r32 + lane);
+        a0 = fmaf(cj, bf16_lo(u), a0);
+        a1 = fmaf(cj, bf16_hi(u), a1);
+      }
+      if (second) {
+        const uint32_t u = __ldg(r32 + 32 + lane);
+        e0 = fmaf(cj, bf16_lo(u), e0);
+        e1 = fmaf(cj, bf16_hi(u), e1);
+      }
+    }
+    if (lane < np) {
+      red[warp * 96 + 2 * lane] = a0;
+      red[warp * 96 + 2 * lane + 1] = a1;
+    }
+    if (second) {
+      red[warp * 96 + 64 + 2 * lane] = e0;
+      red[warp * 96 + 64 + 2 * lane + 1] = e1;
+    }
+    __syncthreads();
+    for (int d = tid; d < hd; d += ABT_THREADS) {
+      float sum = 0.f;
+#pragma unroll
+      for (int x = 0; x < ABT_WARPS; ++x) sum += red[x * 96 + d];   // fixed order: deterministic
+      dst[d] = __float2bfloat16(sum * mul);
+    }
+    __syncthreads();
+  };
+
+  // ---------------------------------------------------------------- row t: every key j (one thread per key)
+  for (int j = tid; j < L; j += ABT_THREADS) {
+    const float s = abt_dot(qb + j * qtok + H * hd, nv, vq);          // q_t . k_j
+    const float dp = abt_dot(qb + j * qtok + 2 * H * hd, nv, vd);     // dO_t . v_j
+    const float p = fast_exp2(fmaf(s, s2, -lse_t2));
+    const float ds = p * (dp - delta_t);
+    c1[j] = ds;
+    if (j < Lm) {
+      wsb[Lm + j] = p;          // P(t, j)   -> dV_j += P(t, j) dO_t
+      wsb[2 * Lm + j] = ds;     // dS(t, j)  -> dK_j += scale dS(t, j) q_t
+    }
+  }
+  __syncthreads();
+  weighted_row_sum(qb + H * hd, qtok, c1, scale, dqkv + (b * L + t) * qtok + h * hd);                  // dq_t = scale sum dS(t, j) k_j
+  // ---------------------------------------------------------------- column t: every query i (one thread per query)
+  for (int i = tid; i < L; i += ABT_THREADS) {
+    const float s = abt_dot(qb + i * qtok, nv, vk);                   // q_i . k_t
+    const float dp = abt_dot(db + i * otok, nv, vv);                  // dO_i . v_t
+    const float dl = abt_dot2(db + i * otok, ob + i * otok, nv);      // delta_i = dO_i . O_i
+    const float p = fast_exp2(fmaf(s, s2, -lse[bh * L + i] * 1.4426950408889634f));
+    const float ds = p * (dp - dl);
+    c1[i] = ds;
+    c2[i] = p;
+    if (i < Lm) wsb[i] = ds;    // dS(i, t)  -> dQ_i += scale dS(i, t) k_t
+  }
+  __syncthreads();
+  weighted_row_sum(qb, qtok, c1, scale, dqkv + (b * L + t) * qtok + H * hd + h * hd);                  // dk_t = scale sum dS(i, t) q_i
+  weighted_row_sum(db, otok, c2, 1.f, dqkv + (b * L + t) * qtok + 2 * H * hd + h * hd);                // dv_t = sum P(i, t) dO_i
+}
+
 }  // namespace ovk
 
 using namespace ovk;
 
 extern "C" int ovk_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                  float* delta, int B, int L, int H, int hd, float scale, void* stream) {
-  return ovk_attention_bwd_ex(qkv, out, dout, lse, dqkv, delta, B, L, H, hd, scale, 0, stream);
+  return ovk_attention_bwd_ex(qkv, out, dout, lse, dqkv, delta, nullptr, B, L, H, hd, scale, 0, stream);
+}
+
+extern "C" long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int flags) {
+  // measured (tools/attn_bwd_ab.py, batch 1024 x 16 heads): L = 257: -4.5 % (head width 64), -8.4 % (80); L = 1025: +5 % (the
+  // tail kernel's extra pass over q, k, v, dO, O outweighs one tile row / column in nine): offered up to three full tiles
+  if (B <= 0 || L <= AB_T || H <= 0 || (L % AB_T) != 1 || L > 3 * AB_T + 1 || (flags & OVK_ATT_CAUSAL)) return 0;
+  return 3LL * B * H * (L - 1);
 }
 
 extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                                    float* delta, int B, int L, int H, int hd, float scale, int flags, void* stream) {
+                                    float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
+                                    void* stream) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
   if (flags & ~OVK_ATT_CAUSAL) return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
   const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
@@ -500,22 +726,41 @@ extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
     attr_once.done();
   }
-  const long long items_ll = static_cast<long long>((L + AB_T - 1) / AB_T) * H * B;
+  // remainder token (L = 128 k + 1) outside the tiles when the caller supplied the workspace
+  const bool tail = workspace != nullptr && ovk_attention_bwd_workspace_floats(B, L, H, flags) > 0 && B <= 65535 && H <= 65535;
+  const int Lm = tail ? L - 1 : L;
+  if (tail) {
+    const size_t sm = (5 * 80 + ABT_WARPS * 96 + 2 * static_cast<size_t>(L)) * sizeof(float);
+    static PerDeviceOnce tail_once;
+    if (tail_once.need()) {
+      cudaError_t e = cudaFuncSetAttribute(attention_bwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd_tail): %s", cudaGetErrorString(e));
+      tail_once.done();
+    }
+    attention_bwd_tail_kernel<<<dim3(H, B), ABT_THREADS, sm, s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
+        reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
+    if ((rc = check_launch("attention_bwd_tail_kernel"))) return rc;
+  }
+  const float* wsp = tail ? workspace : nullptr;
+  auto qg = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  auto dg = reinterpret_cast<const __nv_bfloat16*>(dout);
+  const long long items_ll = static_cast<long long>((Lm + AB_T - 1) / AB_T) * H * B;
   if (items_ll > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention_bwd: too many work items");
   const int items = static_cast<int>(items_ll);
   const int grid = items < num_sms() ? items : num_sms();   // persistent: one CTA per SM (512 TMEM columns each)
   if (ext) {
     attention_bwd_kernel<MODE_DQ, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                 tmDQKVb, lse, delta, L, H, scale, items, causal);
+                                                                                 tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                  tmDQKVb, lse, delta, L, H, scale, items, causal);
+                                                                                  tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
   } else {
     attention_bwd_kernel<MODE_DQ, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                             tmDQKVb, lse, delta, L, H, scale, items, causal);
+                                                                             tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                              tmDQKVb, lse, delta, L, H, scale, items, causal);
+                                                                              tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
   }
   return check_launch("attention_bwd_kernel<dKdV>");
 }

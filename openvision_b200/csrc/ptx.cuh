@@ -276,6 +276,31 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32 pairs (sm_100: FFMA2 / FADD2 work on an aligned register pair): half the FMA-pipe instructions of a softmax step.
+// The attention kernels are bound by the instruction streams of their softmax warps (profiles/r02_attention4_analysis.md), so
+// instruction count is what counts.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` in a [rows x 128 B] SWIZZLE_128B tile
 // whose base is 1024-byte aligned (the layout TMA SWIZZLE_128B reads and writes).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {

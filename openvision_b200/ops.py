@@ -626,10 +626,15 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
     delta = torch.empty((B, H, L), dtype=torch.float32, device=qkv.device)
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
+    import os
+    nws = _lib.load().ovk_attention_bwd_workspace_floats(B, L, H, int(bool(causal)))
+    if os.environ.get("OVK_ATTBWD_TAIL", "1") == "0":   # A/B: the remainder token as a third tile row / column
+        nws = 0
+    ws = torch.empty(nws, dtype=torch.float32, device=qkv.device) if nws > 0 else None   # remainder token of L = 128 k + 1
     with _timed("attention_bwd", 14.0 * B * H * L * L * hd):
-        _lib.call("ovk_attention_bwd_ex", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), B, L, H, hd,
+        _lib.call("ovk_attention_bwd_ex", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), _p(ws), B, L, H, hd,
                   float(scale), int(bool(causal)), _stream())
-    _count(2)
+    _count(3 if ws is not None else 2)
     return dqkv
 
 

@@ -273,3 +273,30 @@ def test_l14_full_size_gradients_match_oracle_autograd():
     for k in watch:
         assert_grad(params[k[len("visual."):]].grad, ref_sd[k].grad, k, 8e-2)
     assert_grad(img.grad, ref_img.grad, "d images", 8e-2)
+
+
+@pytest.mark.parametrize("B,L,H,hd", [(2, 257, 3, 64), (1, 129, 2, 64), (2, 385, 2, 64), (2, 257, 2, 80), (1, 129, 3, 72), (40, 257, 8, 64)])
+def test_attention_bwd_remainder_token_outside_the_tiles(ops, B, L, H, hd, monkeypatch):
+    """L = 128 k + 1: the remainder token's query row and key / value row come from attention_bwd_tail_kernel and reach the
+    other rows as rank-1 terms in the tile kernels' epilogues.  Checked against autograd, row t separately, and against the
+    all-tiles path (OVK_ATTBWD_TAIL=0) which computes the same thing with a third tile row / column."""
+    qkv = rnd(B * L, 3 * H * hd, seed=L + hd + 3).bfloat16()
+    dout = rnd(B * L, H * hd, seed=L + hd + 4).bfloat16()
+    qc = qkv.cuda()
+    out, lse = ops.attention(qc, B, L, H, hd, save_lse=True)
+    n0 = ops.launch_count
+    dqkv = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
+    assert ops.launch_count - n0 == 3, "tail kernel + dQ + dK/dV"
+    monkeypatch.setenv("OVK_ATTBWD_TAIL", "0")
+    dqkv_tiles = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = qf.view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), -1)
+    (p @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd).backward(dout.float())
+    g = dqkv.float().cpu().view(B, L, 3, H, hd)
+    g2 = dqkv_tiles.float().cpu().view(B, L, 3, H, hd)
+    r = qf.grad.view(B, L, 3, H, hd)
+    for i, name in enumerate("qkv"):
+        assert_grad(g[:, :, i], r[:, :, i], f"d{name} (all rows)", 3e-2)
+        assert_grad(g[:, L - 1, i], r[:, L - 1, i], f"d{name} (remainder row)", 3e-2)
+        assert_grad(g[:, :, i], g2[:, :, i], f"d{name}: tail path vs all-tiles path", 2e-2)
