@@ -90,20 +90,25 @@ __global__ void __launch_bounds__(128) ln_pack_kernel(const TW* __restrict__ W, 
         }
       }
     }
-    unsigned rem = __ballot_sync(0xffffffffu, ok_dn || ok_up);
-    while (rem != 0u && r != 0.f) {
-      const int j = __ffs(rem) - 1;
-      rem &= rem - 1;
+    // candidates that can still move r towards zero, re-evaluated after every move (r changes sign / size); entries at or
+    // below the last visited lane are not revisited — the same decisions a serial walk over k makes, at one ballot + one
+    // shuffle per APPLIED move instead of a step per entry
+    unsigned visited = 0u;
+    while (r != 0.f) {
       const bool down = r > 0.f;
-      const float dj = __shfl_sync(0xffffffffu, down ? delta_dn : delta_up, j);
-      const bool okj = __shfl_sync(0xffffffffu, static_cast<int>(down ? ok_dn : ok_up), j) != 0;
-      if (!okj || fabsf(dj) >= 2.f * fabsf(r)) continue;            // not off in that direction / the move would overshoot
+      const float dsel = down ? delta_dn : delta_up;
+      const bool osel = down ? ok_dn : ok_up;
+      const unsigned cand = __ballot_sync(0xffffffffu, osel && fabsf(dsel) < 2.f * fabsf(r)) & ~visited;
+      if (cand == 0u) break;
+      const int j = __ffs(cand) - 1;
+      const float dj = __shfl_sync(0xffffffffu, dsel, j);
       if (lane == j) {
         const float qv = bf16_bits_to_float(b);
         const uint32_t nb = ((qv > 0.f) == down) ? b - 1 : b + 1;
         q[k] = static_cast<unsigned short>(nb);
       }
       r += dj;
+      visited |= (2u << j) - 1u;   // lanes 0..j
     }
   }
 }
