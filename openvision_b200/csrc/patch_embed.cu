@@ -22,6 +22,8 @@
 //
 // HBM traffic: the image is read once (the four 256-column tiles of one 128-patch row block run on neighbouring CTAs and
 // share it through L2), tokens are written once: no im2col buffer (the round-1 path wrote and re-read B * N * 3P^2 bf16).
+#include <stdlib.h>
+
 #include "gemm_core.cuh"
 #include "host_utils.h"
 
@@ -38,11 +40,12 @@ constexpr int PE_A_BYTES = PE_BM * 128;
 constexpr int PE_B_BYTES = PE_BN * 128;
 constexpr int PE_C_BYTES = PE_BM * 128;
 constexpr int PE_OFF_A = 0;
-constexpr int PE_OFF_B = PE_OFF_A + 2 * PE_A_BYTES;
-constexpr int PE_OFF_C = PE_OFF_B + 2 * PE_B_BYTES;
-constexpr int PE_OFF_RAW = PE_OFF_C + 2 * PE_C_BYTES;
-constexpr int PE_OFF_BAR = PE_OFF_RAW + PE_RAW_BYTES;
-constexpr int PE_NUM_BARS = 12 + 2 * PE_RAW_MAX_STAGES;
+constexpr int PE_OFF_C = PE_OFF_A + 2 * PE_A_BYTES;
+constexpr int PE_OFF_B = PE_OFF_C + 2 * PE_C_BYTES;     // b_nst weight stages, then the pixel staging ring (both sized by the host)
+constexpr int PE_DYN_BYTES = 2 * PE_B_BYTES + PE_RAW_BYTES;   // B ring + staging ring together: 152 KB
+constexpr int PE_B_MAX_STAGES = 3;
+constexpr int PE_OFF_BAR = PE_OFF_B + PE_DYN_BYTES;
+constexpr int PE_NUM_BARS = 8 + 2 * PE_B_MAX_STAGES + 2 * PE_RAW_MAX_STAGES;
 constexpr int PE_OFF_SLOT = PE_OFF_BAR + PE_NUM_BARS * 8;
 constexpr int PE_SMEM = PE_OFF_SLOT + 16;
 static_assert(PE_SMEM <= 232448, "exceeds 227 KB of dynamic shared memory");
@@ -50,8 +53,11 @@ static_assert(PE_SMEM <= 232448, "exceeds 227 KB of dynamic shared memory");
 struct PatchEmbedArgs {
   int B, N, gw, D, L;     // images, patches per image, patches per image row, width, tokens per image (N + 1)
   int nx, xbox;           // an image row is fetched as nx boxes of xbox pixels (TMA boxes are <= 256 wide)
-  int box_stride;         // bytes between staged boxes (box bytes rounded up to 128)
+  int row_bytes;          // bytes of one patch row inside a staged box: R image rows x xbox pixels
+  int box_bytes;          // bytes between the staged boxes = npy_box patch rows (rounded up to 128)
+  int box_bytes_tx;       // bytes one box transfers (unrounded)
   int raw_stage, raw_nst; // bytes per staging slot (multiple of 1024) and number of slots (2..4)
+  int b_nst;              // weight k-block stages (2 or 3); the staging ring starts behind them
   int tiles_pi, tiles_n;  // 128-patch tiles per image, 256-column tiles
   const __nv_bfloat16* table;   // [L, D] positional embedding (+ class token in row 0) or null (plain conv tokens)
   __nv_bfloat16* out;           // [B, L, D]
@@ -88,12 +94,13 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PE_OFF_BAR);
   uint64_t* a_full = bars;            // [2]
   uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* b_full = bars + 4;        // [2]
-  uint64_t* b_empty = bars + 6;       // [2]
-  uint64_t* tmem_full = bars + 8;     // [2]
-  uint64_t* tmem_empty = bars + 10;   // [2]
-  uint64_t* raw_full = bars + 12;                         // [raw_nst]
-  uint64_t* raw_empty = bars + 12 + PE_RAW_MAX_STAGES;    // [raw_nst]
+  uint64_t* tmem_full = bars + 4;     // [2]
+  uint64_t* tmem_empty = bars + 6;    // [2]
+  uint64_t* b_full = bars + 8;                            // [b_nst]
+  uint64_t* b_empty = bars + 8 + PE_B_MAX_STAGES;         // [b_nst]
+  uint64_t* raw_full = bars + 8 + 2 * PE_B_MAX_STAGES;                         // [raw_nst]
+  uint64_t* raw_empty = bars + 8 + 2 * PE_B_MAX_STAGES + PE_RAW_MAX_STAGES;    // [raw_nst]
+  uint8_t* const raw_base = smem + PE_OFF_B + a.b_nst * PE_B_BYTES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PE_OFF_SLOT);
   const int warp = threadIdx.x >> 5;
   const uint32_t lane = lane_id();
@@ -108,11 +115,13 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
       mbar_init(&raw_full[i], 1);
       mbar_init(&raw_empty[i], PE_TR_WARPS);
     }
+    for (int i = 0; i < PE_B_MAX_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], PE_TR_WARPS);
       mbar_init(&a_empty[i], 1);
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);
     }
@@ -138,34 +147,36 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ------------------------------------------------------------------------------------------ TMA producer
-      const uint32_t box_bytes = static_cast<uint32_t>(R * a.xbox * ES);
-      uint32_t kbc = 0;   // k-blocks issued so far (ring position / phase of the 2-stage A and B rings)
-      int rs = 0;         // staging ring: slot and phase
-      uint32_t rph = 0;
+
+      int rs = 0, bs = 0;   // staging ring / weight ring: slot and phase
+      uint32_t rph = 0, bph = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
         int b, p0, n0;
         decode(t, b, p0, n0);
         const int py0 = p0 / a.gw;
-        const int py1 = min(a.N - 1, p0 + PE_BM - 1) / a.gw;
-        const int npy = py1 - py0 + 1;
-        for (int kb = 0; kb < NKB; ++kb, ++kbc) {
-          const int s = kbc & 1;
-          const uint32_t ph = (kbc >> 1) & 1;
+        for (int kb = 0; kb < NKB; ++kb) {
           const int c = kb / PG, phg = kb % PG;
           mbar_wait(&raw_empty[rs], rph ^ 1, 11);
-          mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(npy * a.nx) * box_bytes);
-          uint8_t* dst = smem + PE_OFF_RAW + rs * a.raw_stage;
-          for (int pyl = 0; pyl < npy; ++pyl)
-            for (int ix = 0; ix < a.nx; ++ix)
-              tma_load_3d(dst + (pyl * a.nx + ix) * a.box_stride, &tmI, &raw_full[rs], ix * a.xbox, (py0 + pyl) * P + phg * R,
-                          b * 3 + c);
+          // ONE 4-D box per k-block (two when the image is wider than 256 pixels): [npy_box patch rows][R image rows][xbox
+          // pixels] of channel c, image rows phg*R.. of every patch row of the tile.  Rows past the patch (ph >= P) and
+          // patch rows past the image are zero-filled by the map.  (The first version issued one 3-D box per patch row: the
+          // single producer thread could not issue 8-14 of them per k-block fast enough and the transform warps spent 57 %
+          // of their time waiting for pixels.)
+          mbar_arrive_expect_tx(&raw_full[rs], static_cast<uint32_t>(a.nx * a.box_bytes_tx));
+          uint8_t* dst = raw_base + rs * a.raw_stage;
+          for (int ix = 0; ix < a.nx; ++ix)
+            tma_load_4d(dst + ix * a.box_bytes, &tmI, &raw_full[rs], ix * a.xbox, phg * R, py0, b * 3 + c);
           if (++rs == a.raw_nst) {
             rs = 0;
             rph ^= 1;
           }
-          mbar_wait(&b_empty[s], ph ^ 1, 12);
-          mbar_arrive_expect_tx(&b_full[s], PE_B_BYTES);
-          tma_load_2d(smem + PE_OFF_B + s * PE_B_BYTES, &tmB, &b_full[s], kb * 64, n0);
+          mbar_wait(&b_empty[bs], bph ^ 1, 12);
+          mbar_arrive_expect_tx(&b_full[bs], PE_B_BYTES);
+          tma_load_2d(smem + PE_OFF_B + bs * PE_B_BYTES, &tmB, &b_full[bs], kb * 64, n0);
+          if (++bs == a.b_nst) {
+            bs = 0;
+            bph ^= 1;
+          }
         }
       }
     }
@@ -174,6 +185,8 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
       // ------------------------------------------------------------------------------------------ MMA issuer
       constexpr uint32_t idesc = umma_idesc_bf16(PE_BM, PE_BN, 0, 0);
       uint32_t kbc = 0;
+      int bs = 0;
+      uint32_t bph = 0;
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -184,16 +197,20 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
           const int s = kbc & 1;
           const uint32_t ph = (kbc >> 1) & 1;
           mbar_wait(&a_full[s], ph, 14);
-          mbar_wait(&b_full[s], ph, 15);
+          mbar_wait(&b_full[bs], bph, 15);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + PE_OFF_A + s * PE_A_BYTES);
-          const uint32_t b_addr = smem_u32(smem + PE_OFF_B + s * PE_B_BYTES);
+          const uint32_t b_addr = smem_u32(smem + PE_OFF_B + bs * PE_B_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32), idesc,
                          (kb | k) != 0);
           umma_commit(&a_empty[s]);
-          umma_commit(&b_empty[s]);
+          umma_commit(&b_empty[bs]);
+          if (++bs == a.b_nst) {
+            bs = 0;
+            bph ^= 1;
+          }
         }
         umma_commit(&tmem_full[acc]);
       }
@@ -216,14 +233,14 @@ patch_embed_kernel(const __grid_constant__ CUtensorMap tmI, const __grid_constan
       const int pyl = py - p0 / a.gw;
       const int xpix = px * P;
       const int ix = xpix / a.xbox;
-      const uint32_t src_off = static_cast<uint32_t>((pyl * a.nx + ix) * a.box_stride + (xpix - ix * a.xbox) * ES);
+      const uint32_t src_off = static_cast<uint32_t>(ix * a.box_bytes + pyl * a.row_bytes + (xpix - ix * a.xbox) * ES);
       for (int kb = 0; kb < NKB; ++kb, ++kbc) {
         const int s = kbc & 1;
         const uint32_t ph = (kbc >> 1) & 1;
         const int phg = kb % PG;
         uint32_t w[RH][PW / 2];   // bf16 pairs of this thread's RH x PW slice of the k-block
         mbar_wait(&raw_full[rs], rph, 16);
-        const uint32_t src = smem_u32(smem + PE_OFF_RAW + rs * a.raw_stage) + src_off;
+        const uint32_t src = smem_u32(raw_base + rs * a.raw_stage) + src_off;
 #pragma unroll
         for (int rr = 0; rr < RH; ++rr) {
           const int r = r0 + rr;
@@ -376,11 +393,13 @@ static int launch_patch_embed(const CUtensorMap& tmI, const CUtensorMap& tmB, co
 
 using namespace ovk;
 
-// bytes of one staging slot: the most patch rows a 128-patch tile can touch, each nx boxes, rounded up to 1 KB
-static int pe_stage_bytes(int gw, int nx, int box_stride) {
-  const int npy = gw % PE_BM == 0 || PE_BM % gw == 0 ? (PE_BM + gw - 1) / gw : (gw - 1 + PE_BM - 1) / gw + 1;
-  return (npy * nx * box_stride + 1023) / 1024 * 1024;
+// most patch rows a 128-patch tile can touch
+static int pe_npy_box(int gw) {
+  return gw % PE_BM == 0 || PE_BM % gw == 0 ? (PE_BM + gw - 1) / gw : (gw - 1 + PE_BM - 1) / gw + 1;
 }
+// bytes of one staged box ([npy_box][R][xbox] pixels, rounded up to 128) and of one staging slot (nx boxes, rounded up to 1 KB)
+static int pe_box_bytes(int gw, int R, int xbox, int es) { return (pe_npy_box(gw) * R * xbox * es + 127) / 128 * 128; }
+static int pe_stage_bytes(int gw, int nx, int R, int xbox, int es) { return (nx * pe_box_bytes(gw, R, xbox, es) + 1023) / 1024 * 1024; }
 
 extern "C" int ovk_patch_embed_kdim(int P) {
   if (P != 14 && P != 16 && P != 32) return 0;
@@ -395,8 +414,8 @@ extern "C" int ovk_patch_embed_supported(int img_is_f32, int H, int W, int P, in
   const int nx = (W + 255) / 256;
   if (gw % nx || ((W / nx) * es) % 16 || (W * es) % 16) return 0;
   const int R = 64 / (P <= 16 ? 16 : 32);
-  const int box_stride = (R * (W / nx) * es + 127) / 128 * 128;
-  return 2 * pe_stage_bytes(gw, nx, box_stride) <= PE_RAW_BYTES ? 1 : 0;   // at least a double buffer
+  if (pe_npy_box(gw) > 256) return 0;
+  return 2 * pe_stage_bytes(gw, nx, R, W / nx, es) <= PE_DYN_BYTES - 2 * PE_B_BYTES ? 1 : 0;   // at least double buffers
 }
 
 extern "C" int ovk_patch_embed(const void* images, int img_is_f32, const void* w_packed, const void* pos_table, void* tokens,
@@ -416,9 +435,20 @@ extern "C" int ovk_patch_embed(const void* images, int img_is_f32, const void* w
   a.nx = (W + 255) / 256;
   a.xbox = W / a.nx;
   const int R = 64 / (P <= 16 ? 16 : 32);
-  a.box_stride = (R * a.xbox * es + 127) / 128 * 128;
-  a.raw_stage = pe_stage_bytes(a.gw, a.nx, a.box_stride);
-  a.raw_nst = PE_RAW_BYTES / a.raw_stage < PE_RAW_MAX_STAGES ? PE_RAW_BYTES / a.raw_stage : PE_RAW_MAX_STAGES;
+  const int npy_box = pe_npy_box(a.gw);
+  a.row_bytes = R * a.xbox * es;
+  a.box_bytes_tx = npy_box * a.row_bytes;
+  a.box_bytes = pe_box_bytes(a.gw, R, a.xbox, es);
+  a.raw_stage = pe_stage_bytes(a.gw, a.nx, R, a.xbox, es);
+  // 152 KB for the weight ring and the pixel staging ring: a third weight stage when two staging slots still fit behind it
+  // (bytes in flight per SM are what bounds this kernel: both rings are fed from L2 with ~1 us latency)
+  a.b_nst = (PE_DYN_BYTES - 3 * PE_B_BYTES) / a.raw_stage >= 2 ? 3 : 2;
+  {
+    const char* e = getenv("OVK_PE_BSTAGES");   // A/B
+    if (e != nullptr && e[0] == '2') a.b_nst = 2;
+  }
+  const int raw_room = (PE_DYN_BYTES - a.b_nst * PE_B_BYTES) / a.raw_stage;
+  a.raw_nst = raw_room < PE_RAW_MAX_STAGES ? raw_room : PE_RAW_MAX_STAGES;
   a.tiles_pi = (a.N + PE_BM - 1) / PE_BM;
   a.tiles_n = (D + PE_BN - 1) / PE_BN;
   a.table = reinterpret_cast<const __nv_bfloat16*>(pos_table);
@@ -427,11 +457,12 @@ extern "C" int ovk_patch_embed(const void* images, int img_is_f32, const void* w
   CUtensorMap tmI, tmB, tmO;
   int rc;
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(3) * B};
-    uint64_t strides[2] = {static_cast<uint64_t>(W) * es, static_cast<uint64_t>(W) * H * es};
-    uint32_t box[3] = {static_cast<uint32_t>(a.xbox), static_cast<uint32_t>(R), 1};
-    rc = img_is_f32 ? make_tmap_nd_f32(&tmI, images, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)
-                    : make_tmap_nd_bf16(&tmI, images, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    // the image as (x, row inside the patch, patch row, channel x image): one box = R image rows of every patch row of a tile
+    uint64_t dims[4] = {static_cast<uint64_t>(W), static_cast<uint64_t>(P), static_cast<uint64_t>(H / P), static_cast<uint64_t>(3) * B};
+    uint64_t strides[3] = {static_cast<uint64_t>(W) * es, static_cast<uint64_t>(W) * P * es, static_cast<uint64_t>(W) * H * es};
+    uint32_t box[4] = {static_cast<uint32_t>(a.xbox), static_cast<uint32_t>(R), static_cast<uint32_t>(npy_box), 1};
+    rc = img_is_f32 ? make_tmap_nd_f32(&tmI, images, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)
+                    : make_tmap_nd_bf16(&tmI, images, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
     if (rc) return rc;
   }
   if ((rc = make_tmap_2d_bf16(&tmB, w_packed, Kp, D, Kp, 64, PE_BN))) return rc;
