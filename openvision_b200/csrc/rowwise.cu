@@ -34,7 +34,19 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   // registers for all of them (re-reading them per row costs four L1 loads per 16 bytes of data, which is what limited
   // the first version).  MAXV <= 4: RPW = 2 rows are loaded before either is touched (more bytes in flight per SM).
   constexpr int RPW = MAXV >= 8 ? 1 : 2;   // (host: rows per block = 8 * RPW)
-  constexpr bool GB_IN_REGS = MAXV <= 6;   // 16 * MAXV registers; wider rows read gamma / beta through L1 as before
+  constexpr bool GB_IN_REGS = MAXV <= 4;   // 16 * MAXV registers
+  // rows of 1025..1536 elements (H/14: 1280): gamma / beta in registers would cost 80-96 registers and leave one CTA per SM
+  // (measured 3.1 TB/s); they sit in shared memory instead (four conflict-free 16-byte loads per vector), wider rows read them
+  // through L1 as before
+  constexpr bool GB_IN_SMEM = MAXV == 5 || MAXV == 6;
+  __shared__ float gb_s[GB_IN_SMEM ? 2 * MAXV * 256 : 1];
+  if (GB_IN_SMEM) {
+    for (int c = threadIdx.x; c < MAXV * 256; c += blockDim.x) {
+      gb_s[c] = c < D ? gamma[c] : 0.f;
+      gb_s[MAXV * 256 + c] = c < D ? beta[c] : 0.f;
+    }
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int nvec = D >> 3;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
@@ -104,6 +116,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
           float4 a0, a1, c0, c1;
           if (GB_IN_REGS) {
             a0 = g0[i]; a1 = g1[i]; c0 = b0[i]; c1 = b1[i];
+          } else if (GB_IN_SMEM) {
+            a0 = *reinterpret_cast<const float4*>(gb_s + 8 * v);
+            a1 = *reinterpret_cast<const float4*>(gb_s + 8 * v + 4);
+            c0 = *reinterpret_cast<const float4*>(gb_s + MAXV * 256 + 8 * v);
+            c1 = *reinterpret_cast<const float4*>(gb_s + MAXV * 256 + 8 * v + 4);
           } else {
             a0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v);
             a1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1);

@@ -62,3 +62,13 @@ for (B, H, L) in ((1024, 16, 257), (1024, 16, 256), (256, 16, 1025)):
             res.setdefault(name, []).append(t(lambda: ops.attention(qkv, B, L, H, 64)))
     os.environ["OVK_ATT4_TRUNC"] = "0"
     print(f"attention4 B{B} H{H} L{L}: " + "  ".join(f"{k} {min(v):.3f} ms {fl / min(v) / 1e9:.0f} TF/s" for k, v in res.items()), flush=True)
+
+for (rows, D) in ((263168, 1024), (263168, 1280), (295424, 768)):
+    x = torch.randn(rows, D, device="cuda").bfloat16()
+    g, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    ms = t(lambda: ops.layernorm(x, g, b, 1e-6))
+    y, mean, rstd = ops.layernorm(x, g, b, 1e-6, save_stats=True)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    dy = torch.randn_like(x)
+    msb = t(lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=x))
+    print(f"layernorm rows {rows} D {D}: fwd {ms * 1e3:.0f} us {4.0 * rows * D / ms / 1e6:.0f} GB/s   bwd(+res) {msb * 1e3:.0f} us {8.0 * rows * D / msb / 1e6:.0f} GB/s", flush=True)
