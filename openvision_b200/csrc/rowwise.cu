@@ -583,6 +583,7 @@ extern "C" int ovk_layernorm_fwd(const void* x, long long ldx, void* y, long lon
   auto yp = reinterpret_cast<__nv_bfloat16*>(y);
   if (D <= 256) layernorm_fwd_kernel<1><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else if (D <= 512) layernorm_fwd_kernel<2><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
+  else if (D <= 768) layernorm_fwd_kernel<3><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);   // B/16
   else if (D <= 1024) layernorm_fwd_kernel<4><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
   else if (D <= 1280) layernorm_fwd_kernel<5><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);   // H/14
   else if (D <= 1536) layernorm_fwd_kernel<6><<<grid, 256, 0, s>>>(xp, ldx, yp, ldy, gamma, beta, mean, rstd, rows, D, eps);
@@ -628,6 +629,7 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
     }
     if (D <= 256) OVK_LNB_FUSED(1)
     else if (D <= 512) OVK_LNB_FUSED(2)
+    else if (D <= 768) OVK_LNB_FUSED(3)
     else if (D <= 1024) OVK_LNB_FUSED(4)
     else if (D <= 1280) OVK_LNB_FUSED(5)   // H/14: gamma in shared memory (see the kernel)
     else OVK_LNB_FUSED(6)
@@ -650,6 +652,7 @@ extern "C" int ovk_layernorm_bwd(const void* dy, long long lddy, const void* x, 
   const int grid = need_dx < 4 * num_sms() ? need_dx : 4 * num_sms();   // persistent: warps walk the rows with a grid stride
   if (D <= 256) layernorm_bwd_dx_kernel<1><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 512) layernorm_bwd_dx_kernel<2><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
+  else if (D <= 768) layernorm_bwd_dx_kernel<3><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 1024) layernorm_bwd_dx_kernel<4><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else if (D <= 1536) layernorm_bwd_dx_kernel<6><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
   else layernorm_bwd_dx_kernel<8><<<grid, 256, 0, s>>>(dyp, lddy, xp, ldx, gamma, mean, rstd, drp, lddres, dxp, lddx, rows, D);
