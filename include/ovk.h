@@ -104,6 +104,14 @@ int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, long long ldb,
                      int M, int N, int K, float alpha, const void* preact, long long ldp, int act, void* stream);
 int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int c_is_f32,
                      int M, int N, int K, float alpha, void* stream);
+/* ovk_gemm_bf16_nn with the fused GELU backward (C = alpha * (A B) (.) act'(preact), bf16) that ALSO leaves the partial column
+ * sums of C — the bias gradient of the layer whose pre-activation gradient it is (autograd: db = dU.sum(0), transformer.py:233
+ * c_fc) — in colsum_ws: f32 [ovk_gemm_colsum_rows(M)][N], one row per 64 rows of C, plain stores.  ovk_colsum_f32 reduces them
+ * (out ACCUMULATED: zero it first).  Replaces a stand-alone pass over the [M, N] tensor. */
+long long ovk_gemm_colsum_rows(int M);
+int ovk_gemm_bf16_nn_dact_colsum(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N,
+                                 int K, float alpha, const void* preact, long long ldp, int act, float* colsum_ws, void* stream);
+int ovk_colsum_f32(const float* x, int rows, int cols, float* out, void* stream);
 /* C[M,N] = alpha * (*alpha_dev) * op(A) * op(B), op = the storage flags below; bf16 operands, bf16 or (c_is_f32) fp32 output.
  *   a_mn = 0: A stored [M,K] (K contiguous);  a_mn = 1: A stored [K,M]
  *   b_mn = 0: B stored [N,K] (the nn.Linear layout);  b_mn = 1: B stored [K,N]           (a_mn = 1 with b_mn = 0 is not provided)

@@ -50,6 +50,10 @@ _PROTOTYPES = {
     "ovk_row_stats": (c_int, [c_void_p, c_longlong, c_void_p, c_int, c_int, c_void_p]),
     "ovk_gemm_bf16_nn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p, c_longlong, c_int, c_void_p]),
+    "ovk_gemm_colsum_rows": (c_longlong, [c_int]),
+    "ovk_gemm_bf16_nn_dact_colsum": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
+                                             c_float, c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "ovk_colsum_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ovk_gemm_bf16_tn": (c_int, [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_int, c_int,
                                  c_int, c_float, c_void_p]),
     "ovk_gemm_bf16_scaled": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int, c_void_p, c_longlong, c_int,

@@ -532,7 +532,11 @@ class _Block(torch.autograd.Function):
                 h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps)
             u = torch.empty((x_mid.shape[0], p["w1"].shape[0]), dtype=torch.bfloat16, device=x_mid.device)
             f = ops.gemm(h2, p["w1"], bias=p["c1"], act=act, preact_out=u)
-        du = ops.gemm_nn(dy, p["w2"], preact=u, act=act)                                    # (dY W2) . act'(u)
+        fc_b_fused = need_w and fc_b is not None and os.environ.get("OVK_COLSUM_FUSE", "1") != "0"
+        if fc_b_fused:   # the same GEMM also leaves db1 = dU.sum(0): no stand-alone pass over the [tokens, 4 D] tensor
+            du, g_fc_b = ops.gemm_nn_dact_colsum(dy, p["w2"], u, act)
+        else:
+            du = ops.gemm_nn(dy, p["w2"], preact=u, act=act)                                # (dY W2) . act'(u)
         g_pj_w = ops.gemm_tn(dy, f, out_dtype=_grad_dtype(pj_w)) if need_w else None
         g_pj_b = ops.colsum(dy) if need_w and pj_b is not None else None
         del f, u
@@ -544,7 +548,8 @@ class _Block(torch.autograd.Function):
             h2 = ops.layernorm(x_mid, p["g2"], p["b2"], blk.ln_2.eps) if need_w else None   # recomputed, not stored
         dh = ops.gemm_nn(du, p["w1"])
         g_fc_w = ops.gemm_tn(du, h2, out_dtype=_grad_dtype(fc_w)) if need_w else None
-        g_fc_b = ops.colsum(du) if need_w and fc_b is not None else None
+        if not fc_b_fused:
+            g_fc_b = ops.colsum(du) if need_w and fc_b is not None else None
         del du, h2
         dg2, db2 = torch.zeros_like(p["g2"]), torch.zeros_like(p["g2"])
         dxm = ops.layernorm_bwd(dh, x_mid, p["g2"], mean2, rstd2, dg2, db2, dx=dh, dres=dy)  # + residual gradient

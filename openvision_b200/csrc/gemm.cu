@@ -31,6 +31,9 @@ struct GemmEpi {
   // embedding (+ class token in row 0) added to the patch-embedding GEMM's output, transformer.py:615-617
   const __nv_bfloat16* row_add;
   int row_period;
+  // EPI_DACT: partial column sums of the OUTPUT (bf16-rounded, as autograd's bias gradient db = dU.sum(0) sees it):
+  // f32 [2 * ceil(M / 128)][N], one row per 64 output rows, plain stores (deterministic); reduced by ovk_colsum_f32.
+  float* colsum_ws;
 };
 
 // EPI_LINEAR: C = alpha*acc + bias (+ R)                   R  = residual tile [M,N] bf16 (tmR), may alias C
@@ -261,6 +264,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else tma_store_2d(&tmC, cx.c_stage(grp), ncol0, ti.m0);
           tma_store_commit();
         }
+        if constexpr (EPI == EPI_DACT && !OUT_F32) {
+          // bias gradient of the layer whose pre-activation gradient this GEMM writes: column sums of the staged bf16 tile
+          // (thread -> one column x 64 rows; the swizzle spreads a column's rows over the banks, lanes = consecutive columns:
+          // conflict-free 2-byte loads).  Saves the stand-alone pass that re-read the whole [M, N] tensor from HBM.  The
+          // staging buffer is rewritten only after the group's next barrier, which every thread reaches after these reads.
+          if (ep.colsum_ws != nullptr && ti.m0 < M) {   // (CTA pairs: the second CTA of the last pair may sit past the last row)
+            const int cc = et & 63, half = et >> 6;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int rr = 0; rr < 64; rr += 2) {
+              const int r0 = half * 64 + rr;
+              unsigned short a, b;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(a) : "r"(sbuf + sw128_offset(r0, cc >> 3) + (cc & 7) * 2));
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(b) : "r"(sbuf + sw128_offset(r0 + 1, cc >> 3) + (cc & 7) * 2));
+              s0 += __uint_as_float(static_cast<uint32_t>(a) << 16);
+              s1 += __uint_as_float(static_cast<uint32_t>(b) << 16);
+            }
+            if (ncol0 + cc < N) ep.colsum_ws[static_cast<long long>((ti.m0 >> 7) * 2 + half) * N + ncol0 + cc] = s0 + s1;
+          }
+        }
       }
       if constexpr (FUSE) {
         // one slot per (row, 128 output columns) = per epilogue group of a 256-wide tile: plain stores, no atomics
@@ -454,6 +477,25 @@ extern "C" int ovk_gemm_bf16_nn(const void* A, long long lda, const void* B, lon
   if (preact) return launch_gemm_bn<false, true, EPI_DACT, false>(g, s);
   if (c_is_f32) return launch_gemm_bn<false, true, EPI_LINEAR, true>(g, s);
   return launch_gemm_bn<false, true, EPI_LINEAR, false>(g, s);
+}
+
+extern "C" long long ovk_gemm_colsum_rows(int M) { return 2LL * ((M + GEMM_BM - 1) / GEMM_BM); }
+
+extern "C" int ovk_gemm_bf16_nn_dact_colsum(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,
+                                            int M, int N, int K, float alpha, const void* preact, long long ldp, int act,
+                                            float* colsum_ws, void* stream) {
+  GemmArgs g{A, lda, false, B, ldb, true, C, ldc, false, nullptr, 0, nullptr, 0, M, N, K, {}, EPI_LINEAR};
+  if (!preact || !(act & OVK_EPI_ACT_MASK)) return set_error(OVK_ERR_SHAPE, "gemm_nn_dact_colsum: preact and an activation id are required");
+  if (!colsum_ws) return set_error(OVK_ERR_SHAPE, "gemm_nn_dact_colsum: workspace required (f32 [ovk_gemm_colsum_rows(M)][N])");
+  g.ep.bias = nullptr;
+  g.ep.alpha = alpha;
+  g.ep.flags = 0;
+  g.ep.act = act_coef(act & OVK_EPI_ACT_MASK);
+  g.ep.colsum_ws = colsum_ws;
+  g.R = preact, g.ldr = ldp;
+  int rc = check_common(g, "gemm_nn_dact_colsum");
+  if (rc) return rc;
+  return launch_gemm_bn<false, true, EPI_DACT, false>(g, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ovk_gemm_bf16_tn(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc,

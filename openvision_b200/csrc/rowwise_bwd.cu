@@ -202,6 +202,37 @@ static int grid_for_b(long long work_items, int block) {
 
 using namespace ovk;
 
+// out[c] (+)= sum_r x[r][c] for an fp32 [rows, cols] matrix (the partial column sums a GEMM epilogue left behind)
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ x, int rows, int cols, int rows_per_block,
+                                                         float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += x[static_cast<long long>(r) * cols + c];
+    s1 += x[static_cast<long long>(r + 1) * cols + c];
+    s2 += x[static_cast<long long>(r + 2) * cols + c];
+    s3 += x[static_cast<long long>(r + 3) * cols + c];
+  }
+  for (; r < r1; ++r) s0 += x[static_cast<long long>(r) * cols + c];
+  atomicAdd(out + c, (s0 + s1) + (s2 + s3));
+}
+
+extern "C" int ovk_colsum_f32(const float* x, int rows, int cols, float* out, void* stream) {
+  if (rows <= 0 || cols <= 0) return set_error(OVK_ERR_SHAPE, "colsum_f32: empty input");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int gx = (cols + 255) / 256;
+  int gy = (4 * num_sms() + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  const int rpb = (rows + gy - 1) / gy;
+  gy = (rows + rpb - 1) / rpb;
+  colsum_f32_kernel<<<dim3(gx, gy), 256, 0, s>>>(x, rows, cols, rpb, out);
+  return check_launch("colsum_f32_kernel");
+}
+
 extern "C" int ovk_colsum_bf16(const void* x, long long ldx, int rows, int cols, float* out, void* stream) {
   if (rows <= 0 || cols <= 0) return set_error(OVK_ERR_SHAPE, "colsum: empty input");
   if ((cols % 8) || (ldx % 8)) return set_error(OVK_ERR_ALIGN, "colsum: cols and ldx must be multiples of 8");

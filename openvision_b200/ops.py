@@ -240,6 +240,31 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torc
     return out
 
 
+def gemm_nn_dact_colsum(a: torch.Tensor, b: torch.Tensor, preact: torch.Tensor, act: str):
+    """(out, colsum): out[M,N] = (a[M,K] @ b[K,N]) * act'(preact) in bf16, and colsum[N] = out.sum(0) in fp32 — the bias
+    gradient of the layer whose pre-activation gradient `out` is — taken from the GEMM epilogue's staged tiles instead of
+    a second pass over out.  Kernels: gemm_bf16_kernel<EPI_DACT> + colsum_f32_kernel."""
+    _require(a, torch.bfloat16, "gemm_nn_dact_colsum.a", 2)
+    _require(b, torch.bfloat16, "gemm_nn_dact_colsum.b", 2)
+    _require(preact, torch.bfloat16, "gemm_nn_dact_colsum.preact", 2)
+    M, K = a.shape
+    K2, N = b.shape
+    if K2 != K or tuple(preact.shape) != (M, N):
+        raise OvkError("gemm_nn_dact_colsum: shape mismatch")
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    rows = _lib.load().ovk_gemm_colsum_rows(M)
+    ws = torch.empty((rows, N), dtype=torch.float32, device=a.device)
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.call("ovk_gemm_bf16_nn_dact_colsum", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, 1.0,
+                  _p(preact), preact.stride(0), _ACT[act], _p(ws), _stream())
+    _count()
+    cs = torch.zeros(N, dtype=torch.float32, device=a.device)
+    with _timed("colsum", 4.0 * rows * N):
+        _lib.call("ovk_colsum_f32", _p(ws), rows, N, _p(cs), _stream())
+    _count()
+    return out, cs
+
+
 def gemm_tn(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out_dtype=torch.bfloat16,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = alpha * a[K,M]^T @ b[K,N]  (both row-major: the wgrad dW = dY^T @ X, the loss dT = s G^T I)."""

@@ -300,3 +300,25 @@ def test_attention_bwd_remainder_token_outside_the_tiles(ops, B, L, H, hd, monke
         assert_grad(g[:, :, i], r[:, :, i], f"d{name} (all rows)", 3e-2)
         assert_grad(g[:, L - 1, i], r[:, L - 1, i], f"d{name} (remainder row)", 3e-2)
         assert_grad(g[:, :, i], g2[:, :, i], f"d{name}: tail path vs all-tiles path", 2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1000, 512, 128, "gelu"), (4096, 1024, 256, "gelu_tanh"), (777, 3072, 768, "quick_gelu"),
+                                       (263, 256, 64, "gelu"), (808, 768, 192, "gelu"), (640, 512, 128, "gelu")])
+def test_gelu_backward_gemm_leaves_the_bias_gradient(ops, M, N, K, act):
+    """dU = (dY W2) . act'(u) with db1 = dU.sum(0) out of the same GEMM's epilogue (transformer.py:232-236 backward): the
+    output must be bitwise the plain fused GELU' GEMM, the column sums those of the bf16 output."""
+    dy = rnd(M, K, seed=1).bfloat16().cuda()
+    w = rnd(K, N, seed=2, scale=0.1).bfloat16().cuda()
+    u = rnd(M, N, seed=3).bfloat16().cuda()
+    ref = ops.gemm_nn(dy, w, preact=u, act=act)
+    # canary behind the workspace the wrapper is about to allocate from the same pool: the kernel must not write past its rows
+    # (CTA pairs: the second CTA of the last pair can sit past the last row of the matrix)
+    rows = ops._lib.load().ovk_gemm_colsum_rows(M)
+    big = torch.empty((rows + 8, N), dtype=torch.float32, device="cuda")
+    big[rows:] = 12345.0
+    del big
+    out, cs = ops.gemm_nn_dact_colsum(dy, w, u, act)
+    assert torch.equal(out, ref)
+    want = ref.float().sum(0)
+    assert_close_vec = (cs - want).abs().max().item()
+    assert assert_close_vec <= 1e-4 * want.abs().max().item() + 1e-3, assert_close_vec
