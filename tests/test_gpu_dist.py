@@ -37,6 +37,20 @@ def _worker(rank, world, port, outdir, cases):
         torch.cuda.synchronize()
         out[(n, e, local_loss, gwg)] = dict(loss=loss.detach().cpu(), d_img=img_l.grad.cpu(), d_txt=txt_l.grad.cpu(),
                                             d_ls=ls.grad.cpu())
+    # the reference composition (gather_features + get_logits + cross-entropy, loss.py:19-63,102-131) on the same NCCL group:
+    # loss and gradients through the gathers, for the mode DDP training uses
+    n, e, seed = 256, 64, 11
+    img, txt = synth.make_features(n, e, seed=seed)
+    nl = n // world
+    img_l = img[rank * nl:(rank + 1) * nl].cuda().requires_grad_(True)
+    txt_l = txt[rank * nl:(rank + 1) * nl].cuda().requires_grad_(True)
+    ls = torch.tensor(float(np.log(1 / 0.07)), device="cuda", requires_grad=True)
+    crit = ovb.ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+    li, lt = crit.get_logits(img_l, txt_l, ls.exp())
+    labels = crit.get_ground_truth(li.device, li.shape[0])
+    comp = (torch.nn.functional.cross_entropy(li, labels) + torch.nn.functional.cross_entropy(lt, labels)) / 2
+    comp.backward()
+    out["get_logits"] = dict(loss=comp.detach().cpu(), logits=li.detach().cpu(), d_img=img_l.grad.cpu(), d_txt=txt_l.grad.cpu())
     torch.save(out, os.path.join(outdir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -83,3 +97,26 @@ def test_nccl_two_rank_loss_matches_reference_and_single_gpu(golden):
             assert rel.item() <= 2e-2, (n, k, rel.item())
         gs = np.mean([float(x["d_ls"]) for x in xs])
         assert abs(gs - float(ls.grad)) <= 2e-2 * abs(float(ls.grad)) + 1e-6
+
+    # (c) gather_features + get_logits over NCCL: rank r's logits block = rows r of the global matrix; the composed loss equals
+    # the fused one on the same features; gradients through the gathers equal the fused path's
+    n, e, seed = 256, 64, 11
+    img, txt = synth.make_features(n, e, seed=seed)
+    z = float(1 / 0.07) * (img.bfloat16().float() @ txt.bfloat16().float().t())
+    nl = n // world
+    for r in range(world):
+        x = res[r]["get_logits"]
+        assert (x["logits"] - z[r * nl:(r + 1) * nl]).abs().max().item() <= 2e-2 * z.abs().max().item()
+        i_r = img[r * nl:(r + 1) * nl].cuda().requires_grad_(True)
+        t_r = txt[r * nl:(r + 1) * nl].cuda().requires_grad_(True)
+    i1 = img.cuda().requires_grad_(True)
+    t1 = txt.cuda().requires_grad_(True)
+    ls = torch.tensor(float(np.log(1 / 0.07)), device="cuda", requires_grad=True)
+    l1 = ovb.ClipLoss()(i1, t1, ls.exp())
+    l1.backward()
+    mean_loss = np.mean([float(res[r]["get_logits"]["loss"]) for r in range(world)])
+    assert abs(mean_loss - float(l1)) <= 2e-3 * abs(float(l1))
+    for k, ref in (("d_img", i1.grad), ("d_txt", t1.grad)):
+        got = torch.cat([res[r]["get_logits"][k] for r in range(world)]) / world
+        rel = (got - ref.cpu()).norm() / ref.cpu().norm()
+        assert rel.item() <= 3e-2, (k, rel.item())
