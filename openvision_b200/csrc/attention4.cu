@@ -129,7 +129,10 @@ struct A4Item {
 // DBG (only with -DOVK_ATT4_DEBUG_VARIANTS, tools/attn_knockout.py): knock-outs that make the RESULT WRONG but show what a
 // softmax step spends its time on: bit 0 no exponentials / packing, bit 1 no row maximum, bit 2 no P stores, bit 3 no score loads,
 // bit 4 no epilogue work, bit 5 no S / P V MMAs, bit 6 no HBM traffic (every item reads and writes head 0 of image 0).
-template <bool TRUNC, int DBG = 0>
+// MODE specialises the softmax step for the shapes that matter (the kernel is bound by the instruction stream of its softmax
+// warps, so dead branches cost): 0 generic; 1 Lm a multiple of 64 and no remainder token (L = 256, 512, ...): no column masks,
+// no remainder-token code at all; 2 Lm a multiple of 64 with the remainder token (L = 257: the ViT-L/14@224 tower).
+template <bool TRUNC, int DBG = 0, int MODE = 0>
 __global__ void __launch_bounds__(A4_THREADS, 1)
 attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmRow, float* __restrict__ lse_out,
@@ -147,7 +150,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const int npair = (nq + 1) >> 1;
   const int nkv = (Lm + A4_BKV - 1) / A4_BKV;
   const int nhb = (Lm + A4_HB - 1) / A4_HB;
-  const bool tail = L > Lm;   // one remainder token (host guarantees L - Lm <= 1, and then Lm % 128 == 0)
+  const bool tail = MODE == 1 ? false : MODE == 2 ? true : L > Lm;   // one remainder token (host guarantees L - Lm <= 1, and then Lm % 128 == 0)
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
@@ -537,7 +540,7 @@ attention_fwd4_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       for (int hb = 0; hb < nhb; ++hb, ++t) {
         const int half = hb & 1;
         const uint32_t e = t & 1;
-        const int valid = min(A4_HB, Lm - hb * A4_HB);
+        const int valid = MODE != 0 ? A4_HB : min(A4_HB, Lm - hb * A4_HB);
         const uint32_t t_s = t_sw + 64 * e;
         mbar_wait(&bars[A4_B_SFULL + 2 * w + e], (t >> 1) & 1, 47);
         tc_fence_after();
@@ -724,8 +727,16 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
   }
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
+    cudaError_t e = cudaSuccess;
+    auto set_attr = [&](auto kern) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM);
+    };
+    set_attr(attention_fwd4_kernel<false, 0, 0>);
+    set_attr(attention_fwd4_kernel<false, 0, 1>);
+    set_attr(attention_fwd4_kernel<false, 0, 2>);
+    set_attr(attention_fwd4_kernel<true, 0, 0>);
+    set_attr(attention_fwd4_kernel<true, 0, 1>);
+    set_attr(attention_fwd4_kernel<true, 0, 2>);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention4): %s", cudaGetErrorString(e));
     attr_once.done();
   }
@@ -756,11 +767,17 @@ int ovk_attention_fwd4_launch(const void* qkv, void* out, float* lse, int B, int
 #undef OVK_A4_DBG_CASE
   }
 #endif
-  if (trunc)
-    attention_fwd4_kernel<true><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
-                                                                 l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f, stagger);
-  else
-    attention_fwd4_kernel<false><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), L,
-                                                                  l_main, H, nq, static_cast<int>(items), scale * 1.4426950408889634f, stagger);
+  const char* gen = getenv("OVK_ATT4_GENERIC");   // =1: the unspecialised instance for every shape (A/B, tests)
+  const int mode = (gen != nullptr && gen[0] == '1') || (l_main % A4_HB) != 0 ? 0 : (tail ? 2 : 1);
+#define OVK_A4_LAUNCH(TR, MD)                                                                                                 \
+  attention_fwd4_kernel<TR, 0, MD><<<grid, A4_THREADS, A4_SMEM, s>>>(tmQKV, tmO, tmRow, lse, reinterpret_cast<__nv_bfloat16*>(out), \
+                                                                    L, l_main, H, nq, static_cast<int>(items),                 \
+                                                                    scale * 1.4426950408889634f, stagger)
+  if (trunc) {
+    if (mode == 1) OVK_A4_LAUNCH(true, 1); else if (mode == 2) OVK_A4_LAUNCH(true, 2); else OVK_A4_LAUNCH(true, 0);
+  } else {
+    if (mode == 1) OVK_A4_LAUNCH(false, 1); else if (mode == 2) OVK_A4_LAUNCH(false, 2); else OVK_A4_LAUNCH(false, 0);
+  }
+#undef OVK_A4_LAUNCH
   return check_launch("attention_fwd4_kernel");
 }
