@@ -15,6 +15,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    """A TCP port the OS just handed out on 127.0.0.1 (fixed numbers collide with sockets in TIME_WAIT)."""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def _worker(rank, world, local_loss, gwg, port, outdir):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -44,7 +52,7 @@ def _worker(rank, world, local_loss, gwg, port, outdir):
 @pytest.mark.parametrize("local_loss,gwg", [(True, True), (False, False), (False, True)])
 def test_multirank_loss_matches_reference(golden, world, local_loss, gwg):
     g = golden(f"loss_dist_W{world}_N64_E32_local{int(local_loss)}_gwg{int(gwg)}.npz")
-    port = 29700 + world * 10 + int(local_loss) * 2 + int(gwg)
+    port = _free_port()
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(world, local_loss, gwg, port, d), nprocs=world, join=True)
         res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
@@ -105,7 +113,7 @@ def test_gather_features_semantics(local_loss, gwg):
     from oracle import synth
     world = 2
     img, txt = synth.make_features(16, 8, seed=5, dtype=torch.float64)
-    port = 29810 + int(local_loss) * 2 + int(gwg)
+    port = _free_port()
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_gather_worker, args=(world, local_loss, gwg, port, d), nprocs=world, join=True)
         res = [torch.load(os.path.join(d, f"g{r}.pt")) for r in range(world)]
@@ -158,7 +166,7 @@ def test_bucketed_gradient_all_reduce_overlaps_and_sums():
     post-accumulate-grad hooks while backward is still running; result = sum of the ranks' gradients, on every rank."""
     world = 2
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_reducer_worker, args=(world, 29791, d), nprocs=world, join=True)
+        mp.spawn(_reducer_worker, args=(world, _free_port(), d), nprocs=world, join=True)
         res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
     torch.manual_seed(0)
     model = torch.nn.Sequential(torch.nn.Linear(24, 40), torch.nn.GELU(), torch.nn.Linear(40, 40), torch.nn.GELU(),

@@ -12,6 +12,13 @@ import torch
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 pytestmark = pytest.mark.gpu
 
 
@@ -65,7 +72,7 @@ def test_nccl_two_rank_loss_matches_reference_and_single_gpu(golden):
     cases = [(64, 32, True, True, 96), (64, 32, False, False, 96), (64, 32, False, True, 96),
              (2048, 256, True, True, 7), (1280, 768, True, True, 8)]      # 1280 / 2 = 640 rows per rank: odd number of row tiles
     with tempfile.TemporaryDirectory() as d:
-        mp.spawn(_worker, args=(world, 29911, d, cases), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), d, cases), nprocs=world, join=True)
         res = [torch.load(os.path.join(d, f"r{r}.pt")) for r in range(world)]
     # (a) the reference under gloo, three modes
     for (local_loss, gwg) in ((True, True), (False, False), (False, True)):
