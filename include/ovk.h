@@ -221,6 +221,16 @@ int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, con
  * (class token + power-of-two grid) is handled outside the 128-wide tiles (attention_bwd_tail_kernel + rank-1 terms in the
  * tile kernels' epilogues) instead of as a third tile row / column; the function returns 0 when the shape has no such token. */
 long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int flags);
+/* One-pass backward (the default of the Python mirror): the score tiles are walked ONCE (key tile stationary, query tiles
+ * streamed): dK / dV accumulate in TMEM as above, and the partial dQ = dS K of every (query tile, key tile) is added into an
+ * fp32 [B, L, H, hd] scratch by TMA reduce-add, then converted (x scale) into the q slot of dqkv.  10 instead of 14
+ * B H L^2 hd FLOPs and half the exponentials of ovk_attention_bwd_ex, same results up to the fp32 summation order of dQ.
+ * workspace: f32[ovk_attention_bwd_fused_workspace_floats(B, L, H, hd, flags)], required (0 = shape not offered); it also
+ * holds the remainder-token vectors of ovk_attention_bwd_workspace_floats.  delta as above.
+ * Launches: attention_bwd_delta_kernel, (attention_bwd_tail_kernel,) attention_bwd_kernel<fused>, attention_bwd_dq_convert_kernel. */
+long long ovk_attention_bwd_fused_workspace_floats(int B, int L, int H, int hd, int flags);
+int ovk_attention_bwd_fused(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
+                            float* workspace, int B, int L, int H, int hd, float scale, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Pooling head, transformer.py:599-607,638-646.

@@ -79,6 +79,9 @@ _PROTOTYPES = {
     "ovk_attention_fwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p]),
     "ovk_attention_bwd_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_int, c_float, c_int, c_void_p]),
+    "ovk_attention_bwd_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_int, c_float, c_int, c_void_p]),
+    "ovk_attention_bwd_fused_workspace_floats": (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
     "ovk_attention_bwd_workspace_floats": (c_longlong, [c_int, c_int, c_int, c_int]),
     "ovk_pool_tokens_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "ovk_l2_normalize_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_float, c_void_p]),

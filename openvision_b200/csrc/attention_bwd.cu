@@ -13,6 +13,16 @@
 // wait for the same event (the softmax warps are done with S / dP), and the softmax warps need the next S / dP first.
 // The bf16 P / dS tile lives in shared memory as [q rows][kv cols] with 128-byte swizzled rows: the same bytes serve as
 // a K-major A operand (dS K) and as an MN-major A operand (P^T dO, dS^T Q), so no transpose is ever materialised.
+//
+//   MODE_FUSED (default path): ONE pass over the score tiles instead of two.  The DKV walk above, plus per streamed query
+//   tile the fifth MMA dQ_i(partial) = dS K_j into its own TMEM columns, which the softmax warps drain (TMEM -> fp32 rows
+//   in shared memory, each warp its own 32 rows) and add into an fp32 [B, L, H, hd] scratch with TMA reduce-add
+//   (cp.reduce.async.bulk.tensor .add): S, dP, P and dS are computed once (10 instead of 14 B H L^2 hd FLOPs, half the
+//   exponentials).  A CTA walks a CONTIGUOUS run of items (key tile fastest), so the partial sums of one (image, head)
+//   meet in L2.  D = rowsum(dO . O) comes from attention_bwd_delta_kernel, and attention_bwd_dq_convert_kernel turns the
+//   scratch into the bf16 q slot of d(qkv) (x scale, + the remainder token's rank-1 term).
+#include <algorithm>
+
 #include "host_utils.h"
 #include "ptx.cuh"
 
@@ -45,7 +55,18 @@ constexpr int AB_OFF_SBB = AB_OFF_SAB + 2 * AB_BT;    // x2
 constexpr int AB_OFF_XB = AB_OFF_SBB + 2 * AB_BT;
 constexpr int AB_OFF_OUTB = AB_OFF_XB + AB_BT;        // x2 output staging
 constexpr int AB_SMEM_BYTES_RB = AB_OFF_OUTB + 2 * AB_BT;
-constexpr uint32_t AB_TM_ACC0B = 384, AB_TM_ACC1B = 400;
+constexpr uint32_t AB_TM_ACC0B = 448, AB_TM_ACC1B = 464;
+constexpr uint32_t AB_TM_DQ = 384, AB_TM_DQB = 480;   // MODE_FUSED: per-iteration dQ partial (64 + 16 columns)
+// MODE_FUSED: fp32 staging of the dQ partial, one [32 rows x 128 B] SWIZZLE_128B region per softmax warp.
+//   hd = 64: tiles 12, 13 (the second stationary set moves to tiles 10, 11: X is not loaded in this mode)
+//   wide heads: X (column half 0), XB + three regions behind the narrow tiles (column half 1); the 16 narrow columns are
+//   staged in OUTB (dense 64-byte rows), which the item's epilogue reuses for its narrow output tiles.
+constexpr int AB_DQ_REGION = 32 * 128;
+constexpr int AB_OFF_DQST = AB_OFF_ST2 + AB_TILE;
+constexpr int AB_OFF_DQX = AB_SMEM_BYTES_RB;
+constexpr int AB_SMEM_BYTES_RB_FUSED = AB_OFF_DQX + 3 * AB_DQ_REGION;
+static_assert(AB_SMEM_BYTES_RB_FUSED <= 232448 && AB_SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(AB_OFF_DQX % 1024 == 0, "dQ staging regions must be 1024-byte aligned");
 constexpr uint32_t AB_SW32 = 6;
 __device__ __forceinline__ uint64_t ab_desc_sw32(uint32_t saddr) { return umma_desc(saddr, 16, 256, AB_SW32); }
 __device__ __forceinline__ uint32_t ab_sw32_offset(uint32_t row, uint32_t chunk) {
@@ -53,7 +74,7 @@ __device__ __forceinline__ uint32_t ab_sw32_offset(uint32_t row, uint32_t chunk)
 }
 constexpr int AB_TMEM_COLS = 512;
 constexpr uint32_t AB_TM_S = 0, AB_TM_DP = 128, AB_TM_ACC0 = 256, AB_TM_ACC1 = 320;
-enum { MODE_DQ = 0, MODE_DKV = 1 };
+enum { MODE_DQ = 0, MODE_DKV = 1, MODE_FUSED = 2 };
 
 template <int MODE, int RB>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -63,7 +84,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
                      const float* __restrict__ lse, float* __restrict__ delta, int L, int H, float scale, int total_items,
                      int causal, int Lm, const float* __restrict__ ws, const __nv_bfloat16* __restrict__ qkv_g,
-                     const __nv_bfloat16* __restrict__ dout_g, int hd_g) {
+                     const __nv_bfloat16* __restrict__ dout_g, int hd_g, const __grid_constant__ CUtensorMap tmDQF,
+                     const __grid_constant__ CUtensorMap tmDQFb, int per) {
   // Lm < L (= L - 1, remainder token of L = 128 k + 1): the tiles cover tokens [0, Lm) only; the remainder token's query
   // row and key / value row are computed by attention_bwd_tail_kernel, which also leaves, per (image, head), the three
   // vectors the epilogues below add as rank-1 terms: ws[0][i] = dS(i, t), ws[1][j] = P(t, j), ws[2][j] = dS(t, j).
@@ -89,13 +111,21 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const int nt = (Lm + AB_T - 1) / AB_T;  // tiles per sequence: stationary tiles of an item, streamed tiles per item
   const float s2 = scale * 1.4426950408889634f;
   // stationary tile `which` (0: ST0, 1: ST1, 2: X) of set `buf`
-  auto st_off = [](int buf, int which) { return buf == 0 ? (which == 0 ? AB_OFF_ST0 : which == 1 ? AB_OFF_ST1 : AB_OFF_X)
-                                                         : AB_OFF_ST2 + which * AB_TILE; };
+  auto st_off = [](int buf, int which) {
+    if (MODE == MODE_FUSED && buf == 1) return which == 0 ? AB_OFF_X : AB_OFF_ST2;   // tiles 12, 13: dQ staging
+    return buf == 0 ? (which == 0 ? AB_OFF_ST0 : which == 1 ? AB_OFF_ST1 : AB_OFF_X) : AB_OFF_ST2 + which * AB_TILE;
+  };
+  // work items of this CTA: MODE_FUSED walks a contiguous run (key tiles of one (image, head) back to back: their dQ
+  // partial sums meet in L2), the two-pass kernels stride by the grid
+  const int item_first = (MODE == MODE_FUSED) ? blockIdx.x * per : blockIdx.x;
+  const int item_last = (MODE == MODE_FUSED) ? min(total_items, item_first + per) : total_items;
+  const int item_step = (MODE == MODE_FUSED) ? 1 : gridDim.x;
 
   if (warp == AB_SOFTMAX_WARPS && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQKV);
+    if (MODE == MODE_FUSED) tma_prefetch_desc(&tmDQF);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&st_full[i], 1);
       mbar_init(&st_empty[i], 1 + (MODE == MODE_DQ ? 32 * AB_SOFTMAX_WARPS : 0));
@@ -118,7 +148,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     if (elect_one()) {
       // ------------------------------------------------------------------ TMA producer
       int n = 0, g = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+      for (int item = item_first; item < item_last; item += item_step, ++n) {
         const int t0 = (item % nt) * AB_T, h = (item / nt) % H, b = item / (nt * H);
         const int buf = n % NST;
         uint64_t* stf = &st_full[buf];
@@ -171,7 +201,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t p_addr = smem_u32(smem + AB_OFF_P), ds_addr = smem_u32(smem + AB_OFF_DS);
       const uint32_t st0b = smem_u32(smem + AB_OFF_ST0B), st1b = smem_u32(smem + AB_OFF_ST1B);
       int n = 0, g = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+      for (int item = item_first; item < item_last; item += item_step, ++n) {
         const int t0 = (item % nt) * AB_T;
         const int buf = n % NST;
         const uint32_t st0 = smem_u32(smem + st_off(buf, 0)), st1 = smem_u32(smem + st_off(buf, 1));
@@ -256,6 +286,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                              ab_desc_sw32(qb_addr + kk * 512), idescb, (it | kk) != 0);
             }
           }
+          if (MODE == MODE_FUSED) {
+            // dQ_i (partial over this key tile) = dS K_j, fresh every iteration: the softmax warps drained the previous one
+            // before they arrived on pds_ready (it > 0) / acc_free (it = 0)
+            constexpr uint32_t idq = umma_idesc_bf16(AB_T, AB_HD, 0, 1);
+            for (int kk = 0; kk < nkv / 16; ++kk)
+              umma_bf16_ss(tmem_base + AB_TM_DQ, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                           umma_desc_mnmajor_sw128(k_addr + kk * 2048, AB_TILE), idq, kk != 0);
+            if (RB) {
+              constexpr uint32_t idqb = umma_idesc_bf16(AB_T, 16, 0, 1);
+              for (int kk = 0; kk < nkv / 16; ++kk)
+                umma_bf16_ss(tmem_base + AB_TM_DQB, umma_desc_kmajor_sw128(ds_addr + (kk >> 2) * AB_TILE + (kk & 3) * 32),
+                             ab_desc_sw32(kb_addr + kk * 512), idqb, kk != 0);
+            }
+          }
           umma_commit(&se[s]);
           umma_commit(mma_done);
           if (it == nt - 1) umma_commit(&st_empty[buf]);   // the item's stationary tiles are no longer read by any MMA
@@ -269,11 +313,45 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const int r = quad * 32 + lane;       // query row inside the tile = TMEM lane
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     int n = 0, g = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++n) {
+    for (int item = item_first; item < item_last; item += item_step, ++n) {
     const int t0 = (item % nt) * AB_T, h = (item / nt) % H, b = item / (nt * H);
     const int buf = n % NST;
     const long long bh = static_cast<long long>(b) * H + h;
     float lse2 = INFINITY, dlt = 0.f;
+    // MODE_FUSED: the dQ partial of the query tile at q0 leaves TMEM: fp32 rows into this warp's own staging region, then
+    // one TMA reduce-add per warp (32 rows x 32 columns) into the fp32 scratch.  No CTA-wide synchronisation: the region
+    // is private to the warp, whose lane 0 issued (and waits for) the previous reduce.
+    auto drain_dq = [&](int q0) {
+      if (q0 + quad * 32 >= Lm) return;   // warp-uniform: nothing but clipped rows
+      tc_fence_after();                   // behind the mma_done wait of the caller
+      uint32_t o[32];
+      tmem_ld_x32(tmem_base + t_lane + AB_TM_DQ + hsel * 32, o);
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      uint32_t region;
+      if (RB) region = hsel == 0 ? AB_OFF_X + quad * AB_DQ_REGION : (quad == 0 ? AB_OFF_XB : AB_OFF_DQX + (quad - 1) * AB_DQ_REGION);
+      else region = AB_OFF_DQST + hsel * AB_TILE + quad * AB_DQ_REGION;
+      const uint32_t dst = smem_u32(smem + region);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        sts128(dst + sw128_offset(lane, q), make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+      if (RB && hsel == 0) {
+        uint32_t ob[16];
+        tmem_ld_x16(tmem_base + t_lane + AB_TM_DQB, ob);
+        tmem_ld_wait();
+        const uint32_t dstb = smem_u32(smem + AB_OFF_OUTB + quad * (32 * 64)) + lane * 64;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sts128(dstb + q * 16, make_uint4(ob[4 * q], ob[4 * q + 1], ob[4 * q + 2], ob[4 * q + 3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
+        if (RB && hsel == 0) tma_reduce_add_4d(&tmDQFb, smem + AB_OFF_OUTB + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+        tma_store_commit();
+      }
+    };
     // the previous item's output tiles (staged in the P region) must have left shared memory before P / dS are rewritten
     if (threadIdx.x == 0) tma_store_wait_read<0>();
     named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
@@ -316,7 +394,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       // is the same per-element masking as the columns past the end of the sequence, with a per-thread column count
       const int qrow = ((MODE == MODE_DQ) ? t0 : it * AB_T) + r;
       const int kmax = causal ? min(valid_kv, qrow - kv0 + 1) : valid_kv;
-      if (MODE == MODE_DKV) {
+      if (MODE != MODE_DQ) {
         const int row = it * AB_T + r;
         lse2 = row < Lm ? lse[bh * L + row] * 1.4426950408889634f : INFINITY;
         dlt = row < Lm ? delta[bh * L + row] : 0.f;
@@ -324,6 +402,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_wait(s_full, g & 1, 25);
       tc_fence_after();
       if (g > 0) mbar_wait(mma_done, (g - 1) & 1, 26);  // previous accumulating MMAs no longer read P / dS
+      if (MODE == MODE_FUSED && it > 0) drain_dq((it - 1) * AB_T);
       // Which parts of the P / dS tile the accumulating MMAs read (the rest may hold anything: it only reaches output
       // rows that the TMA store clips).  DQ: A = dS[q rows][keys < nkv].  DKV: A = (P | dS)^T, contraction over the first
       // nq query rows, key columns >= valid_kv only feed clipped dK / dV rows.  With L = 128 k + 1 most of the remainder
@@ -367,7 +446,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const uint32_t chunk0 = c >> 3;  // 16-byte chunk inside the 64-column atom
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          if (MODE == MODE_DKV)
+          if (MODE != MODE_DQ)
             sts128(smem_u32(smem + AB_OFF_P + hsel * AB_TILE) + sw128_offset(r, chunk0 + q),
                    make_uint4(pp[4 * q], pp[4 * q + 1], pp[4 * q + 2], pp[4 * q + 3]));
           sts128(smem_u32(smem + AB_OFF_DS + hsel * AB_TILE) + sw128_offset(r, chunk0 + q),
@@ -381,6 +460,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     // -------------------------------------------------------------------- epilogue: accumulators -> bf16 -> TMA store
     mbar_wait(mma_done, (g - 1) & 1, 27);
     tc_fence_after();
+    if (MODE == MODE_FUSED) {
+      drain_dq((nt - 1) * AB_T);
+      if (RB) {   // the narrow output tiles below reuse OUTB: every warp's narrow reduce must have read it
+        if (lane == 0) tma_store_wait_read<0>();
+        named_bar_sync(1, 32 * AB_SOFTMAX_WARPS);
+      }
+    }
     // staging reuses the P region: atom 0 <- ACC0 (dQ or dK), atom 1 <- ACC1 (dV)
     // rank-1 terms of the remainder token (see the kernel header): coefficient of this thread's row, and the row of the
     // packed qkv / dout tensors that multiplies it
@@ -465,7 +551,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                             pack_bf16x2(__uint_as_float(o[8 * q + 6]) * mul, __uint_as_float(o[8 * q + 7]) * mul)));
       }
     }
-    if (RB && (MODE == MODE_DKV || hsel == 0)) {
+    if (RB && (MODE != MODE_DQ || hsel == 0)) {
       // narrow accumulators: DQ: dQ_b (hsel 0); DKV: dK_b (hsel 0, scaled), dV_b (hsel 1)
       const float mulb = (MODE == MODE_DQ || hsel == 0) ? scale : 1.f;
       const uint32_t srcb = (MODE == MODE_DQ || hsel == 0) ? AB_TM_ACC0B : AB_TM_ACC1B;
@@ -501,7 +587,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       tma_store_commit();
     }
     }   // items
-    if (threadIdx.x == 0) tma_store_wait_all<0>();
+    if (threadIdx.x == 0 || (MODE == MODE_FUSED && lane == 0)) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -665,6 +751,74 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   weighted_row_sum(db, otok, c2, 1.f, dqkv + (b * L + t) * qtok + 2 * H * hd + h * hd);                // dv_t = sum P(i, t) dO_i
 }
 
+// ------------------------------------------------------------------------------------------------ MODE_FUSED helpers
+// delta[b, h, l] = sum_d dO[b, l, h, d] * O[b, l, h, d]: eight lanes per (token, head), one 16-byte vector each (two for the
+// dims past 64), fully coalesced; HBM-bound (reads 2 * B * L * H * hd * 2 bytes).
+__global__ void __launch_bounds__(256)
+attention_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                           float* __restrict__ delta, long long rows, int L, int H, int hd) {
+  const int sub = threadIdx.x & 7;
+  const int nv = hd >> 3;
+  // four (token, head) rows per warp and trip; the trip count is warp-uniform (full-mask shuffles below)
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long row0 = warp0 * 4; row0 < rows; row0 += nwarps * 4) {
+    const long long row = row0 + ((threadIdx.x & 31) >> 3);   // row = (b * L + l) * H + h
+    const bool valid = row < rows;
+    const uint4* po = reinterpret_cast<const uint4*>(out + row * hd);
+    const uint4* pd = reinterpret_cast<const uint4*>(dout + row * hd);
+    float a = 0.f;
+    for (int v = sub; valid && v < nv; v += 8) {
+      const uint4 x = __ldg(po + v), y = __ldg(pd + v);
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a = fmaf(bf16_lo(xw[q]), bf16_lo(yw[q]), fmaf(bf16_hi(xw[q]), bf16_hi(yw[q]), a));
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    if (valid && sub == 0) {
+      const long long tok = row / H;
+      const int h = static_cast<int>(row - tok * H);
+      const long long b = tok / L;
+      const int l = static_cast<int>(tok - b * L);
+      delta[(b * H + h) * L + l] = a;
+    }
+  }
+}
+
+// d(qkv)[b, l, q slot, h, :] = bf16(scale * (acc[b, l, h, :] + dS(l, t) * k_t)) for the tokens l < Lm the tiles cover; the
+// second term only when the remainder token t = L - 1 is handled outside the tiles (ws: see attention_bwd_tail_kernel).
+// One thread per 8 elements: two 16-byte loads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+attention_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv,
+                                const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ ws, long long total8,
+                                int L, int Lm, int H, int hd, float scale) {
+  const int nv = hd >> 3;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nv);
+    long long rest = i / nv;
+    const int h = static_cast<int>(rest % H);
+    rest /= H;
+    const int l = static_cast<int>(rest % Lm);
+    const long long b = rest / Lm;
+    const float4* src = reinterpret_cast<const float4*>(acc + (((b * L + l) * H + h) * hd + v * 8));
+    float4 x0 = __ldg(src), x1 = __ldg(src + 1);
+    if (ws != nullptr) {
+      const float c = ws[(b * H + h) * 3LL * Lm + l];                                             // dS(l, t)
+      const uint4 k = __ldg(reinterpret_cast<const uint4*>(qkv + ((b * L + Lm) * 3LL * H + H + h) * hd + v * 8));   // k_t
+      x0.x = fmaf(c, bf16_lo(k.x), x0.x); x0.y = fmaf(c, bf16_hi(k.x), x0.y);
+      x0.z = fmaf(c, bf16_lo(k.y), x0.z); x0.w = fmaf(c, bf16_hi(k.y), x0.w);
+      x1.x = fmaf(c, bf16_lo(k.z), x1.x); x1.y = fmaf(c, bf16_hi(k.z), x1.y);
+      x1.z = fmaf(c, bf16_lo(k.w), x1.z); x1.w = fmaf(c, bf16_hi(k.w), x1.w);
+    }
+    const uint4 o = make_uint4(pack_bf16x2(x0.x * scale, x0.y * scale), pack_bf16x2(x0.z * scale, x0.w * scale),
+                               pack_bf16x2(x1.x * scale, x1.y * scale), pack_bf16x2(x1.z * scale, x1.w * scale));
+    *reinterpret_cast<uint4*>(dqkv + ((b * L + l) * 3LL * H + h) * hd + v * 8) = o;
+  }
+}
+
 }  // namespace ovk
 
 using namespace ovk;
@@ -681,9 +835,31 @@ extern "C" long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int
   return 3LL * B * H * (L - 1);
 }
 
+extern "C" long long ovk_attention_bwd_fused_workspace_floats(int B, int L, int H, int hd, int flags) {
+  if (B <= 0 || L <= 0 || H <= 0 || hd < 64 || hd > 80 || (hd % 8)) return 0;
+  return ovk_attention_bwd_workspace_floats(B, L, H, flags) + static_cast<long long>(B) * L * H * hd;
+}
+
+static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                              float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
+                              void* stream, bool fused);
+
 extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                     float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
                                     void* stream) {
+  return attention_bwd_impl(qkv, out, dout, lse, dqkv, delta, workspace, B, L, H, hd, scale, flags, stream, false);
+}
+
+extern "C" int ovk_attention_bwd_fused(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                       float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
+                                       void* stream) {
+  if (!workspace) return set_error(OVK_ERR_SHAPE, "attention_bwd_fused: the workspace is required");
+  return attention_bwd_impl(qkv, out, dout, lse, dqkv, delta, workspace, B, L, H, hd, scale, flags, stream, true);
+}
+
+static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                              float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
+                              void* stream, bool fused) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
   if (flags & ~OVK_ATT_CAUSAL) return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
   const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
@@ -723,6 +899,10 @@ extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void
       e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DQ, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_DKV, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_FUSED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<MODE_FUSED, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM_BYTES_RB_FUSED);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e));
     attr_once.done();
   }
@@ -749,18 +929,50 @@ extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void
   if (items_ll > 0x7fffffffLL) return set_error(OVK_ERR_SHAPE, "attention_bwd: too many work items");
   const int items = static_cast<int>(items_ll);
   const int grid = items < num_sms() ? items : num_sms();   // persistent: one CTA per SM (512 TMEM columns each)
+  if (fused) {
+    // workspace = [remainder-token vectors (when offered)] [fp32 dQ accumulator B x L x H x hd]
+    const long long nacc = static_cast<long long>(B) * L * H * hd;
+    float* acc = workspace + ovk_attention_bwd_workspace_floats(B, L, H, flags);
+    CUtensorMap tmDQF, tmDQFb;
+    {
+      const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+      const uint64_t strides[3] = {(uint64_t)hd * 4, (uint64_t)H * hd * 4, (uint64_t)L * H * hd * 4};
+      const uint32_t box[4] = {32, 1, 32, 1};
+      const uint32_t boxb[4] = {16, 1, 32, 1};
+      if ((rc = make_tmap_nd_f32(&tmDQF, acc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      if ((rc = make_tmap_nd_f32(&tmDQFb, acc, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(nacc) * sizeof(float), s);
+    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "attention_bwd_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const long long drows = static_cast<long long>(B) * L * H;
+    const int dgrid = static_cast<int>(std::min<long long>((drows * 8 + 255) / 256, 16LL * num_sms()));
+    attention_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), dg, delta, drows, L, H, hd);
+    if ((rc = check_launch("attention_bwd_delta_kernel"))) return rc;
+    const int per = (items + grid - 1) / grid;
+    if (ext)
+      attention_bwd_kernel<MODE_FUSED, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB_FUSED, s>>>(
+          tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb, tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmDQF, tmDQFb, per);
+    else
+      attention_bwd_kernel<MODE_FUSED, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(
+          tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb, tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmDQF, tmDQFb, per);
+    if ((rc = check_launch("attention_bwd_kernel<fused>"))) return rc;
+    const long long total8 = static_cast<long long>(B) * Lm * H * (hd / 8);
+    const int cgrid = static_cast<int>(std::min<long long>((total8 + 255) / 256, 16LL * num_sms()));
+    attention_bwd_dq_convert_kernel<<<cgrid, 256, 0, s>>>(acc, reinterpret_cast<__nv_bfloat16*>(dqkv), qg, wsp, total8, L, Lm, H, hd, scale);
+    return check_launch("attention_bwd_dq_convert_kernel");
+  }
   if (ext) {
     attention_bwd_kernel<MODE_DQ, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                 tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
+                                                                                 tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmQKV, tmQKVb, 0);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                                  tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
+                                                                                  tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmQKV, tmQKVb, 0);
   } else {
     attention_bwd_kernel<MODE_DQ, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                             tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
+                                                                             tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmQKV, tmQKVb, 0);
     if ((rc = check_launch("attention_bwd_kernel<dQ>"))) return rc;
     attention_bwd_kernel<MODE_DKV, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb,
-                                                                              tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd);
+                                                                              tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmQKV, tmQKVb, 0);
   }
   return check_launch("attention_bwd_kernel<dKdV>");
 }

@@ -641,7 +641,8 @@ def clip_loss_grad_logits(a_loc, b_all, row_offset: int, scale, row_lse, col_lse
 def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: Optional[float] = None,
                   causal: bool = False) -> torch.Tensor:
     """dqkv bf16 [B*L, 3*H*hd] from qkv, the forward output, its gradient and the saved lse.
-    Kernels: attention_bwd_kernel<dQ>, attention_bwd_kernel<dKdV>."""
+    Kernels: attention_bwd_delta_kernel, attention_bwd_kernel<fused>, attention_bwd_dq_convert_kernel (one pass over the
+    score tiles); OVK_ATTBWD_FUSED=0: attention_bwd_kernel<dQ>, attention_bwd_kernel<dKdV> (two passes, no scratch)."""
     for t, name, cols in ((qkv, "qkv", 3 * H * hd), (out, "out", H * hd), (dout, "dout", H * hd)):
         _require(t, torch.bfloat16, f"attention_bwd.{name}", 2)
         if not t.is_contiguous() or tuple(t.shape) != (B * L, cols):
@@ -652,13 +653,26 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
     if scale is None:
         scale = 1.0 / math.sqrt(hd)
     import os
-    nws = _lib.load().ovk_attention_bwd_workspace_floats(B, L, H, int(bool(causal)))
-    if os.environ.get("OVK_ATTBWD_TAIL", "1") == "0":   # A/B: the remainder token as a third tile row / column
+    flags = int(bool(causal))
+    tail_off = os.environ.get("OVK_ATTBWD_TAIL", "1") == "0"   # A/B: the remainder token as a third tile row / column
+    nws = _lib.load().ovk_attention_bwd_workspace_floats(B, L, H, flags)
+    nfused = _lib.load().ovk_attention_bwd_fused_workspace_floats(B, L, H, hd, flags)
+    # measured (tools/attn_bwd_ab.py): L = 577, hd 64: 4.32 -> 3.40 ms; L = 257: 3.81 -> 3.43 ms; hd 80: no gain (4.89 vs 4.94)
+    want_fused = os.environ.get("OVK_ATTBWD_FUSED", "1" if hd == 64 else "0") != "0"
+    if want_fused and nfused > 0 and not tail_off:
+        # one pass over the score tiles; dQ partial sums through an fp32 scratch (attention_bwd.cu, MODE_FUSED)
+        ws = torch.empty(nfused, dtype=torch.float32, device=qkv.device)
+        with _timed("attention_bwd", 10.0 * B * H * L * L * hd):
+            _lib.call("ovk_attention_bwd_fused", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), _p(ws), B, L, H, hd,
+                      float(scale), flags, _stream())
+        _count(4 if nws > 0 else 3)
+        return dqkv
+    if tail_off:
         nws = 0
     ws = torch.empty(nws, dtype=torch.float32, device=qkv.device) if nws > 0 else None   # remainder token of L = 128 k + 1
     with _timed("attention_bwd", 14.0 * B * H * L * L * hd):
         _lib.call("ovk_attention_bwd_ex", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), _p(ws), B, L, H, hd,
-                  float(scale), int(bool(causal)), _stream())
+                  float(scale), flags, _stream())
     _count(3 if ws is not None else 2)
     return dqkv
 

@@ -78,6 +78,39 @@ def test_attention_bwd_wide_heads(ops, hd, B, L, H):
         assert_grad(g[:, :, i], r[:, :, i], f"attention hd{hd} d{name} B{B} L{L} H{H}", 3e-2)
 
 
+@pytest.mark.parametrize("B,L,H,hd,causal", [(2, 577, 3, 64, False), (1, 300, 2, 64, True), (3, 77, 2, 64, True), (2, 577, 2, 80, False),
+                                             (1, 200, 3, 72, False), (30, 577, 12, 64, False), (20, 640, 8, 80, False),
+                                             (1, 1025, 2, 64, False)])
+def test_attention_bwd_one_pass_matches_two_pass(ops, B, L, H, hd, causal, monkeypatch):
+    """MODE_FUSED (one walk over the score tiles, dQ through an fp32 scratch + TMA reduce-add) against the two-pass kernels
+    on the same inputs: dV comes out of the same MMAs (bitwise equal), dK sees a delta summed in another order, dQ an fp32
+    summation order of its own;
+    and both against autograd of the fp32 composition (transformer.py:225,250-252; causal mask :757-763)."""
+    qkv = rnd(B * L, 3 * H * hd, seed=L + hd + 7).bfloat16()
+    dout = rnd(B * L, H * hd, seed=L + hd + 8).bfloat16()
+    qc, dc = qkv.cuda(), dout.cuda()
+    out, lse = ops.attention(qc, B, L, H, hd, save_lse=True, causal=causal)
+    monkeypatch.setenv("OVK_ATTBWD_FUSED", "1")
+    fused = ops.attention_bwd(qc, out, dc, lse, B, L, H, hd, causal=causal)
+    monkeypatch.setenv("OVK_ATTBWD_FUSED", "0")
+    two = ops.attention_bwd(qc, out, dc, lse, B, L, H, hd, causal=causal)
+    gf = fused.float().cpu().view(B, L, 3, H, hd)
+    gt = two.float().cpu().view(B, L, 3, H, hd)
+    assert torch.equal(gf[:, :, 2], gt[:, :, 2]), "dV: same MMAs in the same order"
+    assert_grad(gf[:, :, 1], gt[:, :, 1], "dK one-pass vs two-pass (delta summed in another order)", 2e-3)
+    assert_grad(gf[:, :, 0], gt[:, :, 0], "dQ one-pass vs two-pass", 1e-2)
+    if B * H <= 16:
+        qf = qkv.float().requires_grad_(True)
+        q, k, v = qf.view(B, L, 3, H, hd).permute(2, 0, 3, 1, 4)
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        if causal:
+            sc = sc + torch.full((L, L), float("-inf")).triu_(1)
+        (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd).backward(dout.float())
+        r = qf.grad.view(B, L, 3, H, hd)
+        for i, name in enumerate("qkv"):
+            assert_grad(gf[:, :, i], r[:, :, i], f"one-pass d{name}", 3e-2)
+
+
 def test_h14_style_tower_forward_backward_vs_oracle():
     """head width 80 (H/14, BASELINE configs[4]) end to end at toy size: embeddings and image / parameter gradients
     against autograd of the CPU oracle (no golden fixture for this config: the oracle is pinned on the others)."""
@@ -284,6 +317,11 @@ def test_attention_bwd_remainder_token_outside_the_tiles(ops, B, L, H, hd, monke
     dout = rnd(B * L, H * hd, seed=L + hd + 4).bfloat16()
     qc = qkv.cuda()
     out, lse = ops.attention(qc, B, L, H, hd, save_lse=True)
+    monkeypatch.setenv("OVK_ATTBWD_FUSED", "1")
+    n0 = ops.launch_count
+    dqkv_fused = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
+    assert ops.launch_count - n0 == 4, "delta + tail kernel + one-pass tile kernel + dQ conversion"
+    monkeypatch.setenv("OVK_ATTBWD_FUSED", "0")
     n0 = ops.launch_count
     dqkv = ops.attention_bwd(qc, out, dout.cuda(), lse, B, L, H, hd)
     assert ops.launch_count - n0 == 3, "tail kernel + dQ + dK/dV"
@@ -295,8 +333,12 @@ def test_attention_bwd_remainder_token_outside_the_tiles(ops, B, L, H, hd, monke
     (p @ v).permute(0, 2, 1, 3).reshape(B * L, H * hd).backward(dout.float())
     g = dqkv.float().cpu().view(B, L, 3, H, hd)
     g2 = dqkv_tiles.float().cpu().view(B, L, 3, H, hd)
+    g3 = dqkv_fused.float().cpu().view(B, L, 3, H, hd)
     r = qf.grad.view(B, L, 3, H, hd)
     for i, name in enumerate("qkv"):
+        assert_grad(g3[:, :, i], r[:, :, i], f"one-pass d{name} (all rows)", 3e-2)
+        assert_grad(g3[:, L - 1, i], r[:, L - 1, i], f"one-pass d{name} (remainder row)", 3e-2)
+        assert_grad(g3[:, :, i], g[:, :, i], f"d{name}: one-pass vs two-pass", 2e-2)
         assert_grad(g[:, :, i], r[:, :, i], f"d{name} (all rows)", 3e-2)
         assert_grad(g[:, L - 1, i], r[:, L - 1, i], f"d{name} (remainder row)", 3e-2)
         assert_grad(g[:, :, i], g2[:, :, i], f"d{name}: tail path vs all-tiles path", 2e-2)

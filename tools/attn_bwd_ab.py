@@ -24,9 +24,13 @@ for (B, H, L, hd) in ((256, 16, 257, 64), (1024, 16, 257, 64), (512, 12, 577, 64
     dout = torch.randn(B * L, H * hd, device="cuda").bfloat16()
     out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
     f = t(lambda: ops.attention(qkv, B, L, H, hd, save_lse=True))
+    os.environ["OVK_ATTBWD_FUSED"] = "0"
     os.environ["OVK_ATTBWD_TAIL"] = "0"
     b0 = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
     os.environ["OVK_ATTBWD_TAIL"] = "1"
     b = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
+    os.environ["OVK_ATTBWD_FUSED"] = "1"
+    bf = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
     fl = 4.0 * B * H * L * L * hd
-    print(f"B{B} H{H} L{L} hd{hd}: fwd {f:.3f} ms {fl / f / 1e9:.0f} TF/s   bwd {b:.3f} ms {3.5 * fl / b / 1e9:.0f} TF/s (14 B H L^2 hd)   [remainder token as tiles: {b0:.3f} ms]", flush=True)
+    print(f"B{B} H{H} L{L} hd{hd}: fwd {f:.3f} ms {fl / f / 1e9:.0f} TF/s   bwd one-pass {bf:.3f} ms {2.5 * fl / bf / 1e9:.0f} TF/s (10 B H L^2 hd)   "
+          f"two-pass {b:.3f} ms {3.5 * fl / b / 1e9:.0f} TF/s (14 B H L^2 hd)   [two-pass, remainder token as tiles: {b0:.3f} ms]", flush=True)
