@@ -604,62 +604,42 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 //   row t      : s_j = q_t . k_j, P(t, j), dS(t, j) for every key j  ->  dq_t = scale * sum_j dS(t, j) k_j
 //   column t   : s_i = q_i . k_t, P(i, t), dS(i, t) for every query i ->  dk_t = scale * sum_i dS(i, t) q_i,  dv_t = sum_i P(i, t) dO_i
 // and the vectors dS(., t), P(t, .), dS(t, .) over the tile tokens go to `ws` for the tile kernels' epilogues (rank-1 terms).
+// One pass over q, k, v, dO, O of the (image, head): a row is read ONCE, 16 bytes per lane, LPR lanes per row (coalesced
+// 128 - 160 byte segments); the five dot products of token j (as key of row t, as query of column t) are reduced over the
+// row's lanes by shuffles, and the three weighted row sums accumulate in registers (8 dims per lane), reduced over rows at the
+// end in a fixed order.  HBM-bound: 5 * B * L * H * hd * 2 bytes.  (The first version walked the rows once per dot product and
+// once per weighted sum, one thread per row: 9 row passes with 16-byte accesses 7 680 bytes apart, 1.4 ms at batch 1024 x 16
+// heads x 80 dims where the traffic bound is 0.5 ms.)
 constexpr int ABT_THREADS = 256;
 constexpr int ABT_WARPS = ABT_THREADS / 32;
-constexpr int ABT_MAXV = 10;   // head width <= 80: ten 16-byte vectors per row
 
-// dot product of a global bf16 row (one thread streams the whole row) with an fp32 vector in shared memory
-__device__ __forceinline__ float abt_dot(const __nv_bfloat16* p, int nv, const float* vec) {
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int v = 0; v < ABT_MAXV; ++v) {
-    if (v < nv) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + v);
-      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        a0 = fmaf(bf16_lo(w4[q]), vec[8 * v + 2 * q], a0);
-        a1 = fmaf(bf16_hi(w4[q]), vec[8 * v + 2 * q + 1], a1);
-      }
-    }
-  }
-  return a0 + a1;
+__device__ __forceinline__ float abt_dot8(const uint4& u, const float (&v)[8]) {
+  return fmaf(bf16_lo(u.x), v[0], fmaf(bf16_hi(u.x), v[1], fmaf(bf16_lo(u.y), v[2], fmaf(bf16_hi(u.y), v[3],
+         fmaf(bf16_lo(u.z), v[4], fmaf(bf16_hi(u.z), v[5], fmaf(bf16_lo(u.w), v[6], bf16_hi(u.w) * v[7])))))));
 }
-// dot product of two global bf16 rows
-__device__ __forceinline__ float abt_dot2(const __nv_bfloat16* p, const __nv_bfloat16* q, int nv) {
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int v = 0; v < ABT_MAXV; ++v) {
-    if (v < nv) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + v);
-      const uint4 w = __ldg(reinterpret_cast<const uint4*>(q) + v);
-      const uint32_t u4[4] = {u.x, u.y, u.z, u.w}, w4[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        a0 = fmaf(bf16_lo(u4[k]), bf16_lo(w4[k]), a0);
-        a1 = fmaf(bf16_hi(u4[k]), bf16_hi(w4[k]), a1);
-      }
-    }
-  }
-  return a0 + a1;
+__device__ __forceinline__ float abt_dot8b(const uint4& u, const uint4& w) {
+  return fmaf(bf16_lo(u.x), bf16_lo(w.x), fmaf(bf16_hi(u.x), bf16_hi(w.x), fmaf(bf16_lo(u.y), bf16_lo(w.y), fmaf(bf16_hi(u.y), bf16_hi(w.y),
+         fmaf(bf16_lo(u.z), bf16_lo(w.z), fmaf(bf16_hi(u.z), bf16_hi(w.z), fmaf(bf16_lo(u.w), bf16_lo(w.w), bf16_hi(u.w) * bf16_hi(w.w))))))));
+}
+__device__ __forceinline__ void abt_axpy8(float (&a)[8], float c, const uint4& u) {
+  a[0] = fmaf(c, bf16_lo(u.x), a[0]); a[1] = fmaf(c, bf16_hi(u.x), a[1]);
+  a[2] = fmaf(c, bf16_lo(u.y), a[2]); a[3] = fmaf(c, bf16_hi(u.y), a[3]);
+  a[4] = fmaf(c, bf16_lo(u.z), a[4]); a[5] = fmaf(c, bf16_hi(u.z), a[5]);
+  a[6] = fmaf(c, bf16_lo(u.w), a[6]); a[7] = fmaf(c, bf16_hi(u.w), a[7]);
 }
 
-__global__ void __launch_bounds__(ABT_THREADS, 4)
+template <int LPR>   // lanes per row: 8 (hd = 64) or 16 (64 < hd <= 128: the lanes past hd / 8 idle)
+__global__ void __launch_bounds__(ABT_THREADS, 2)
 attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                           const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                           float* __restrict__ ws, int L, int H, int hd, float scale) {
-  extern __shared__ float abt_smem[];
+  constexpr int RPW = 32 / LPR;               // rows per warp and trip
+  __shared__ float vec[5][LPR * 8];           // q_t, k_t, v_t, dO_t, O_t (zero past hd)
+  __shared__ float red[ABT_WARPS][3][LPR * 8];
   const int Lm = L - 1, t = L - 1;
-  const int nv = hd >> 3;
-  float* vq = abt_smem;            // q_t, k_t, v_t, dO_t, O_t as fp32 [5][80]
-  float* vk = vq + 80;
-  float* vv = vk + 80;
-  float* vd = vv + 80;
-  float* vo = vd + 80;
-  float* red = vo + 80;            // [ABT_WARPS][96] per-warp partial sums of a weighted row sum
-  float* c1 = red + ABT_WARPS * 96;   // [L] coefficient vectors of the current part
-  float* c2 = c1 + L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const bool active = sub * 8 < hd;
   const int h = blockIdx.x;
   const long long b = blockIdx.y;
   const long long bh = b * H + h;
@@ -669,86 +649,94 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   const __nv_bfloat16* ob = out + b * L * otok + h * hd;
   const __nv_bfloat16* db = dout + b * L * otok + h * hd;
   const float s2 = scale * 1.4426950408889634f;
-  for (int d = tid; d < hd; d += ABT_THREADS) {
-    vq[d] = __bfloat162float(qb[t * qtok + d]);
-    vk[d] = __bfloat162float(qb[t * qtok + H * hd + d]);
-    vv[d] = __bfloat162float(qb[t * qtok + 2 * H * hd + d]);
-    vd[d] = __bfloat162float(db[t * otok + d]);
-    vo[d] = __bfloat162float(ob[t * otok + d]);
+  for (int d = tid; d < LPR * 8; d += ABT_THREADS) {
+    const bool in = d < hd;
+    vec[0][d] = in ? __bfloat162float(qb[t * qtok + d]) : 0.f;
+    vec[1][d] = in ? __bfloat162float(qb[t * qtok + H * hd + d]) : 0.f;
+    vec[2][d] = in ? __bfloat162float(qb[t * qtok + 2 * H * hd + d]) : 0.f;
+    vec[3][d] = in ? __bfloat162float(db[t * otok + d]) : 0.f;
+    vec[4][d] = in ? __bfloat162float(ob[t * otok + d]) : 0.f;
   }
   __syncthreads();
   float delta_t = 0.f;
-  for (int d = 0; d < hd; ++d) delta_t = fmaf(vd[d], vo[d], delta_t);
+  for (int d = 0; d < hd; ++d) delta_t = fmaf(vec[3][d], vec[4][d], delta_t);
   const float lse_t2 = lse[bh * L + t] * 1.4426950408889634f;
-  float* wsb = ws + bh * 3 * Lm;
-
-  // dst[0..hd) = mul * sum_j coef[j] * row_j[0..hd)  (rows `pitch` elements apart).  Lanes own dimension pairs (one coalesced
-  // 4-byte load per lane and row: 128 contiguous bytes per warp), warps own every ABT_WARPS-th row.
-  auto weighted_row_sum = [&](const __nv_bfloat16* rows, long long pitch, const float* coef, float mul, __nv_bfloat16* dst) {
-    const int np = hd >> 1;                    // dimension pairs (32 for hd = 64, 40 for hd = 80)
-    const bool second = lane + 32 < np;        // lanes 0..7 carry a second pair when hd > 64
-    float a0 = 0.f, a1 = 0.f, e0 = 0.f, e1 = 0.f;
-#pragma unroll 8
-    for (int j = warp; j < L; j += ABT_WARPS) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(rows + j * pitch);
-      const float cj = coef[j];
-      if (lane < np) {
-        const uint32_t u = __ldg(r32 + lane);
-        a0 = fmaf(cj, bf16_lo(u), a0);
-        a1 = fmaf(cj, bf16_hi(u), a1);
-      }
-      if (second) {
-        const uint32_t u = __ldg(r32 + 32 + lane);
-        e0 = fmaf(cj, bf16_lo(u), e0);
-        e1 = fmaf(cj, bf16_hi(u), e1);
-      }
-    }
-    if (lane < np) {
-      red[warp * 96 + 2 * lane] = a0;
-      red[warp * 96 + 2 * lane + 1] = a1;
-    }
-    if (second) {
-      red[warp * 96 + 64 + 2 * lane] = e0;
-      red[warp * 96 + 64 + 2 * lane + 1] = e1;
-    }
-    __syncthreads();
-    for (int d = tid; d < hd; d += ABT_THREADS) {
-      float sum = 0.f;
+  float qt[8], kt[8], vt[8], dt[8];
 #pragma unroll
-      for (int x = 0; x < ABT_WARPS; ++x) sum += red[x * 96 + d];   // fixed order: deterministic
-      dst[d] = __float2bfloat16(sum * mul);
+  for (int e = 0; e < 8; ++e) {
+    qt[e] = vec[0][sub * 8 + e];
+    kt[e] = vec[1][sub * 8 + e];
+    vt[e] = vec[2][sub * 8 + e];
+    dt[e] = vec[3][sub * 8 + e];
+  }
+  float* wsb = ws + bh * 3 * Lm;
+  float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dq_t = scale * sum_j dS(t, j) k_j
+  float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dk_t = scale * sum_i dS(i, t) q_i
+  float av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dv_t = sum_i P(i, t) dO_i
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 2
+  for (int j0 = warp * RPW; j0 < L; j0 += ABT_WARPS * RPW) {   // warp-uniform trip count (full-mask shuffles below)
+    const int j = j0 + grp;
+    const bool ok = j < L;
+    const bool ld = ok && active;
+    const uint4 qq = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok) + sub) : z4;
+    const uint4 kk = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + H * hd) + sub) : z4;
+    const uint4 vv = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + 2 * H * hd) + sub) : z4;
+    const uint4 dd = ld ? __ldg(reinterpret_cast<const uint4*>(db + j * otok) + sub) : z4;
+    const uint4 oo = ld ? __ldg(reinterpret_cast<const uint4*>(ob + j * otok) + sub) : z4;
+    const float lse_j2 = ok ? __ldg(lse + bh * L + j) * 1.4426950408889634f : 0.f;
+    float s1 = abt_dot8(kk, qt);     // q_t . k_j      token j as a key of row t
+    float dp1 = abt_dot8(vv, dt);    // dO_t . v_j
+    float s2q = abt_dot8(qq, kt);    // q_j . k_t      token j as a query of column t
+    float dp2 = abt_dot8(dd, vt);    // dO_j . v_t
+    float dl = abt_dot8b(dd, oo);    // delta_j = dO_j . O_j
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+      dp1 += __shfl_xor_sync(0xffffffffu, dp1, off);
+      s2q += __shfl_xor_sync(0xffffffffu, s2q, off);
+      dp2 += __shfl_xor_sync(0xffffffffu, dp2, off);
+      dl += __shfl_xor_sync(0xffffffffu, dl, off);
     }
-    __syncthreads();
-  };
-
-  // ---------------------------------------------------------------- row t: every key j (one thread per key)
-  for (int j = tid; j < L; j += ABT_THREADS) {
-    const float s = abt_dot(qb + j * qtok + H * hd, nv, vq);          // q_t . k_j
-    const float dp = abt_dot(qb + j * qtok + 2 * H * hd, nv, vd);     // dO_t . v_j
-    const float p = fast_exp2(fmaf(s, s2, -lse_t2));
-    const float ds = p * (dp - delta_t);
-    c1[j] = ds;
-    if (j < Lm) {
-      wsb[Lm + j] = p;          // P(t, j)   -> dV_j += P(t, j) dO_t
-      wsb[2 * Lm + j] = ds;     // dS(t, j)  -> dK_j += scale dS(t, j) q_t
+    const float p1 = ok ? fast_exp2(fmaf(s1, s2, -lse_t2)) : 0.f;   // P(t, j)
+    const float ds1 = p1 * (dp1 - delta_t);                          // dS(t, j)
+    const float p2 = ok ? fast_exp2(fmaf(s2q, s2, -lse_j2)) : 0.f;  // P(j, t)
+    const float ds2 = p2 * (dp2 - dl);                               // dS(j, t)
+    abt_axpy8(aq, ds1, kk);
+    abt_axpy8(ak, ds2, qq);
+    abt_axpy8(av, p2, dd);
+    if (sub == 0 && j < Lm) {
+      wsb[j] = ds2;              // dS(i, t)  -> dQ_i += scale dS(i, t) k_t
+      wsb[Lm + j] = p1;          // P(t, j)   -> dV_j += P(t, j) dO_t
+      wsb[2 * Lm + j] = ds1;     // dS(t, j)  -> dK_j += scale dS(t, j) q_t
+    }
+  }
+  // rows of the warp (lanes with the same dims), then warps through shared memory, both in a fixed order: deterministic
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], off);
+      ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], off);
+      av[e] += __shfl_xor_sync(0xffffffffu, av[e], off);
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red[warp][0][sub * 8 + e] = aq[e];
+      red[warp][1][sub * 8 + e] = ak[e];
+      red[warp][2][sub * 8 + e] = av[e];
     }
   }
   __syncthreads();
-  weighted_row_sum(qb + H * hd, qtok, c1, scale, dqkv + (b * L + t) * qtok + h * hd);                  // dq_t = scale sum dS(t, j) k_j
-  // ---------------------------------------------------------------- column t: every query i (one thread per query)
-  for (int i = tid; i < L; i += ABT_THREADS) {
-    const float s = abt_dot(qb + i * qtok, nv, vk);                   // q_i . k_t
-    const float dp = abt_dot(db + i * otok, nv, vv);                  // dO_i . v_t
-    const float dl = abt_dot2(db + i * otok, ob + i * otok, nv);      // delta_i = dO_i . O_i
-    const float p = fast_exp2(fmaf(s, s2, -lse[bh * L + i] * 1.4426950408889634f));
-    const float ds = p * (dp - dl);
-    c1[i] = ds;
-    c2[i] = p;
-    if (i < Lm) wsb[i] = ds;    // dS(i, t)  -> dQ_i += scale dS(i, t) k_t
+  for (int x = tid; x < 3 * hd; x += ABT_THREADS) {
+    const int which = x / hd, d = x - which * hd;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < ABT_WARPS; ++w) sum += red[w][which][d];
+    dqkv[(b * L + t) * qtok + which * H * hd + h * hd + d] = __float2bfloat16(which == 2 ? sum : sum * scale);
   }
-  __syncthreads();
-  weighted_row_sum(qb, qtok, c1, scale, dqkv + (b * L + t) * qtok + H * hd + h * hd);                  // dk_t = scale sum dS(i, t) q_i
-  weighted_row_sum(db, otok, c2, 1.f, dqkv + (b * L + t) * qtok + 2 * H * hd + h * hd);                // dv_t = sum P(i, t) dO_i
 }
 
 // ------------------------------------------------------------------------------------------------ MODE_FUSED helpers
@@ -756,7 +744,10 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
 // dims past 64), fully coalesced; HBM-bound (reads 2 * B * L * H * hd * 2 bytes).
 __global__ void __launch_bounds__(256)
 attention_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
-                           float* __restrict__ delta, long long rows, int L, int H, int hd) {
+                           float* __restrict__ delta, long long rows, int L, int H, int hd, const float* __restrict__ lse,
+                           float* __restrict__ stats, int Lp) {
+  // stats (optional): f32 [B * H][2][Lp], what attention_bwd_t_kernel streams per query tile: [0] = -lse * log2(e), [1] = -delta,
+  // tokens l < min(L, Lp); l in [L, Lp) padded with (-inf, 0) (a query past the end then has P = dS = 0)
   const int sub = threadIdx.x & 7;
   const int nv = hd >> 3;
   // four (token, head) rows per warp and trip; the trip count is warp-uniform (full-mask shuffles below)
@@ -783,6 +774,21 @@ attention_bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfl
       const long long b = tok / L;
       const int l = static_cast<int>(tok - b * L);
       delta[(b * H + h) * L + l] = a;
+      if (stats != nullptr && l < Lp) {
+        stats[((b * H + h) * 2 + 0) * Lp + l] = -lse[(b * H + h) * L + l] * 1.4426950408889634f;
+        stats[((b * H + h) * 2 + 1) * Lp + l] = -a;
+      }
+    }
+  }
+  if (stats != nullptr && Lp > L) {
+    const int padn = Lp - L;
+    const long long total = rows / L * padn;   // B * H * padn
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long bh = i / padn;
+      const int l = L + static_cast<int>(i - bh * padn);
+      stats[(bh * 2 + 0) * Lp + l] = -INFINITY;
+      stats[(bh * 2 + 1) * Lp + l] = 0.f;
     }
   }
 }
@@ -837,12 +843,21 @@ extern "C" long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int
 
 extern "C" long long ovk_attention_bwd_fused_workspace_floats(int B, int L, int H, int hd, int flags) {
   if (B <= 0 || L <= 0 || H <= 0 || hd < 64 || hd > 80 || (hd % 8)) return 0;
-  return ovk_attention_bwd_workspace_floats(B, L, H, flags) + static_cast<long long>(B) * L * H * hd;
+  // [remainder-token vectors] [fp32 dQ accumulator B x L x H x hd] [per-query statistics B x H x 2 x Lp]
+  return ovk_attention_bwd_workspace_floats(B, L, H, flags) + static_cast<long long>(B) * L * H * hd +
+         2LL * B * H * ((L + AB_T - 1) / AB_T * AB_T);
 }
 
 static int attention_bwd_impl(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                               float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
                               void* stream, bool fused);
+namespace ovk {
+int launch_attention_bwd_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmDQKV,
+                           const CUtensorMap& tmQKVb, const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb,
+                           const CUtensorMap& tmDQF, const CUtensorMap& tmDQFb, const float* stats, int Lp, int L,
+                           int H, float scale, int items, int grid, int causal, int Lm, const float* ws,
+                           const __nv_bfloat16* qkv_g, const __nv_bfloat16* dout_g, int hd, cudaStream_t s);
+}
 
 extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                     float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
@@ -861,7 +876,8 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
                               float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
                               void* stream, bool fused) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
-  if (flags & ~OVK_ATT_CAUSAL) return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
+  if (flags & ~(OVK_ATT_CAUSAL | (fused ? (OVK_ATT_BWD_ONEPASS_V1 | 0xff00) : 0)))
+    return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
   const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
   if (hd < 64 || hd > 80 || (hd % 8))
     return set_error(OVK_ERR_SHAPE, "attention_bwd: head dim %d not supported (64, 72 or 80)", hd);
@@ -910,16 +926,13 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
   const bool tail = workspace != nullptr && ovk_attention_bwd_workspace_floats(B, L, H, flags) > 0 && B <= 65535 && H <= 65535;
   const int Lm = tail ? L - 1 : L;
   if (tail) {
-    const size_t sm = (5 * 80 + ABT_WARPS * 96 + 2 * static_cast<size_t>(L)) * sizeof(float);
-    static PerDeviceOnce tail_once;
-    if (tail_once.need()) {
-      cudaError_t e = cudaFuncSetAttribute(attention_bwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-      if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd_tail): %s", cudaGetErrorString(e));
-      tail_once.done();
-    }
-    attention_bwd_tail_kernel<<<dim3(H, B), ABT_THREADS, sm, s>>>(
-        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
-        reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
+    auto q_ = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    auto o_ = reinterpret_cast<const __nv_bfloat16*>(out);
+    auto d_ = reinterpret_cast<const __nv_bfloat16*>(dout);
+    if (hd == 64)
+      attention_bwd_tail_kernel<8><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
+    else
+      attention_bwd_tail_kernel<16><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
     if ((rc = check_launch("attention_bwd_tail_kernel"))) return rc;
   }
   const float* wsp = tail ? workspace : nullptr;
@@ -946,16 +959,25 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "attention_bwd_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
     const long long drows = static_cast<long long>(B) * L * H;
     const int dgrid = static_cast<int>(std::min<long long>((drows * 8 + 255) / 256, 16LL * num_sms()));
-    attention_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), dg, delta, drows, L, H, hd);
+    const bool v2 = !(flags & OVK_ATT_BWD_ONEPASS_V1);
+    float* stats = acc + nacc;
+    const int Lp = (Lm + AB_T - 1) / AB_T * AB_T;
+    attention_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), dg, delta, drows, L, H, hd, lse,
+                                                     v2 ? stats : nullptr, Lp);
     if ((rc = check_launch("attention_bwd_delta_kernel"))) return rc;
     const int per = (items + grid - 1) / grid;
-    if (ext)
+    if (v2) {
+      // transposed score tiles, half-tile software pipeline (attention_bwd2.cu)
+      if ((rc = launch_attention_bwd_t(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats, Lp, L, H, scale, items,
+                                       grid, causal | (flags & 0xff00), Lm, wsp, qg, dg, hd, s)))
+        return rc;
+    } else if (ext)
       attention_bwd_kernel<MODE_FUSED, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB_FUSED, s>>>(
           tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb, tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmDQF, tmDQFb, per);
     else
       attention_bwd_kernel<MODE_FUSED, 0><<<grid, AB_THREADS, AB_SMEM_BYTES, s>>>(
           tmQKV, tmO, tmDO, tmDQKV, tmQKVb, tmOb, tmDOb, tmDQKVb, lse, delta, L, H, scale, items, causal, Lm, wsp, qg, dg, hd, tmDQF, tmDQFb, per);
-    if ((rc = check_launch("attention_bwd_kernel<fused>"))) return rc;
+    if ((flags & OVK_ATT_BWD_ONEPASS_V1) && (rc = check_launch("attention_bwd_kernel<fused>"))) return rc;
     const long long total8 = static_cast<long long>(B) * Lm * H * (hd / 8);
     const int cgrid = static_cast<int>(std::min<long long>((total8 + 255) / 256, 16LL * num_sms()));
     attention_bwd_dq_convert_kernel<<<cgrid, 256, 0, s>>>(acc, reinterpret_cast<__nv_bfloat16*>(dqkv), qg, wsp, total8, L, Lm, H, hd, scale);

@@ -658,8 +658,11 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
     nws = _lib.load().ovk_attention_bwd_workspace_floats(B, L, H, flags)
     nfused = _lib.load().ovk_attention_bwd_fused_workspace_floats(B, L, H, hd, flags)
     # measured (tools/attn_bwd_ab.py): L = 577, hd 64: 4.32 -> 3.40 ms; L = 257: 3.81 -> 3.43 ms; hd 80: no gain (4.89 vs 4.94)
-    want_fused = os.environ.get("OVK_ATTBWD_FUSED", "1" if hd == 64 else "0") != "0"
-    if want_fused and nfused > 0 and not tail_off:
+    mode = os.environ.get("OVK_ATTBWD_FUSED", "2")   # 2: attention_bwd_t_kernel, 1: attention_bwd_kernel<fused>, 0: two passes
+    if mode != "0" and nfused > 0 and not tail_off:
+        if mode == "1":
+            flags |= 2   # OVK_ATT_BWD_ONEPASS_V1
+        flags |= (int(os.environ.get("OVK_ATTBWD_DBG", "0")) & 0xff) << 8   # knock-outs (tools/attn_bwd_knockout.py)
         # one pass over the score tiles; dQ partial sums through an fp32 scratch (attention_bwd.cu, MODE_FUSED)
         ws = torch.empty(nfused, dtype=torch.float32, device=qkv.device)
         with _timed("attention_bwd", 10.0 * B * H * L * L * hd):
@@ -667,6 +670,7 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
                       float(scale), flags, _stream())
         _count(4 if nws > 0 else 3)
         return dqkv
+    flags &= 1
     if tail_off:
         nws = 0
     ws = torch.empty(nws, dtype=torch.float32, device=qkv.device) if nws > 0 else None   # remainder token of L = 128 k + 1
