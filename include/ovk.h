@@ -227,7 +227,8 @@ long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int flags);
  * B H L^2 hd FLOPs and half the exponentials of ovk_attention_bwd_ex, same results up to the fp32 summation order of dQ.
  * workspace: f32[ovk_attention_bwd_fused_workspace_floats(B, L, H, hd, flags)], required (0 = shape not offered); it also
  * holds the remainder-token vectors of ovk_attention_bwd_workspace_floats.  delta as above.
- * Launches: attention_bwd_delta_kernel, (attention_bwd_tail_kernel,) the tile kernel, attention_bwd_dq_convert_kernel.
+ * Launches: attention_bwd_delta_kernel OR attention_bwd_tail_kernel (which leaves delta and the statistics as well), the tile
+ * kernel, attention_bwd_dq_convert_kernel.
  * Kernel: attention_bwd_t_kernel (attention_bwd2.cu: transposed score tiles, keys on the TMEM lanes, P^T / dS^T consumed as
  * TMEM operands, half-tile software pipeline); flags | OVK_ATT_BWD_ONEPASS_V1 selects its predecessor attention_bwd_kernel<fused>. */
 #define OVK_ATT_BWD_ONEPASS_V1 2

@@ -632,7 +632,10 @@ template <int LPR>   // lanes per row: 8 (hd = 64) or 16 (64 < hd <= 128: the la
 __global__ void __launch_bounds__(ABT_THREADS, 2)
 attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                           const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                          float* __restrict__ ws, int L, int H, int hd, float scale) {
+                          float* __restrict__ ws, int L, int H, int hd, float scale, float* __restrict__ delta_out,
+                          float* __restrict__ stats, int Lp) {
+  // delta_out / stats (optional): this kernel computes delta_j = dO_j . O_j of every token anyway, so for the one-pass tile
+  // kernel it also leaves what attention_bwd_delta_kernel would (delta [B, H, L]; stats [B * H][2][Lp], Lp = L - 1)
   constexpr int RPW = 32 / LPR;               // rows per warp and trip
   __shared__ float vec[5][LPR * 8];           // q_t, k_t, v_t, dO_t, O_t (zero past hd)
   __shared__ float red[ABT_WARPS][3][LPR * 8];
@@ -705,6 +708,13 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
     abt_axpy8(aq, ds1, kk);
     abt_axpy8(ak, ds2, qq);
     abt_axpy8(av, p2, dd);
+    if (sub == 0 && ok && delta_out != nullptr) {
+      delta_out[bh * L + j] = dl;
+      if (stats != nullptr && j < Lp) {
+        stats[(bh * 2 + 0) * Lp + j] = -lse_j2;
+        stats[(bh * 2 + 1) * Lp + j] = -dl;
+      }
+    }
     if (sub == 0 && j < Lm) {
       wsb[j] = ds2;              // dS(i, t)  -> dQ_i += scale dS(i, t) k_t
       wsb[Lm + j] = p1;          // P(t, j)   -> dV_j += P(t, j) dO_t
@@ -925,14 +935,22 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
   // remainder token (L = 128 k + 1) outside the tiles when the caller supplied the workspace
   const bool tail = workspace != nullptr && ovk_attention_bwd_workspace_floats(B, L, H, flags) > 0 && B <= 65535 && H <= 65535;
   const int Lm = tail ? L - 1 : L;
+  // one-pass path: fp32 dQ accumulator and per-query statistics behind the remainder-token vectors
+  const bool v2 = fused && !(flags & OVK_ATT_BWD_ONEPASS_V1);
+  float* acc = fused ? workspace + ovk_attention_bwd_workspace_floats(B, L, H, flags) : nullptr;
+  float* stats = v2 ? acc + static_cast<long long>(B) * L * H * hd : nullptr;
+  const int Lp = (Lm + AB_T - 1) / AB_T * AB_T;
   if (tail) {
     auto q_ = reinterpret_cast<const __nv_bfloat16*>(qkv);
     auto o_ = reinterpret_cast<const __nv_bfloat16*>(out);
     auto d_ = reinterpret_cast<const __nv_bfloat16*>(dout);
+    float* dl_ = fused ? delta : nullptr;   // the two-pass dQ kernel computes delta itself
     if (hd == 64)
-      attention_bwd_tail_kernel<8><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
+      attention_bwd_tail_kernel<8><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
+                                                                    scale, dl_, stats, Lp);
     else
-      attention_bwd_tail_kernel<16><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd, scale);
+      attention_bwd_tail_kernel<16><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
+                                                                     scale, dl_, stats, Lp);
     if ((rc = check_launch("attention_bwd_tail_kernel"))) return rc;
   }
   const float* wsp = tail ? workspace : nullptr;
@@ -943,9 +961,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
   const int items = static_cast<int>(items_ll);
   const int grid = items < num_sms() ? items : num_sms();   // persistent: one CTA per SM (512 TMEM columns each)
   if (fused) {
-    // workspace = [remainder-token vectors (when offered)] [fp32 dQ accumulator B x L x H x hd]
     const long long nacc = static_cast<long long>(B) * L * H * hd;
-    float* acc = workspace + ovk_attention_bwd_workspace_floats(B, L, H, flags);
     CUtensorMap tmDQF, tmDQFb;
     {
       const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
@@ -955,16 +971,16 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
       if ((rc = make_tmap_nd_f32(&tmDQF, acc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
       if ((rc = make_tmap_nd_f32(&tmDQFb, acc, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
     }
-    cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(nacc) * sizeof(float), s);
-    if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "attention_bwd_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
-    const long long drows = static_cast<long long>(B) * L * H;
-    const int dgrid = static_cast<int>(std::min<long long>((drows * 8 + 255) / 256, 16LL * num_sms()));
-    const bool v2 = !(flags & OVK_ATT_BWD_ONEPASS_V1);
-    float* stats = acc + nacc;
-    const int Lp = (Lm + AB_T - 1) / AB_T * AB_T;
-    attention_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), dg, delta, drows, L, H, hd, lse,
-                                                     v2 ? stats : nullptr, Lp);
-    if ((rc = check_launch("attention_bwd_delta_kernel"))) return rc;
+    if (!v2) {   // attention_bwd_t_kernel STORES the partial of an item's first key tile instead: no zero-fill
+      cudaError_t e = cudaMemsetAsync(acc, 0, static_cast<size_t>(nacc) * sizeof(float), s);
+      if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "attention_bwd_fused: cudaMemsetAsync: %s", cudaGetErrorString(e));
+    }
+    if (!tail) {   // with the remainder-token kernel in front, delta and the statistics are already there
+      const long long drows = static_cast<long long>(B) * L * H;
+      const int dgrid = static_cast<int>(std::min<long long>((drows * 8 + 255) / 256, 16LL * num_sms()));
+      attention_bwd_delta_kernel<<<dgrid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(out), dg, delta, drows, L, H, hd, lse, stats, Lp);
+      if ((rc = check_launch("attention_bwd_delta_kernel"))) return rc;
+    }
     const int per = (items + grid - 1) / grid;
     if (v2) {
       // transposed score tiles, half-tile software pipeline (attention_bwd2.cu)

@@ -409,13 +409,15 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     };
     // dQ partial #q (of the query tile at q0 of (h, b)): TMEM -> fp32 rows in this warp's own staging region -> one TMA
     // reduce-add per warp
-    auto drain_dq = [&](int q, int q0, int h, int b) {
+    auto drain_dq = [&](int q, int q0, int h, int b, bool first_key_tile) {
       t2_wait_t(dq_full, q & 1, 50, spin, prof, w0);
       tc_fence_after();
       if (q0 + quad * 32 < Lm && !(dbg & 2)) {   // warp-uniform: otherwise nothing but clipped rows
         uint32_t o[32];
         tmem_ld_x32(tmem_base + t_lane + T2_TM_DQ + hsel * 32, o);
-        if (lane == 0) tma_store_wait_read<0>();
+        // the warp's previous store / reduce-add has COMPLETED (not only read its staging rows): the same warp owns this block
+        // of the accumulator for every key tile, and its first key tile's plain store must land before the adds that follow
+        if (lane == 0) tma_store_wait_all<0>();
         __syncwarp();
         const uint32_t region = T2_OFF_DQST + (hsel * 4 + quad) * T2_DQ_REGION;
         const uint32_t dst = smem_u32(smem + region);
@@ -434,8 +436,13 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0 && !(dbg & 1)) {
-          tma_reduce_add_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
-          if (RB && hsel == 0) tma_reduce_add_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+          if (first_key_tile) {   // no zero-filled accumulator: the first key tile of an (image, head) writes, the others add
+            tma_store_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
+            if (RB && hsel == 0) tma_store_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+          } else {
+            tma_reduce_add_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
+            if (RB && hsel == 0) tma_reduce_add_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+          }
           tma_store_commit();
         }
       }
@@ -445,7 +452,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     // accumulators -> (+ rank-1 terms of the remainder token) -> bf16 -> staging in dS buffer `sbuf` -> TMA store.
     auto item_epilogue = [&](int t0, int h, int b, int q_last, int sbuf) {
       const long long bh = static_cast<long long>(b) * H + h;
-      drain_dq(q_last, (nt - 1) * T2_T, h, b);
+      drain_dq(q_last, (nt - 1) * T2_T, h, b, t0 == 0);
       if (RB) {                    // the narrow output tiles below reuse the narrow dQ staging
         if (lane == 0) tma_store_wait_read<0>();
         named_bar_sync(1, 32 * T2_CW);
@@ -625,7 +632,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
       // the previous tile's dQ partial (same item): its MMA went out a whole tile ago, and reading it here, behind this tile's
       // last half, lets dQ of THIS tile start as soon as its dS is complete
-      if (it > 0) drain_dq(G - 1, (it - 1) * T2_T, h, b);
+      if (it > 0) drain_dq(G - 1, (it - 1) * T2_T, h, b, t0 == 0);
       if (++it == nt) it = 0, ++n;
     }
     if (total_tiles > 0) item_epilogue(t0, h, b, total_tiles - 1, (total_tiles + 1) & 1);
@@ -656,7 +663,9 @@ int launch_attention_bwd_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, co
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd_t): %s", cudaGetErrorString(e));
     attr_once.done();
   }
-  const int per = (items + grid - 1) / grid;
+  // whole (image, head)s per CTA: the first key tile's STORE into the dQ accumulator and the adds of the others stay in one CTA
+  const int nt = (Lm + T2_T - 1) / T2_T;
+  const int per = ((items + grid - 1) / grid + nt - 1) / nt * nt;
   if (hd > T2_HD)
     attention_bwd_t_kernel<16><<<grid, T2_THREADS, T2_SMEM_BYTES, s>>>(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats,
                                                                        Lp, L, H, scale, items, per, causal, Lm, ws, qkv_g, dout_g, hd);

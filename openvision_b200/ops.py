@@ -668,7 +668,7 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
         with _timed("attention_bwd", 10.0 * B * H * L * L * hd):
             _lib.call("ovk_attention_bwd_fused", _p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(delta), _p(ws), B, L, H, hd,
                       float(scale), flags, _stream())
-        _count(4 if nws > 0 else 3)
+        _count(3)   # delta kernel OR remainder-token kernel (which leaves delta too), tile kernel, dQ conversion
         return dqkv
     flags &= 1
     if tail_off:
