@@ -581,8 +581,28 @@ def attention_vs_sdpa(torch, ops, peaks, iters=10):
                 row[f"sdpa_{name}_error"] = str(ex).splitlines()[0][:120]
         best = min([x for x in (row.get("sdpa_cudnn_ms"), row.get("sdpa_flash_ms")) if x], default=None)
         row["speedup_vs_best_sdpa"] = (best / ms) if best else None
+        # backward (ovk_attention_bwd_fused: delta / remainder-token kernel + tile kernel + dQ conversion) against autograd of SDPA
+        out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+        dout = torch.randn(B * L, H * hd, device="cuda").bfloat16()
+        ms_bwd = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
+        row["ours_bwd_ms"] = ms_bwd
+        row["ours_bwd_tflops"] = 2.5 * flops / ms_bwd / 1e9
+        for name, backend in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION)):
+            try:
+                qg, kg, vg = (x.detach().contiguous().requires_grad_(True) for x in (q, k, v))
+                with sdpa_kernel(backend):
+                    o = F.scaled_dot_product_attention(qg, kg, vg)
+                    go = torch.randn_like(o)
+                    ms_b = t(lambda: torch.autograd.grad(o, (qg, kg, vg), go, retain_graph=True))
+                row[f"sdpa_{name}_bwd_ms"] = ms_b
+                del o, go, qg, kg, vg
+            except Exception as ex:
+                row[f"sdpa_{name}_bwd_ms"] = None
+                row[f"sdpa_{name}_bwd_error"] = str(ex).splitlines()[0][:120]
+        best_b = min([x for x in (row.get("sdpa_cudnn_bwd_ms"), row.get("sdpa_flash_bwd_ms")) if x], default=None)
+        row["bwd_speedup_vs_best_sdpa"] = (best_b / ms_bwd) if best_b else None
         rows.append(row)
-        del qkv, q, k, v
+        del qkv, q, k, v, out, lse, dout
     torch.cuda.empty_cache()
     return rows
 
