@@ -232,6 +232,8 @@ long long ovk_attention_bwd_workspace_floats(int B, int L, int H, int flags);
  * Kernel: attention_bwd_t_kernel (attention_bwd2.cu: transposed score tiles, keys on the TMEM lanes, P^T / dS^T consumed as
  * TMEM operands, half-tile software pipeline); flags | OVK_ATT_BWD_ONEPASS_V1 selects its predecessor attention_bwd_kernel<fused>. */
 #define OVK_ATT_BWD_ONEPASS_V1 2
+#define OVK_ATT_BWD_8_WARPS 4 /* attention_bwd_t_kernel with 8 compute warps (32 query columns each; what the Python mirror passes)
+                               * instead of 16 (16 columns each; measured 7-10 % slower: twice the TMEM / barrier instructions) */
 long long ovk_attention_bwd_fused_workspace_floats(int B, int L, int H, int hd, int flags);
 int ovk_attention_bwd_fused(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* delta,
                             float* workspace, int B, int L, int H, int hd, float scale, int flags, void* stream);

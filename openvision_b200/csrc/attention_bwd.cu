@@ -863,10 +863,10 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
                               void* stream, bool fused);
 namespace ovk {
 int launch_attention_bwd_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmDQKV,
-                           const CUtensorMap& tmQKVb, const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb,
-                           const CUtensorMap& tmDQF, const CUtensorMap& tmDQFb, const float* stats, int Lp, int L,
-                           int H, float scale, int items, int grid, int causal, int Lm, const float* ws,
-                           const __nv_bfloat16* qkv_g, const __nv_bfloat16* dout_g, int hd, cudaStream_t s);
+                           const CUtensorMap& tmQKVb, const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb, float* acc, int B,
+                           const float* stats, int Lp, int L, int H, float scale, int items, int grid, int causal, int Lm,
+                           const float* ws, const __nv_bfloat16* qkv_g, const __nv_bfloat16* dout_g, int hd, bool warps16,
+                           cudaStream_t s);
 }
 
 extern "C" int ovk_attention_bwd_ex(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
@@ -886,7 +886,7 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
                               float* delta, float* workspace, int B, int L, int H, int hd, float scale, int flags,
                               void* stream, bool fused) {
   if (B <= 0 || L <= 0 || H <= 0) return set_error(OVK_ERR_SHAPE, "attention_bwd: empty problem");
-  if (flags & ~(OVK_ATT_CAUSAL | (fused ? (OVK_ATT_BWD_ONEPASS_V1 | 0xff00) : 0)))
+  if (flags & ~(OVK_ATT_CAUSAL | (fused ? (OVK_ATT_BWD_ONEPASS_V1 | OVK_ATT_BWD_8_WARPS | 0xff00) : 0)))
     return set_error(OVK_ERR_SHAPE, "attention_bwd: unknown flags 0x%x", flags);
   const int causal = (flags & OVK_ATT_CAUSAL) ? 1 : 0;
   if (hd < 64 || hd > 80 || (hd % 8))
@@ -984,8 +984,8 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
     const int per = (items + grid - 1) / grid;
     if (v2) {
       // transposed score tiles, half-tile software pipeline (attention_bwd2.cu)
-      if ((rc = launch_attention_bwd_t(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats, Lp, L, H, scale, items,
-                                       grid, causal | (flags & 0xff00), Lm, wsp, qg, dg, hd, s)))
+      if ((rc = launch_attention_bwd_t(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, acc, B, stats, Lp, L, H, scale, items, grid,
+                                       causal | (flags & 0xff00), Lm, wsp, qg, dg, hd, !(flags & OVK_ATT_BWD_8_WARPS), s)))
         return rc;
     } else if (ext)
       attention_bwd_kernel<MODE_FUSED, 16><<<grid, AB_THREADS, AB_SMEM_BYTES_RB_FUSED, s>>>(

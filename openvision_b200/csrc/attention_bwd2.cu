@@ -25,8 +25,8 @@ namespace ovk {
 constexpr int T2_T = 128;
 constexpr int T2_HD = 64;
 constexpr int T2_TILE = T2_T * 128;            // 16 KB: [128 rows x 64 bf16]
-constexpr int T2_CW = 8;                       // compute warps
-constexpr int T2_THREADS = 32 * (T2_CW + 2);   // + TMA producer warp + MMA warp
+// compute warps: NW per TMEM lane quarter (2 or 4): a warp owns 32 key rows and CG = 64 / NW query columns of a half
+constexpr int t2_threads(int nw) { return 32 * (4 * nw + 2); }   // + TMA producer warp + MMA warp
 constexpr int T2_OFF_K0 = 0;
 constexpr int T2_OFF_V0 = 1 * T2_TILE;
 constexpr int T2_OFF_Q = 2 * T2_TILE;          // x2 (streamed)
@@ -51,7 +51,6 @@ static_assert(T2_SMEM_BYTES <= 232448, "shared memory budget");
 constexpr uint32_t T2_TM_S = 0, T2_TM_DP = 128, T2_TM_DK = 256, T2_TM_DV = 320, T2_TM_DQ = 384;
 constexpr uint32_t T2_TM_DKB = 448, T2_TM_DVB = 464, T2_TM_DQB = 480;
 constexpr uint32_t T2_TM_K = 448, T2_TM_V = 480;   // hd = 64: K_j / V_j as TMEM-resident A operands (32 columns each)
-constexpr int T2_DQ_REGION = 32 * 128;
 
 __device__ __forceinline__ uint64_t t2_desc_sw32(uint32_t saddr) { return umma_desc(saddr, 16, 256, 6); }
 __device__ __forceinline__ uint32_t t2_sw32_offset(uint32_t row, uint32_t chunk) {
@@ -73,7 +72,20 @@ __device__ __forceinline__ void t2_tmem_cp_128x256b(uint32_t taddr, uint64_t sde
 }
 // TMEM column (inside a half's 64 columns) of the bf16 A block of 16-query group kk: the two 32-column thread groups of a
 // half each write their 16 packed columns at the START of their own 32 fp32 columns (nobody writes where another warp reads)
-__device__ __forceinline__ uint32_t t2_acol(int kk) { return static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8); }
+template <int CG>
+__device__ __forceinline__ uint32_t t2_acol(int kk) {
+  return CG == 32 ? static_cast<uint32_t>((kk >> 1) * 32 + (kk & 1) * 8) : static_cast<uint32_t>(kk * 16);
+}
+__device__ __forceinline__ void t2_tmem_ld(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_x32(taddr, r); }
+__device__ __forceinline__ void t2_tmem_ld(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_x16(taddr, r); }
+__device__ __forceinline__ void t2_tmem_st(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st_x16(taddr, r); }
+__device__ __forceinline__ void t2_tmem_st(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 16-byte chunk `chunk` of row `row` in a [rows x 64 B] SWIZZLE_64B tile (base 512-byte aligned)
+__device__ __forceinline__ uint32_t t2_sw64_offset(uint32_t row, uint32_t chunk) { return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4); }
 
 __device__ __forceinline__ void t2_wait(uint64_t* bar, uint32_t parity, int code, bool spin) {
   if (spin) {
@@ -97,8 +109,8 @@ __device__ __forceinline__ void t2_wait_t(uint64_t* bar, uint32_t parity, int co
   }
 }
 
-template <int RB>
-__global__ void __launch_bounds__(T2_THREADS, 1)
+template <int RB, int NW>
+__global__ void __launch_bounds__(t2_threads(NW), 1)
 attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                        const __grid_constant__ CUtensorMap tmDQKV, const __grid_constant__ CUtensorMap tmQKVb,
                        const __grid_constant__ CUtensorMap tmDOb, const __grid_constant__ CUtensorMap tmDQKVb,
@@ -113,6 +125,8 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     if (threadIdx.x == 0) printf("[ovk] attention_bwd_t: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
+  constexpr int CW = 4 * NW;        // compute warps
+  constexpr int CG = 64 / NW;       // query columns of a half per warp
   constexpr int NST = RB ? 1 : 2;   // stationary tile sets
   constexpr bool KVT = (RB == 0);   // K_j / V_j also live in TMEM (the 64 columns the narrow accumulators would take)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T2_OFF_BAR);
@@ -150,7 +164,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   auto off_k = [](int buf) { return buf == 0 ? T2_OFF_K0 : T2_OFF_K1; };
   auto off_v = [](int buf) { return buf == 0 ? T2_OFF_V0 : T2_OFF_V1; };
 
-  if (warp == T2_CW && lane == 0) {
+  if (warp == CW && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmDQKV);
@@ -161,14 +175,14 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       mbar_init(&sf[i], 1);
       mbar_init(&se[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], T2_CW);
+      mbar_init(&p_ready[i], CW);
     }
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, T2_CW);
-    mbar_init(acc_free, T2_CW);
+    mbar_init(dq_free, CW);
+    mbar_init(acc_free, CW);
     fence_mbar_init();
   }
-  if (warp == T2_CW + 1) tmem_alloc<512>(tmem_slot);
+  if (warp == CW + 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -180,7 +194,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   const int n_items = max(0, item_last - item_first);
   const int total_tiles = n_items * nt;
 
-  if (warp == T2_CW) {
+  if (warp == CW) {
     // ---------------------------------------------------------------------- producer (one thread): TMA tiles + statistics
     if (lane == 0) {
     int n = 0, it = 0, t0 = 0, h = 0, b = 0;
@@ -218,7 +232,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       if (++it == nt) it = 0, ++n;
     }
     }
-  } else if (warp == T2_CW + 1) {
+  } else if (warp == CW + 1) {
     if (elect_one() && total_tiles > 0) {
       // -------------------------------------------------------------------- MMA issuer
       // The issue loop of ONE thread is what paces this kernel when its MMAs are small (N = 64: 32 tensor clocks each): building
@@ -319,33 +333,33 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           const long long m0 = prof ? clock64() : 0;
           if (dbg & 64) {
           } else if (ksteps == 4) {   // the common case, straight-line
-            t2_umma_ts(tmem_base + T2_TM_DV, tp + 0, dk(do_lo, 0), idesc, first);
-            t2_umma_ts(tmem_base + T2_TM_DV, tp + 8, dk(do_lo, 2048), idesc, 1);
-            t2_umma_ts(tmem_base + T2_TM_DV, tp + 32, dk(do_lo, 4096), idesc, 1);
-            t2_umma_ts(tmem_base + T2_TM_DV, tp + 40, dk(do_lo, 6144), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol<CG>(0), dk(do_lo, 0), idesc, first);
+            t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol<CG>(1), dk(do_lo, 2048), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol<CG>(2), dk(do_lo, 4096), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol<CG>(3), dk(do_lo, 6144), idesc, 1);
             if (RB) {
-              t2_umma_ts(tmem_base + T2_TM_DVB, tp + 0, dn(dob_lo, 0), idescb, first);
-              t2_umma_ts(tmem_base + T2_TM_DVB, tp + 8, dn(dob_lo, 512), idescb, 1);
-              t2_umma_ts(tmem_base + T2_TM_DVB, tp + 32, dn(dob_lo, 1024), idescb, 1);
-              t2_umma_ts(tmem_base + T2_TM_DVB, tp + 40, dn(dob_lo, 1536), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol<CG>(0), dn(dob_lo, 0), idescb, first);
+              t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol<CG>(1), dn(dob_lo, 512), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol<CG>(2), dn(dob_lo, 1024), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol<CG>(3), dn(dob_lo, 1536), idescb, 1);
             }
-            t2_umma_ts(tmem_base + T2_TM_DK, tds + 0, dk(q_lo, 0), idesc, first);
-            t2_umma_ts(tmem_base + T2_TM_DK, tds + 8, dk(q_lo, 2048), idesc, 1);
-            t2_umma_ts(tmem_base + T2_TM_DK, tds + 32, dk(q_lo, 4096), idesc, 1);
-            t2_umma_ts(tmem_base + T2_TM_DK, tds + 40, dk(q_lo, 6144), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol<CG>(0), dk(q_lo, 0), idesc, first);
+            t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol<CG>(1), dk(q_lo, 2048), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol<CG>(2), dk(q_lo, 4096), idesc, 1);
+            t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol<CG>(3), dk(q_lo, 6144), idesc, 1);
             if (RB) {
-              t2_umma_ts(tmem_base + T2_TM_DKB, tds + 0, dn(qb_lo, 0), idescb, first);
-              t2_umma_ts(tmem_base + T2_TM_DKB, tds + 8, dn(qb_lo, 512), idescb, 1);
-              t2_umma_ts(tmem_base + T2_TM_DKB, tds + 32, dn(qb_lo, 1024), idescb, 1);
-              t2_umma_ts(tmem_base + T2_TM_DKB, tds + 40, dn(qb_lo, 1536), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol<CG>(0), dn(qb_lo, 0), idescb, first);
+              t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol<CG>(1), dn(qb_lo, 512), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol<CG>(2), dn(qb_lo, 1024), idescb, 1);
+              t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol<CG>(3), dn(qb_lo, 1536), idescb, 1);
             }
           } else {
-            for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol(kk), dk(do_lo, kk * 2048), idesc, first | kk);
+            for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DV, tp + t2_acol<CG>(kk), dk(do_lo, kk * 2048), idesc, first | kk);
             if (RB)
-              for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol(kk), dn(dob_lo, kk * 512), idescb, first | kk);
-            for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol(kk), dk(q_lo, kk * 2048), idesc, first | kk);
+              for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DVB, tp + t2_acol<CG>(kk), dn(dob_lo, kk * 512), idescb, first | kk);
+            for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DK, tds + t2_acol<CG>(kk), dk(q_lo, kk * 2048), idesc, first | kk);
             if (RB)
-              for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol(kk), dn(qb_lo, kk * 512), idescb, first | kk);
+              for (int kk = 0; kk < ksteps; ++kk) t2_umma_ts(tmem_base + T2_TM_DKB, tds + t2_acol<CG>(kk), dn(qb_lo, kk * 512), idescb, first | kk);
           }
           if (prof) w6 += clock64() - m0;
           if (hh == 1) commit_t(&se[s]);   // last readers of Q_i / dO_i
@@ -397,11 +411,11 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
   } else {
     // ---------------------------------------------------------------------- compute warps
     const int quad = warp & 3;
-    const int hsel = warp >> 2;           // which 32 of a half's 64 query columns
+    const int csel = warp >> 2;           // which CG of a half's 64 query columns
     const int r = quad * 32 + lane;       // key row inside the tile = TMEM lane
     const uint32_t t_lane = static_cast<uint32_t>(quad * 32) << 16;
     const uint64_t sc2 = f2_pack(s2, s2);
-    // per-warp arrival on a barrier of count T2_CW: every lane has fenced its own TMEM / shared-memory accesses
+    // per-warp arrival on a barrier of count CW: every lane has fenced its own TMEM / shared-memory accesses
     auto warp_arrive = [&](uint64_t* bar) {
       tc_fence_before();
       __syncwarp();
@@ -413,19 +427,19 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       t2_wait_t(dq_full, q & 1, 50, spin, prof, w0);
       tc_fence_after();
       if (q0 + quad * 32 < Lm && !(dbg & 2)) {   // warp-uniform: otherwise nothing but clipped rows
-        uint32_t o[32];
-        tmem_ld_x32(tmem_base + t_lane + T2_TM_DQ + hsel * 32, o);
+        uint32_t o[CG];
+        t2_tmem_ld(tmem_base + t_lane + T2_TM_DQ + csel * CG, o);
         // the warp's previous store / reduce-add has COMPLETED (not only read its staging rows): the same warp owns this block
         // of the accumulator for every key tile, and its first key tile's plain store must land before the adds that follow
         if (lane == 0) tma_store_wait_all<0>();
         __syncwarp();
-        const uint32_t region = T2_OFF_DQST + (hsel * 4 + quad) * T2_DQ_REGION;
+        const uint32_t region = T2_OFF_DQST + (csel * 4 + quad) * (32 * CG * 4);
         const uint32_t dst = smem_u32(smem + region);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          sts128(dst + sw128_offset(lane, k), make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
-        if (RB && hsel == 0) {
+        for (int k = 0; k < CG / 4; ++k)
+          sts128(dst + (CG == 32 ? sw128_offset(lane, k) : t2_sw64_offset(lane, k)), make_uint4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]));
+        if (RB && csel == 0) {
           uint32_t ob[16];
           tmem_ld_x16(tmem_base + t_lane + T2_TM_DQB, ob);
           tmem_ld_wait();
@@ -437,11 +451,11 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         __syncwarp();
         if (lane == 0 && !(dbg & 1)) {
           if (first_key_tile) {   // no zero-filled accumulator: the first key tile of an (image, head) writes, the others add
-            tma_store_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
-            if (RB && hsel == 0) tma_store_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+            tma_store_4d(&tmDQF, smem + region, csel * CG, h, q0 + quad * 32, b);
+            if (RB && csel == 0) tma_store_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
           } else {
-            tma_reduce_add_4d(&tmDQF, smem + region, hsel * 32, h, q0 + quad * 32, b);
-            if (RB && hsel == 0) tma_reduce_add_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
+            tma_reduce_add_4d(&tmDQF, smem + region, csel * CG, h, q0 + quad * 32, b);
+            if (RB && csel == 0) tma_reduce_add_4d(&tmDQFb, smem + T2_OFF_NST + quad * (32 * 64), 64, h, q0 + quad * 32, b);
           }
           tma_store_commit();
         }
@@ -455,15 +469,18 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       drain_dq(q_last, (nt - 1) * T2_T, h, b, t0 == 0);
       if (RB) {                    // the narrow output tiles below reuse the narrow dQ staging
         if (lane == 0) tma_store_wait_read<0>();
-        named_bar_sync(1, 32 * T2_CW);
+        named_bar_sync(1, 32 * CW);
       }
+      // this warp's share of the [128 keys x (dK | dV)] read-out: tensor `which` (0: dK, scaled; 1: dV), columns [col0, col0 + ncols)
+      constexpr int ncols = 128 / NW;
+      const int which = csel / (NW / 2), col0 = (csel % (NW / 2)) * ncols;
       const bool tail = ws != nullptr;
       float tcoef = 0.f;
       const __nv_bfloat16* tvec = nullptr;
       if (tail) {
         const float* wsb = ws + bh * 3 * Lm;
         const long long trow = static_cast<long long>(b) * L + Lm;   // the remainder token
-        if (hsel == 0) {
+        if (which == 0) {
           tcoef = wsb[2 * Lm + t0 + r];                              // dS(t, j)
           tvec = qkv_g + (trow * 3 * H + h) * hd_g;                  // q_t
         } else {
@@ -471,12 +488,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           tvec = dout_g + (trow * H + h) * hd_g;                     // dO_t
         }
       }
-      const float mul = hsel == 0 ? scale : 1.f;   // hsel 0: dK (scaled), hsel 1: dV
-      const uint32_t src = hsel == 0 ? T2_TM_DK : T2_TM_DV;
+      const float mul = which == 0 ? scale : 1.f;
+      const uint32_t src = which == 0 ? T2_TM_DK : T2_TM_DV;
       uint8_t* stage_tiles = smem + T2_OFF_DS + sbuf * 2 * T2_TILE;
-      const uint32_t stage = smem_u32(stage_tiles + hsel * T2_TILE);   // atom 0 <- dK, atom 1 <- dV
+      const uint32_t stage = smem_u32(stage_tiles + which * T2_TILE);   // atom 0 <- dK, atom 1 <- dV
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
+      for (int c = col0; c < col0 + ncols; c += 32) {
         uint32_t o[32];
         tmem_ld_x32(tmem_base + t_lane + src + c, o);
         tmem_ld_wait();
@@ -500,9 +517,9 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
                             pack_bf16x2(__uint_as_float(o[8 * k + 4]) * mul, __uint_as_float(o[8 * k + 5]) * mul),
                             pack_bf16x2(__uint_as_float(o[8 * k + 6]) * mul, __uint_as_float(o[8 * k + 7]) * mul)));
       }
-      if (RB) {
+      if (RB && col0 == 0) {
         uint32_t ob[16];
-        tmem_ld_x16(tmem_base + t_lane + (hsel == 0 ? T2_TM_DKB : T2_TM_DVB), ob);
+        tmem_ld_x16(tmem_base + t_lane + (which == 0 ? T2_TM_DKB : T2_TM_DVB), ob);
         tmem_ld_wait();
         if (tail) {
           const int nb = hd_g - 64 < 16 ? hd_g - 64 : 16;   // dims 64 .. hd (the columns past hd stay zero)
@@ -516,7 +533,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             }
           }
         }
-        const uint32_t dstb = smem_u32(smem + T2_OFF_NST + hsel * T2_BT);
+        const uint32_t dstb = smem_u32(smem + T2_OFF_NST + which * T2_BT);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
           sts128(dstb + t2_sw32_offset(r, c),
@@ -527,7 +544,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       }
       warp_arrive(acc_free);   // dK / dV read: the next item's first accumulating MMA may overwrite them
       fence_proxy_async_smem();
-      named_bar_sync(1, 32 * T2_CW);
+      named_bar_sync(1, 32 * CW);
       if (threadIdx.x == 0) {
         tma_store_4d(&tmDQKV, stage_tiles, 0, H + h, t0, b);
         tma_store_4d(&tmDQKV, stage_tiles + T2_TILE, 0, 2 * H + h, t0, b);
@@ -553,7 +570,7 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
       const int s = G & 1;
       if (staged) {
         if (threadIdx.x == 0) tma_store_wait_read<0>();
-        named_bar_sync(1, 32 * T2_CW);
+        named_bar_sync(1, 32 * CW);
         staged = false;
       }
       // wide heads (one stationary set): this tile's scores cannot be issued before the previous item's last MMA, so its
@@ -572,18 +589,18 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
         }
         t2_wait_t(&s_full[hh], G & 1, 52, spin, prof, hh ? w3 : w2);
         tc_fence_after();
-        const int c0 = hh * 64 + hsel * 32;     // first query column (inside the tile) of this thread's chunk
+        const int c0 = hh * 64 + csel * CG;     // first query column (inside the tile) of this thread's chunk
         const int q0c = it * T2_T + c0;
         // warp-uniform: chunks past the last query are read by no MMA; key rows past nkv16 only reach clipped dK / dV rows
         if (q0c < Lm && quad * 32 < nkv16 && !(dbg & 4)) {
-          uint32_t sv[32], dv[32];
-          tmem_ld_x32(tmem_base + t_lane + T2_TM_S + c0, sv);
-          tmem_ld_x32(tmem_base + t_lane + T2_TM_DP + c0, dv);
+          uint32_t sv[CG], dv[CG];
+          t2_tmem_ld(tmem_base + t_lane + T2_TM_S + c0, sv);
+          t2_tmem_ld(tmem_base + t_lane + T2_TM_DP + c0, dv);
           tmem_ld_wait();
-          uint32_t pp[16], dd[16];
+          uint32_t pp[CG / 2], dd[CG / 2];
           if (!causal || q0c >= jr) {   // queries past the end: nl = -inf and zero-filled Q / dO rows give exact zeros
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {
+            for (int v = 0; v < CG / 4; ++v) {
               const float4 nl = lds_f32x4(st_addr + (c0 + 4 * v) * 4);
               const float4 nd = lds_f32x4(st_addr + (128 + c0 + 4 * v) * 4);
               float x0, x1, x2, x3, d0, d1, d2, d3;
@@ -600,12 +617,12 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
             // keys past the end of the sequence: K rows are zero-filled (a finite score), but nothing of them may survive
             if (!row_ok) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) pp[j] = dd[j] = 0u;
+              for (int j = 0; j < CG / 2; ++j) pp[j] = dd[j] = 0u;
             }
           } else {
             // the causal mask (transformer.py:757-763: query q sees keys <= q): exact zeros
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < CG / 2; ++j) {
               const int q = q0c + 2 * j;
               const bool ok0 = row_ok && q < Lm && (!causal || q >= jr);
               const bool ok1 = row_ok && q + 1 < Lm && (!causal || q + 1 >= jr);
@@ -619,11 +636,11 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
               dd[j] = pack_bf16x2(d0, d1);
             }
           }
-          tmem_st_x16(tmem_base + t_lane + T2_TM_S + c0, pp);    // P^T: A operand of dV
-          tmem_st_x16(tmem_base + t_lane + T2_TM_DP + c0, dd);   // dS^T: A operand of dK
+          t2_tmem_st(tmem_base + t_lane + T2_TM_S + c0, pp);    // P^T: A operand of dV
+          t2_tmem_st(tmem_base + t_lane + T2_TM_DP + c0, dd);   // dS^T: A operand of dK
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                             // dS^T row of this key: A operand of dQ
-            sts128(ds_base + hh * T2_TILE + sw128_offset(r, hsel * 4 + k),
+          for (int k = 0; k < CG / 8; ++k)                        // dS^T row of this key: A operand of dQ
+            sts128(ds_base + hh * T2_TILE + sw128_offset(r, csel * (CG / 8) + k),
                    make_uint4(dd[4 * k], dd[4 * k + 1], dd[4 * k + 2], dd[4 * k + 3]));
           tmem_st_wait();
           fence_proxy_async_smem();
@@ -637,42 +654,60 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
     }
     if (total_tiles > 0) item_epilogue(t0, h, b, total_tiles - 1, (total_tiles + 1) & 1);
     if (lane == 0) tma_store_wait_all<0>();
-    if (prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 224))
+    if (prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 32 * CW - 32))
       printf("[t2 compute warp %d] total %lld clk; waits: dq_full %lld sf %lld s_full0 %lld s_full1 %lld\n", warp, clock64() - t_start, w0, w1,
              w2, w3);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == T2_CW + 1) {
+  if (warp == CW + 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
-// Launch (called by attention_bwd.cu's host code, which owns the tensor maps, the delta / tail / conversion kernels).
-int launch_attention_bwd_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmDQKV,
-                           const CUtensorMap& tmQKVb, const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb,
-                           const CUtensorMap& tmDQF, const CUtensorMap& tmDQFb, const float* stats, int Lp, int L,
-                           int H, float scale, int items, int grid, int causal, int Lm, const float* ws,
-                           const __nv_bfloat16* qkv_g, const __nv_bfloat16* dout_g, int hd, cudaStream_t s) {
+// Launch (called by attention_bwd.cu's host code, which owns the operand tensor maps, the delta / tail / conversion kernels).
+// acc: the fp32 dQ accumulator [B, L, H, hd]; warps16: 16 compute warps (16 query columns of a half each) instead of 8.
+template <int RB, int NW>
+static int launch_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmDQKV, const CUtensorMap& tmQKVb,
+                    const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb, float* acc, int B, const float* stats, int Lp, int L, int H,
+                    float scale, int items, int grid, int per, int causal, int Lm, const float* ws, const __nv_bfloat16* qkv_g,
+                    const __nv_bfloat16* dout_g, int hd, cudaStream_t s) {
+  constexpr int CG = 64 / NW;
+  CUtensorMap tmDQF, tmDQFb;
+  int rc;
+  {
+    const uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)hd * 4, (uint64_t)H * hd * 4, (uint64_t)L * H * hd * 4};
+    const uint32_t box[4] = {CG, 1, 32, 1};
+    const uint32_t boxb[4] = {16, 1, 32, 1};
+    if ((rc = make_tmap_nd_f32(&tmDQF, acc, 4, dims, strides, box, CG == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap_nd_f32(&tmDQFb, acc, 4, dims, strides, boxb, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_t_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_t_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_t_kernel<RB, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd_t): %s", cudaGetErrorString(e));
     attr_once.done();
   }
+  attention_bwd_t_kernel<RB, NW><<<grid, t2_threads(NW), T2_SMEM_BYTES, s>>>(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats, Lp,
+                                                                         L, H, scale, items, per, causal, Lm, ws, qkv_g, dout_g, hd);
+  return check_launch("attention_bwd_t_kernel");
+}
+
+int launch_attention_bwd_t(const CUtensorMap& tmQKV, const CUtensorMap& tmDO, const CUtensorMap& tmDQKV,
+                           const CUtensorMap& tmQKVb, const CUtensorMap& tmDOb, const CUtensorMap& tmDQKVb, float* acc, int B,
+                           const float* stats, int Lp, int L, int H, float scale, int items, int grid, int causal, int Lm,
+                           const float* ws, const __nv_bfloat16* qkv_g, const __nv_bfloat16* dout_g, int hd, bool warps16,
+                           cudaStream_t s) {
   // whole (image, head)s per CTA: the first key tile's STORE into the dQ accumulator and the adds of the others stay in one CTA
   const int nt = (Lm + T2_T - 1) / T2_T;
   const int per = ((items + grid - 1) / grid + nt - 1) / nt * nt;
-  if (hd > T2_HD)
-    attention_bwd_t_kernel<16><<<grid, T2_THREADS, T2_SMEM_BYTES, s>>>(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats,
-                                                                       Lp, L, H, scale, items, per, causal, Lm, ws, qkv_g, dout_g, hd);
-  else
-    attention_bwd_t_kernel<0><<<grid, T2_THREADS, T2_SMEM_BYTES, s>>>(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, tmDQF, tmDQFb, stats,
-                                                                      Lp, L, H, scale, items, per, causal, Lm, ws, qkv_g, dout_g, hd);
-  return check_launch("attention_bwd_t_kernel");
+#define T2_LAUNCH(RB, NW) \
+  launch_t<RB, NW>(tmQKV, tmDO, tmDQKV, tmQKVb, tmDOb, tmDQKVb, acc, B, stats, Lp, L, H, scale, items, grid, per, causal, Lm, ws, qkv_g, dout_g, hd, s)
+  if (hd > T2_HD) return warps16 ? T2_LAUNCH(16, 4) : T2_LAUNCH(16, 2);
+  return warps16 ? T2_LAUNCH(0, 4) : T2_LAUNCH(0, 2);
+#undef T2_LAUNCH
 }
 
 }  // namespace ovk

@@ -662,6 +662,8 @@ def attention_bwd(qkv, out, dout, lse, B: int, L: int, H: int, hd: int, scale: O
     if mode != "0" and nfused > 0 and not tail_off:
         if mode == "1":
             flags |= 2   # OVK_ATT_BWD_ONEPASS_V1
+        if os.environ.get("OVK_ATTBWD_WARPS", "8") != "16":   # measured: 16 compute warps are 7-10 % slower
+            flags |= 4   # OVK_ATT_BWD_8_WARPS
         flags |= (int(os.environ.get("OVK_ATTBWD_DBG", "0")) & 0xff) << 8   # knock-outs (tools/attn_bwd_knockout.py)
         # one pass over the score tiles; dQ partial sums through an fp32 scratch (attention_bwd.cu, MODE_FUSED)
         ws = torch.empty(nfused, dtype=torch.float32, device=qkv.device)

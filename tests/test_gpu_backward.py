@@ -81,7 +81,7 @@ def test_attention_bwd_wide_heads(ops, hd, B, L, H):
 @pytest.mark.parametrize("B,L,H,hd,causal", [(2, 577, 3, 64, False), (1, 300, 2, 64, True), (3, 77, 2, 64, True), (2, 577, 2, 80, False),
                                              (1, 200, 3, 72, False), (30, 577, 12, 64, False), (20, 640, 8, 80, False),
                                              (1, 1025, 2, 64, False)])
-@pytest.mark.parametrize("mode", ["2", "1"])
+@pytest.mark.parametrize("mode", ["2", "2w16", "1"])
 def test_attention_bwd_one_pass_matches_two_pass(ops, B, L, H, hd, causal, mode, monkeypatch):
     """MODE_FUSED (one walk over the score tiles, dQ through an fp32 scratch + TMA reduce-add) against the two-pass kernels
     on the same inputs: dV comes out of the same MMAs (bitwise equal), dK sees a delta summed in another order, dQ an fp32
@@ -91,6 +91,9 @@ def test_attention_bwd_one_pass_matches_two_pass(ops, B, L, H, hd, causal, mode,
     dout = rnd(B * L, H * hd, seed=L + hd + 8).bfloat16()
     qc, dc = qkv.cuda(), dout.cuda()
     out, lse = ops.attention(qc, B, L, H, hd, save_lse=True, causal=causal)
+    if mode == "2w16":   # attention_bwd_t_kernel with 16 instead of 8 compute warps (A/B variant)
+        monkeypatch.setenv("OVK_ATTBWD_WARPS", "16")
+        mode = "2"
     monkeypatch.setenv("OVK_ATTBWD_FUSED", mode)   # 2: attention_bwd_t_kernel (transposed tiles), 1: attention_bwd_kernel<fused>
     fused = ops.attention_bwd(qc, out, dc, lse, B, L, H, hd, causal=causal)
     monkeypatch.setenv("OVK_ATTBWD_FUSED", "0")
