@@ -166,8 +166,23 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   } else if (warp == ATT_SM_WARPS + 1) {
     if (elect_one()) {
       // ------------------------------------------------------------------ MMA issuer
-      const uint32_t q_addr = smem_u32(sQ);
-      const uint32_t p_addr = smem_u32(sP);
+      // Descriptors as `base low word + constant`: building both 64-bit descriptors of every MMA from addresses costs ~10
+      // uniform-datapath instructions each, which for MMAs this small is more than their tensor time (measured in the attention
+      // backward: profiles/r02_attention_bwd_analysis.md).  The address field counts 16-byte units and never carries out.
+      constexpr uint64_t HI128 = 0x40004040ull << 32;   // SWIZZLE_128B, SBO 1024, descriptor version 1
+      constexpr uint64_t HI32 = 0xC0004010ull << 32;    // SWIZZLE_32B, SBO 256
+      constexpr uint64_t HIROW0 = 0x00004001ull << 32;  // no swizzle, SBO 16 (umma_desc_row0)
+      constexpr uint32_t LBO16 = 1u << 16;
+      constexpr uint32_t LBO_MN = (ATT_TILE_BYTES >> 4) << 16;
+      auto d128 = [](uint32_t lo, uint32_t bytes) { return HI128 | (lo + (bytes >> 4)); };
+      auto d32 = [](uint32_t lo, uint32_t bytes) { return HI32 | (lo + (bytes >> 4)); };
+      auto drow0 = [](uint32_t lo, uint32_t bytes) { return HIROW0 | (lo + (bytes >> 4)); };
+      const uint32_t q_lo = ((smem_u32(sQ) & 0x3FFFF) >> 4) | LBO16;
+      const uint32_t p_lo = ((smem_u32(sP) & 0x3FFFF) >> 4) | LBO16;
+      const uint32_t qb_lo = ((smem_u32(smem + LL::OFF_QB) & 0x3FFFF) >> 4) | LBO16;
+      const uint32_t kt_lo = ((smem_u32(smem + LL::OFF_TAIL) & 0x3FFFF) >> 4) | LBO16;
+      const uint32_t qr_lo = ((smem_u32(smem + LL::OFF_QR) & 0x3FFFF) >> 4) | LBO16;
+      const uint32_t pt_lo = ((smem_u32(smem + LL::OFF_PT) & 0x3FFFF) >> 4) | LBO16;
       int n = 0, g = 0;
       // Issue order per item: S(0) | S(1) P V(0) | S(2) P V(1) | ... | P V(last).  S(j+1) goes out BEFORE P V(j): both
       // wait for the same event (the softmax warps are done with S(j)), and the softmax warps need S(j+1) first —
@@ -176,33 +191,24 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         const int s = gg % NS;
         const int valid = min(ATT_BKV, Lm - j * ATT_BKV);
         const int nblk = (valid + 15) & ~15;  // MMA N of S and K-extent of PV for this block
-        const uint32_t k_addr = smem_u32(sK + s * ATT_TILE_BYTES);
+        const uint32_t k_lo = ((smem_u32(sK + s * ATT_TILE_BYTES) & 0x3FFFF) >> 4) | LBO16;
         mbar_wait(&k_full[s], (gg / NS) & 1, 13);
         tc_fence_after();
         const uint32_t idesc_s = umma_idesc_bf16(ATT_BQ, nblk, 0, 0);
 #pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k) {
-          umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_kmajor_sw128(q_addr + k * 32),
-                       umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
-        }
+        for (int k = 0; k < ATT_HD / 16; ++k) umma_bf16_ss(tmem_base + ATT_TMEM_S, d128(q_lo, k * 32), d128(k_lo, k * 32), idesc_s, k != 0);
         if (RB)   // dims 64 .. 64 + RB: one more k-step from the narrow tiles
-          umma_bf16_ss(tmem_base + ATT_TMEM_S, umma_desc_sw32(smem_u32(smem + LL::OFF_QB)),
-                       umma_desc_sw32(smem_u32(smem + LL::OFF_KB + s * ATT_BT)), idesc_s, 1);
+          umma_bf16_ss(tmem_base + ATT_TMEM_S, d32(qb_lo, 0), d32(((smem_u32(smem + LL::OFF_KB + s * ATT_BT) & 0x3FFFF) >> 4) | LBO16, 0),
+                       idesc_s, 1);
         if (RB == 0 && ntail > 0 && j == 0) {   // scores against the remainder key: s_k = Q k_t^T (N = 16, column 0 is real)
           constexpr uint32_t idesc_sk = umma_idesc_bf16(128, 16, 0, 0);
-          const uint32_t kt_addr = smem_u32(smem + LL::OFF_TAIL);
 #pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + ATT_TMEM_SK, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_row0(kt_addr + k * 32),
-                         idesc_sk, k != 0);
+          for (int k = 0; k < ATT_HD / 16; ++k) umma_bf16_ss(tmem_base + ATT_TMEM_SK, d128(q_lo, k * 32), drow0(kt_lo, k * 32), idesc_sk, k != 0);
         }
         if (titem) {   // S_t^T = K_j q_t^T
           constexpr uint32_t idesc_st = umma_idesc_bf16(128, 16, 0, 0);
-          const uint32_t qr_addr = smem_u32(smem + LL::OFF_QR);
 #pragma unroll
-          for (int k = 0; k < ATT_HD / 16; ++k)
-            umma_bf16_ss(tmem_base + ATT_TMEM_ST, umma_desc_kmajor_sw128(k_addr + k * 32), umma_desc_row0(qr_addr + k * 32),
-                         idesc_st, k != 0);
+          for (int k = 0; k < ATT_HD / 16; ++k) umma_bf16_ss(tmem_base + ATT_TMEM_ST, d128(k_lo, k * 32), drow0(qr_lo, k * 32), idesc_st, k != 0);
         }
         umma_commit(&k_empty[s]);
         umma_commit(s_full);
@@ -226,27 +232,36 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           tc_fence_after();
           constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BQ, ATT_HD, 0, 1);
           const int ksteps = nblk / 16;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
-            const uint32_t bb = v_addr + kk * 16 * 128;
-            umma_bf16_ss(tmem_base + ATT_TMEM_O, umma_desc_kmajor_sw128(a), umma_desc_mnmajor_sw128(bb, ATT_TILE_BYTES),
-                         idesc_pv, (j | kk) != 0);
+          const uint32_t v_lo = ((v_addr & 0x3FFFF) >> 4) | LBO_MN;
+          if (ksteps == 8) {   // full key block: straight-line
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ss(tmem_base + ATT_TMEM_O, d128(p_lo, (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32), d128(v_lo, kk * 2048), idesc_pv,
+                           (j | kk) != 0);
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk)
+              umma_bf16_ss(tmem_base + ATT_TMEM_O, d128(p_lo, (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32), d128(v_lo, kk * 2048), idesc_pv,
+                           (j | kk) != 0);
           }
           if (RB) {   // output dims 64 .. 64 + RB: N = 16 accumulator, V_b consumed MN-major from its 32-byte rows
             constexpr uint32_t idesc_pvb = umma_idesc_bf16(ATT_BQ, 16, 0, 1);
-            const uint32_t vb_addr = smem_u32(smem + LL::OFF_VB + s * ATT_BT);
-            for (int kk = 0; kk < ksteps; ++kk) {
-              const uint32_t a = p_addr + (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32;
-              umma_bf16_ss(tmem_base + ATT_TMEM_OB, umma_desc_kmajor_sw128(a), umma_desc_sw32(vb_addr + kk * 512), idesc_pvb,
-                           (j | kk) != 0);
+            const uint32_t vb_lo = ((smem_u32(smem + LL::OFF_VB + s * ATT_BT) & 0x3FFFF) >> 4) | LBO16;
+            if (ksteps == 8) {
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk)
+                umma_bf16_ss(tmem_base + ATT_TMEM_OB, d128(p_lo, (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32), d32(vb_lo, kk * 512), idesc_pvb,
+                             (j | kk) != 0);
+            } else {
+              for (int kk = 0; kk < ksteps; ++kk)
+                umma_bf16_ss(tmem_base + ATT_TMEM_OB, d128(p_lo, (kk >> 2) * ATT_TILE_BYTES + (kk & 3) * 32), d32(vb_lo, kk * 512), idesc_pvb,
+                             (j | kk) != 0);
             }
           }
           if (titem) {   // O_t^T += V_j^T p_t^T  (A = V MN-major: M runs over head dims; rows 64..127 are padding)
             constexpr uint32_t idesc_ot = umma_idesc_bf16(128, 16, 1, 0);
-            const uint32_t pt_addr = smem_u32(smem + LL::OFF_PT);
+#pragma unroll
             for (int kk = 0; kk < ATT_BKV / 16; ++kk)
-              umma_bf16_ss(tmem_base + ATT_TMEM_OT, umma_desc_mnmajor_sw128(v_addr + kk * 16 * 128, ATT_TILE_BYTES),
-                           umma_desc_row0(pt_addr + kk * 32), idesc_ot, (j | kk) != 0);
+              umma_bf16_ss(tmem_base + ATT_TMEM_OT, d128(v_lo, kk * 2048), drow0(pt_lo, kk * 32), idesc_ot, (j | kk) != 0);
           }
           umma_commit(&v_empty[s]);
           umma_commit(pv_done);

@@ -613,9 +613,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 constexpr int ABT_THREADS = 256;
 constexpr int ABT_WARPS = ABT_THREADS / 32;
 
-__device__ __forceinline__ float abt_dot8(const uint4& u, const float (&v)[8]) {
-  return fmaf(bf16_lo(u.x), v[0], fmaf(bf16_hi(u.x), v[1], fmaf(bf16_lo(u.y), v[2], fmaf(bf16_hi(u.y), v[3],
-         fmaf(bf16_lo(u.z), v[4], fmaf(bf16_hi(u.z), v[5], fmaf(bf16_lo(u.w), v[6], bf16_hi(u.w) * v[7])))))));
+// 8 bf16 of a row times 8 fp32 of one of the remainder token's vectors (kept in shared memory: the four vectors as registers
+// cost 32 of them and a third resident CTA per SM)
+__device__ __forceinline__ float abt_dot8(const uint4& u, const float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(v), b = *reinterpret_cast<const float4*>(v + 4);
+  return fmaf(bf16_lo(u.x), a.x, fmaf(bf16_hi(u.x), a.y, fmaf(bf16_lo(u.y), a.z, fmaf(bf16_hi(u.y), a.w,
+         fmaf(bf16_lo(u.z), b.x, fmaf(bf16_hi(u.z), b.y, fmaf(bf16_lo(u.w), b.z, bf16_hi(u.w) * b.w)))))));
 }
 __device__ __forceinline__ float abt_dot8b(const uint4& u, const uint4& w) {
   return fmaf(bf16_lo(u.x), bf16_lo(w.x), fmaf(bf16_hi(u.x), bf16_hi(w.x), fmaf(bf16_lo(u.y), bf16_lo(w.y), fmaf(bf16_hi(u.y), bf16_hi(w.y),
@@ -629,7 +632,7 @@ __device__ __forceinline__ void abt_axpy8(float (&a)[8], float c, const uint4& u
 }
 
 template <int LPR>   // lanes per row: 8 (hd = 64) or 16 (64 < hd <= 128: the lanes past hd / 8 idle)
-__global__ void __launch_bounds__(ABT_THREADS, 2)
+__global__ void __launch_bounds__(ABT_THREADS, 3)
 attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                           const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                           float* __restrict__ ws, int L, int H, int hd, float scale, float* __restrict__ delta_out,
@@ -637,7 +640,7 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   // delta_out / stats (optional): this kernel computes delta_j = dO_j . O_j of every token anyway, so for the one-pass tile
   // kernel it also leaves what attention_bwd_delta_kernel would (delta [B, H, L]; stats [B * H][2][Lp], Lp = L - 1)
   constexpr int RPW = 32 / LPR;               // rows per warp and trip
-  __shared__ float vec[5][LPR * 8];           // q_t, k_t, v_t, dO_t, O_t (zero past hd)
+  __shared__ __align__(16) float vec[5][LPR * 8];   // q_t, k_t, v_t, dO_t, O_t (zero past hd)
   __shared__ float red[ABT_WARPS][3][LPR * 8];
   const int Lm = L - 1, t = L - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -664,20 +667,13 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   float delta_t = 0.f;
   for (int d = 0; d < hd; ++d) delta_t = fmaf(vec[3][d], vec[4][d], delta_t);
   const float lse_t2 = lse[bh * L + t] * 1.4426950408889634f;
-  float qt[8], kt[8], vt[8], dt[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    qt[e] = vec[0][sub * 8 + e];
-    kt[e] = vec[1][sub * 8 + e];
-    vt[e] = vec[2][sub * 8 + e];
-    dt[e] = vec[3][sub * 8 + e];
-  }
+  const float *qt = &vec[0][sub * 8], *kt = &vec[1][sub * 8], *vt = &vec[2][sub * 8], *dt = &vec[3][sub * 8];
   float* wsb = ws + bh * 3 * Lm;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dq_t = scale * sum_j dS(t, j) k_j
   float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dk_t = scale * sum_i dS(i, t) q_i
   float av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dv_t = sum_i P(i, t) dO_i
   const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 2
+#pragma unroll 1
   for (int j0 = warp * RPW; j0 < L; j0 += ABT_WARPS * RPW) {   // warp-uniform trip count (full-mask shuffles below)
     const int j = j0 + grp;
     const bool ok = j < L;

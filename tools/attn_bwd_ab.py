@@ -32,10 +32,10 @@ for (B, H, L, hd) in ((256, 16, 257, 64), (1024, 16, 257, 64), (512, 12, 577, 64
     os.environ["OVK_ATTBWD_FUSED"] = "1"
     bf1 = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
     os.environ["OVK_ATTBWD_FUSED"] = "2"
-    os.environ["OVK_ATTBWD_WARPS"] = "8"
-    bf8 = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
     os.environ["OVK_ATTBWD_WARPS"] = "16"
+    bf16w = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
+    os.environ["OVK_ATTBWD_WARPS"] = "8"
     bf = t(lambda: ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd))
     fl = 4.0 * B * H * L * L * hd
-    print(f"B{B} H{H} L{L} hd{hd}: fwd {f:.3f} ms {fl / f / 1e9:.0f} TF/s   bwd one-pass {bf:.3f} ms {2.5 * fl / bf / 1e9:.0f} TF/s (10 B H L^2 hd)   [8 compute warps {bf8:.3f} ms, v1 {bf1:.3f} ms]   "
+    print(f"B{B} H{H} L{L} hd{hd}: fwd {f:.3f} ms {fl / f / 1e9:.0f} TF/s   bwd one-pass {bf:.3f} ms {2.5 * fl / bf / 1e9:.0f} TF/s (10 B H L^2 hd)   [16 compute warps {bf16w:.3f} ms, v1 {bf1:.3f} ms]   "
           f"two-pass {b:.3f} ms {3.5 * fl / b / 1e9:.0f} TF/s (14 B H L^2 hd)   [two-pass, remainder token as tiles: {b0:.3f} ms]", flush=True)
