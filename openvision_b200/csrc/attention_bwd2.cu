@@ -213,6 +213,16 @@ attention_bwd_t_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_c
           tma_load_4d(smem + T2_OFF_KB, &tmQKVb, &st_full[buf], 64, H + h, t0, b);
           tma_load_4d(smem + T2_OFF_VB, &tmQKVb, &st_full[buf], 64, 2 * H + h, t0, b);
         }
+        if (NST == 1 && n + 1 < n_items) {
+          // one stationary set: the next item's K / V can only be fetched when this item's last MMA has completed, and the
+          // scores of its first tile wait for them.  Pulling the tiles into L2 now takes the DRAM part out of that wait.
+          const int item1 = item + 1;
+          const int t1 = (item1 % nt) * T2_T, h1 = (item1 / nt) % H, b1 = item1 / (nt * H);
+          tma_prefetch_l2_4d(&tmQKV, 0, H + h1, t1, b1);
+          tma_prefetch_l2_4d(&tmQKV, 0, 2 * H + h1, t1, b1);
+          tma_prefetch_l2_4d(&tmQKVb, 64, H + h1, t1, b1);
+          tma_prefetch_l2_4d(&tmQKVb, 64, 2 * H + h1, t1, b1);
+        }
       }
       const int s = G & 1;
       t2_wait_t(&se[s], ((G >> 1) & 1) ^ 1, 41, spin, prof, w1);
