@@ -271,7 +271,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
   const int wib = threadIdx.x >> 5;
   const int nvec = D >> 3;
   const int warps_total = gridDim.x * (blockDim.x >> 5);
-  float gm[G_SMEM ? 1 : MAXV][8], dg[MAXV][8], db[MAXV][8];
+  // Packed fp32 pairs throughout (FFMA2 / FMUL2 / FADD2 on aligned register pairs): inside a training step the SMs run at
+  // 1.2-1.3 GHz under the power cap and the 19 scalar instructions per element of the first version made this kernel
+  // issue-bound there (0.62 of the HBM rate in the step against 0.87 alone); with xhat = x * rstd + (-mean * rstd) as one FMA
+  // and the output as three, it is 11.
+  uint64_t gm[G_SMEM ? 1 : MAXV][4], dg[MAXV][4], db[MAXV][4];
   float* gs = red + 16 * DP;
   if (G_SMEM) {
     for (int c = threadIdx.x; c < DP; c += blockDim.x) gs[c] = c < D ? gamma[c] : 0.f;
@@ -283,21 +287,28 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
       const int v = lane + i * 32;
       const float4 g0 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 g1 = v < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + 2 * v + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-      gm[i][0] = g0.x; gm[i][1] = g0.y; gm[i][2] = g0.z; gm[i][3] = g0.w;
-      gm[i][4] = g1.x; gm[i][5] = g1.y; gm[i][6] = g1.z; gm[i][7] = g1.w;
+      gm[i][0] = f2_pack(g0.x, g0.y); gm[i][1] = f2_pack(g0.z, g0.w);
+      gm[i][2] = f2_pack(g1.x, g1.y); gm[i][3] = f2_pack(g1.z, g1.w);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dg[i][j] = db[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) dg[i][j] = db[i][j] = f2_pack(0.f, 0.f);
   }
-  auto gamma_of = [&](int i, float (&g)[8]) {
+  auto gamma_of = [&](int i, uint64_t (&g)[4]) {
     if (G_SMEM) {
       const float4 a = *reinterpret_cast<const float4*>(gs + (lane + i * 32) * 8);
       const float4 b = *reinterpret_cast<const float4*>(gs + (lane + i * 32) * 8 + 4);
-      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+      g[0] = f2_pack(a.x, a.y); g[1] = f2_pack(a.z, a.w); g[2] = f2_pack(b.x, b.y); g[3] = f2_pack(b.z, b.w);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = gm[G_SMEM ? 0 : i][j];
+      for (int j = 0; j < 4; ++j) g[j] = gm[G_SMEM ? 0 : i][j];
     }
+  };
+  // the four 32-bit words of a 16-byte vector as fp32 pairs (elements 2j, 2j + 1)
+  auto unpack4 = [](const uint4& u, uint64_t (&f)[4]) {
+    f[0] = f2_pack(bf16_lo(u.x), bf16_hi(u.x));
+    f[1] = f2_pack(bf16_lo(u.y), bf16_hi(u.y));
+    f[2] = f2_pack(bf16_lo(u.z), bf16_hi(u.z));
+    f[3] = f2_pack(bf16_lo(u.w), bf16_hi(u.w));
   };
   for (int row = blockIdx.x * (blockDim.x >> 5) + wib; row < rows; row += warps_total) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<long long>(row) * ldx);
@@ -313,38 +324,51 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
       rr[i] = (ok && drr) ? drr[v] : make_uint4(0, 0, 0, 0);
     }
     const float mu = mean[row], rs = rstd[row];
-    float s1 = 0.f, s2 = 0.f;
+    const uint64_t a2 = f2_pack(rs, rs), b2 = f2_pack(-mu * rs, -mu * rs);   // xhat = x * a + b
+    uint64_t s1 = f2_pack(0.f, 0.f), s2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      float fx[8], fd[8], gv[8];
-      unpack8(rx[i], fx);
-      unpack8(rd[i], fd);
+      uint64_t fx[4], fd[4], gv[4];
+      unpack4(rx[i], fx);
+      unpack4(rd[i], fd);
       gamma_of(i, gv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (fx[j] - mu) * rs;
-        const float g = fd[j] * gv[j];
-        s1 += g;
-        s2 = fmaf(g, xh, s2);
-        dg[i][j] = fmaf(fd[j], xh, dg[i][j]);
-        db[i][j] += fd[j];
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t xh = f2_fma(fx[j], a2, b2);
+        const uint64_t g = f2_mul(fd[j], gv[j]);
+        s1 = f2_add(s1, g);
+        s2 = f2_fma(g, xh, s2);
+        dg[i][j] = f2_fma(fd[j], xh, dg[i][j]);
+        db[i][j] = f2_add(db[i][j], fd[j]);
       }
     }
-    const float m1 = warp_sum(s1) / static_cast<float>(D);
-    const float m2 = warp_sum(s2) / static_cast<float>(D);
+    float s1a, s1b, s2a, s2b;
+    f2_unpack(s1, s1a, s1b);
+    f2_unpack(s2, s2a, s2b);
+    const float m1 = warp_sum(s1a + s1b) / static_cast<float>(D);
+    const float m2 = warp_sum(s2a + s2b) / static_cast<float>(D);
+    // dx = rstd * (dy * gamma - m1 - xhat * m2) + dres  =  (dy * gamma) * rstd + dres  +  xhat * (-rstd * m2)  +  (-rstd * m1)
+    const uint64_t c1 = f2_pack(-rs * m1, -rs * m1), c2 = f2_pack(-rs * m2, -rs * m2);
     uint4* dxr = reinterpret_cast<uint4*>(dx + static_cast<long long>(row) * lddx);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int v = lane + i * 32;
       if (v < nvec) {
-        float fx[8], fd[8], fr[8], o[8], gv[8];
-        unpack8(rx[i], fx);
-        unpack8(rd[i], fd);
-        unpack8(rr[i], fr);
+        uint64_t fx[4], fd[4], fr[4], gv[4];
+        unpack4(rx[i], fx);
+        unpack4(rd[i], fd);
+        unpack4(rr[i], fr);
         gamma_of(i, gv);
+        uint32_t ow[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(rs, fd[j] * gv[j] - m1 - (fx[j] - mu) * rs * m2, fr[j]);
-        dxr[v] = pack8(o);
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t xh = f2_fma(fx[j], a2, b2);
+          const uint64_t t = f2_fma(f2_mul(fd[j], gv[j]), a2, fr[j]);
+          float o0, o1;
+          f2_unpack(f2_add(f2_fma(xh, c2, t), c1), o0, o1);
+          ow[j] = pack_bf16x2(o0, o1);
+        }
+        dxr[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
   }
@@ -352,10 +376,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(const __nv_bfl
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = (lane + i * 32) * 8 + j;
-      red[(wib * 2 + 0) * DP + c] = dg[i][j];
-      red[(wib * 2 + 1) * DP + c] = db[i][j];
+    for (int j = 0; j < 4; ++j) {
+      const int c = (lane + i * 32) * 8 + 2 * j;
+      float g0, g1, b0, b1;
+      f2_unpack(dg[i][j], g0, g1);
+      f2_unpack(db[i][j], b0, b1);
+      red[(wib * 2 + 0) * DP + c] = g0;
+      red[(wib * 2 + 0) * DP + c + 1] = g1;
+      red[(wib * 2 + 1) * DP + c] = b0;
+      red[(wib * 2 + 1) * DP + c + 1] = b1;
     }
   __syncthreads();
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
