@@ -117,6 +117,40 @@ def test_attention_bwd_one_pass_matches_two_pass(ops, B, L, H, hd, causal, mode,
             assert_grad(gf[:, :, i], r[:, :, i], f"one-pass d{name}", 3e-2)
 
 
+@pytest.mark.parametrize("B,L,H,hd", [(1024, 257, 16, 64), (512, 577, 12, 64), (256, 257, 16, 80)])
+def test_attention_bwd_full_size_invariants(ops, B, L, H, hd):
+    """BASELINE-size shapes (L/14 and H/14 at 257 tokens, B/16@384 at 577), where an fp32 reference of the whole problem is
+    out of reach on the host: two size-independent identities of softmax attention (transformer.py:225,250-252).
+      rows of P sum to one            =>  sum_j dV[j] = sum_i dO[i]                     per (image, head)
+      f(a q, k / a) does not depend on a  =>  <dQ, Q> = <dK, K>                          per (image, head)
+    plus a sampled (image, head) against autograd of the fp32 composition."""
+    g = torch.Generator(device="cuda").manual_seed(L + hd)
+    qkv = (torch.randn(B * L, 3 * H * hd, device="cuda", generator=g) * 0.7).bfloat16()
+    dout = torch.randn(B * L, H * hd, device="cuda", generator=g).bfloat16()
+    out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+    dqkv = ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd)
+    q5, d5 = qkv.view(B, L, 3, H, hd).float(), dqkv.view(B, L, 3, H, hd).float()
+    do4 = dout.view(B, L, H, hd).float()
+    assert torch.isfinite(d5).all()
+    # sum_j dV_j = sum_i dO_i.  Two roundings: the bf16 outputs (2^-9 relative each) and the bf16 P the tensor core consumes
+    # (rows of the rounded P sum to 1 + eps_i, |eps_i| ~ 2^-9, independent: six standard deviations of sum_i eps_i dO_i)
+    lhs, rhs = d5[:, :, 2].sum(1), do4.sum(1)
+    tol = 2.0 ** -8 * d5[:, :, 2].abs().sum(1) + 6.0 * 2.0 ** -9 * do4.pow(2).sum(1).sqrt() + 1e-3
+    assert bool(((lhs - rhs).abs() <= tol).all()), float((lhs - rhs).abs().max())
+    # <dQ, Q> = <dK, K>
+    a = (d5[:, :, 0] * q5[:, :, 0]).sum((1, 3))
+    b = (d5[:, :, 1] * q5[:, :, 1]).sum((1, 3))
+    scale_ab = (d5[:, :, 0] * q5[:, :, 0]).abs().sum((1, 3)) + (d5[:, :, 1] * q5[:, :, 1]).abs().sum((1, 3))
+    assert bool(((a - b).abs() <= 2.0 ** -7 * scale_ab + 1e-3).all()), float(((a - b).abs() / (scale_ab + 1e-9)).max())
+    # one (image, head) in full against fp32 autograd
+    bi, hi = B - 1, H // 2
+    qf = q5[bi, :, :, hi].cpu().clone().requires_grad_(True)           # [L, 3, hd]
+    sc = (qf[:, 0] @ qf[:, 1].T) / math.sqrt(hd)
+    (torch.softmax(sc, -1) @ qf[:, 2]).backward(do4[bi, :, hi].cpu())
+    for i, name in enumerate("qkv"):
+        assert_grad(d5[bi, :, i, hi].cpu(), qf.grad[:, i], f"full-size d{name} of image {bi} head {hi}", 3e-2)
+
+
 def test_h14_style_tower_forward_backward_vs_oracle():
     """head width 80 (H/14, BASELINE configs[4]) end to end at toy size: embeddings and image / parameter gradients
     against autograd of the CPU oracle (no golden fixture for this config: the oracle is pinned on the others)."""
