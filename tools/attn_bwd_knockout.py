@@ -1,5 +1,8 @@
 """Knock-out timings of attention_bwd_t_kernel (results wrong on purpose): which part of an iteration bounds the kernel.
-bits: 1 no TMA reduce-add, 2 no dQ drain at all, 4 no softmax work (TMEM loads, exponentials, P / dS stores), 8 no dQ MMA, 16 spinning instead of suspending barrier waits.
+bits: 1 no TMA reduce-add, 2 no dQ drain at all, 4 no softmax work (TMEM loads, exponentials, P / dS stores), 8 no dQ MMA, 16 spinning instead of suspending barrier waits,
+32 per-wait / per-issue-site cycle counters printed by block 0, 64 no dV / dK MMAs, 128 no score MMAs.
+Needs libovk built with the debug hooks: make -C openvision_b200/csrc clean all NVCCFLAGS_EXTRA=-DOVK_ATTBWD_DEBUG
+(the shipped library compiles them out; the bits are then ignored).
 usage (GPU box): python tools/attn_bwd_knockout.py [B H L hd]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
