@@ -612,13 +612,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 // heads x 80 dims where the traffic bound is 0.5 ms.)
 constexpr int ABT_THREADS = 256;
 constexpr int ABT_WARPS = ABT_THREADS / 32;
+constexpr int ABT_STAGES = 3;
+constexpr int ABT_STAGE_BYTES = ABT_STAGES * ABT_THREADS * 80;   // 60 KB: three CTAs per SM
 
 // 8 bf16 of a row times 8 fp32 of one of the remainder token's vectors (kept in shared memory: the four vectors as registers
 // cost 32 of them and a third resident CTA per SM)
-__device__ __forceinline__ float abt_dot8(const uint4& u, const float* v) {
+__device__ __forceinline__ float abt_dot8(const uint4& u, const float* v) {   // v in shared memory
   const float4 a = *reinterpret_cast<const float4*>(v), b = *reinterpret_cast<const float4*>(v + 4);
   return fmaf(bf16_lo(u.x), a.x, fmaf(bf16_hi(u.x), a.y, fmaf(bf16_lo(u.y), a.z, fmaf(bf16_hi(u.y), a.w,
          fmaf(bf16_lo(u.z), b.x, fmaf(bf16_hi(u.z), b.y, fmaf(bf16_lo(u.w), b.z, bf16_hi(u.w) * b.w)))))));
+}
+__device__ __forceinline__ float abt_dot8(const uint4& u, const float (&v)[8]) {
+  return fmaf(bf16_lo(u.x), v[0], fmaf(bf16_hi(u.x), v[1], fmaf(bf16_lo(u.y), v[2], fmaf(bf16_hi(u.y), v[3],
+         fmaf(bf16_lo(u.z), v[4], fmaf(bf16_hi(u.z), v[5], fmaf(bf16_lo(u.w), v[6], bf16_hi(u.w) * v[7])))))));
 }
 __device__ __forceinline__ float abt_dot8b(const uint4& u, const uint4& w) {
   return fmaf(bf16_lo(u.x), bf16_lo(w.x), fmaf(bf16_hi(u.x), bf16_hi(w.x), fmaf(bf16_lo(u.y), bf16_lo(w.y), fmaf(bf16_hi(u.y), bf16_hi(w.y),
@@ -631,8 +637,30 @@ __device__ __forceinline__ void abt_axpy8(float (&a)[8], float c, const uint4& u
   a[6] = fmaf(c, bf16_lo(u.w), a[6]); a[7] = fmaf(c, bf16_hi(u.w), a[7]);
 }
 
-template <int LPR>   // lanes per row: 8 (hd = 64) or 16 (64 < hd <= 128: the lanes past hd / 8 idle)
-__global__ void __launch_bounds__(ABT_THREADS, 3)
+// Sum of v over the LPR lanes of a row group, delivered to all of them.  LPR = 8: xor butterfly.  LPR = 10 (head widths 72 / 80:
+// ten 16-byte chunks per row, three rows per warp, lanes 30 / 31 idle): fold the upper five lanes onto the lower five, add those
+// five up in lane 0 of the group, broadcast.  (The kernel is bound by its instruction stream: with 16 lanes per row, ten of them
+// loading, every row cost 16 lane-passes and the wide-head kernel ran at 49 % issue utilisation and 32 % of the HBM rate.)
+template <int LPR>
+__device__ __forceinline__ float abt_group_sum(float v, int base) {
+  if (LPR == 8) {
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  } else {
+    v += __shfl_down_sync(0xffffffffu, v, 5);           // lanes 0..4 of the group: a_i + a_(i+5)
+    float t = v + __shfl_down_sync(0xffffffffu, v, 1);  // lane 0: c0 + c1, lane 2: c2 + c3
+    t += __shfl_down_sync(0xffffffffu, t, 2);           // lane 0: c0 + c1 + c2 + c3
+    t += __shfl_down_sync(0xffffffffu, v, 4);           // lane 0: + c4
+    return __shfl_sync(0xffffffffu, t, base);
+  }
+}
+
+// LPR lanes per row: 8 (hd = 64) or 10 (hd = 72 / 80; three rows per warp).  PIPE: rows through the cp.async pipeline and the
+// token's vectors in registers (two CTAs per SM) instead of plain loads and vectors in shared memory (three CTAs).  Measured
+// (ncu, batch 1024 x 16 heads x 257 tokens): hd 64: plain 0.75 ms, pipeline 0.84-0.86; hd 80: plain 1.38, pipeline 1.08.
+template <int LPR, bool PIPE>
+__global__ void __launch_bounds__(ABT_THREADS, PIPE ? 2 : 3)
 attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
                           const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
                           float* __restrict__ ws, int L, int H, int hd, float scale, float* __restrict__ delta_out,
@@ -644,8 +672,9 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   __shared__ float red[ABT_WARPS][3][LPR * 8];
   const int Lm = L - 1, t = L - 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sub = lane % LPR, grp = lane / LPR;
-  const bool active = sub * 8 < hd;
+  const int grp = lane / LPR;                 // LPR = 10: lanes 30, 31 form an idle fourth group
+  const int sub = lane - grp * LPR;
+  const bool active = grp < RPW && sub * 8 < hd;
   const int h = blockIdx.x;
   const long long b = blockIdx.y;
   const long long bh = b * H + h;
@@ -655,48 +684,103 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   const __nv_bfloat16* ob = out + b * L * otok + h * hd;
   const __nv_bfloat16* db = dout + b * L * otok + h * hd;
   const float s2 = scale * 1.4426950408889634f;
+  __shared__ float part[ABT_WARPS];
+  float pr = 0.f;   // this thread's share of delta_t = dO_t . O_t
   for (int d = tid; d < LPR * 8; d += ABT_THREADS) {
     const bool in = d < hd;
+    const float dv = in ? __bfloat162float(db[t * otok + d]) : 0.f;
+    const float ov = in ? __bfloat162float(ob[t * otok + d]) : 0.f;
     vec[0][d] = in ? __bfloat162float(qb[t * qtok + d]) : 0.f;
     vec[1][d] = in ? __bfloat162float(qb[t * qtok + H * hd + d]) : 0.f;
     vec[2][d] = in ? __bfloat162float(qb[t * qtok + 2 * H * hd + d]) : 0.f;
-    vec[3][d] = in ? __bfloat162float(db[t * otok + d]) : 0.f;
-    vec[4][d] = in ? __bfloat162float(ob[t * otok + d]) : 0.f;
+    vec[3][d] = dv;
+    vec[4][d] = ov;
+    pr = fmaf(dv, ov, pr);
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, off);
+  if (lane == 0) part[warp] = pr;
   __syncthreads();
-  float delta_t = 0.f;
-  for (int d = 0; d < hd; ++d) delta_t = fmaf(vec[3][d], vec[4][d], delta_t);
+  float delta_t = 0.f;   // (every thread walking the two vectors itself: 2 x hd shared-memory loads per thread and CTA)
+#pragma unroll
+  for (int w = 0; w < ABT_WARPS; ++w) delta_t += part[w];
   const float lse_t2 = lse[bh * L + t] * 1.4426950408889634f;
-  const float *qt = &vec[0][sub * 8], *kt = &vec[1][sub * 8], *vt = &vec[2][sub * 8], *dt = &vec[3][sub * 8];
+  // the token's own vectors in registers: re-reading them from shared memory for every row (8 LDS.128 per trip) kept the
+  // L1 / shared-memory pipe, which also carries the cp.async stream below, at 75 %
+  float qt[8], kt[8], vt[8], dt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    qt[e] = vec[0][sub * 8 + e];
+    kt[e] = vec[1][sub * 8 + e];
+    vt[e] = vec[2][sub * 8 + e];
+    dt[e] = vec[3][sub * 8 + e];
+  }
+  const float *qs = &vec[0][sub * 8], *ks = &vec[1][sub * 8], *vs = &vec[2][sub * 8], *ds = &vec[3][sub * 8];
   float* wsb = ws + bh * 3 * Lm;
   float aq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dq_t = scale * sum_j dS(t, j) k_j
   float ak[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dk_t = scale * sum_i dS(i, t) q_i
   float av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // dv_t = sum_i P(i, t) dO_i
-  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll 1
-  for (int j0 = warp * RPW; j0 < L; j0 += ABT_WARPS * RPW) {   // warp-uniform trip count (full-mask shuffles below)
-    const int j = j0 + grp;
-    const bool ok = j < L;
-    const bool ld = ok && active;
-    const uint4 qq = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok) + sub) : z4;
-    const uint4 kk = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + H * hd) + sub) : z4;
-    const uint4 vv = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + 2 * H * hd) + sub) : z4;
-    const uint4 dd = ld ? __ldg(reinterpret_cast<const uint4*>(db + j * otok) + sub) : z4;
-    const uint4 oo = ld ? __ldg(reinterpret_cast<const uint4*>(ob + j * otok) + sub) : z4;
-    const float lse_j2 = ok ? __ldg(lse + bh * L + j) * 1.4426950408889634f : 0.f;
-    float s1 = abt_dot8(kk, qt);     // q_t . k_j      token j as a key of row t
-    float dp1 = abt_dot8(vv, dt);    // dO_t . v_j
-    float s2q = abt_dot8(qq, kt);    // q_j . k_t      token j as a query of column t
-    float dp2 = abt_dot8(dd, vt);    // dO_j . v_t
-    float dl = abt_dot8b(dd, oo);    // delta_j = dO_j . O_j
-#pragma unroll
-    for (int off = 1; off < LPR; off <<= 1) {
-      s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-      dp1 += __shfl_xor_sync(0xffffffffu, dp1, off);
-      s2q += __shfl_xor_sync(0xffffffffu, s2q, off);
-      dp2 += __shfl_xor_sync(0xffffffffu, dp2, off);
-      dl += __shfl_xor_sync(0xffffffffu, dl, off);
+  // PIPE: the rows come in through a three-deep cp.async pipeline, each lane fetching (and later reading back) its own five
+  // 16-byte chunks (wide heads: neither fewer instructions per row nor contiguous rows nor a cheaper prologue moved the
+  // plain-load kernel off 1.38 ms = 2.4 TB/s; two more trips in flight did).
+  extern __shared__ __align__(16) uint8_t abt_stage[];   // [ABT_STAGES][ABT_THREADS][5] x 16 bytes, lane-private records
+  const int ntrips = (L + ABT_WARPS * RPW - 1) / (ABT_WARPS * RPW);   // the same for every warp (rows past L are zero-filled)
+  auto issue = [&](int trip) {
+    if (trip < ntrips) {
+      const int jj = trip * ABT_WARPS * RPW + warp * RPW + grp;
+      const bool ldd = jj < L && active;
+      const uint32_t nb = ldd ? 16u : 0u;
+      const long long jr = ldd ? jj : 0;
+      const uint32_t dst = smem_u32(abt_stage) + ((trip % ABT_STAGES) * ABT_THREADS + tid) * 80;
+      cp_async_16(dst, reinterpret_cast<const uint4*>(qb + jr * qtok) + sub, nb);
+      cp_async_16(dst + 16, reinterpret_cast<const uint4*>(qb + jr * qtok + H * hd) + sub, nb);
+      cp_async_16(dst + 32, reinterpret_cast<const uint4*>(qb + jr * qtok + 2 * H * hd) + sub, nb);
+      cp_async_16(dst + 48, reinterpret_cast<const uint4*>(db + jr * otok) + sub, nb);
+      cp_async_16(dst + 64, reinterpret_cast<const uint4*>(ob + jr * otok) + sub, nb);
     }
+    cp_async_commit();   // (an empty group past the last trip keeps the wait count uniform)
+  };
+  auto lse_of = [&](int trip) {
+    const int jj = trip * ABT_WARPS * RPW + warp * RPW + grp;
+    return (trip < ntrips && jj < L && grp < RPW) ? __ldg(lse + bh * L + jj) * 1.4426950408889634f : 0.f;
+  };
+  if (PIPE) {
+    issue(0);
+    issue(1);
+  }
+  float lse_a = lse_of(0), lse_b = lse_of(1);
+#pragma unroll 1
+  for (int trip = 0; trip < ntrips; ++trip) {
+    if (PIPE) issue(trip + 2);
+    const float lse_j2 = lse_a;
+    lse_a = lse_b;
+    lse_b = lse_of(trip + 2);
+    const int j = trip * ABT_WARPS * RPW + warp * RPW + grp;
+    const bool ok = j < L && grp < RPW;
+    uint4 qq, kk, vv, dd, oo;
+    if (PIPE) {
+      cp_async_wait_group<2>();   // this trip's five chunks have landed (the two younger groups may still be in flight)
+      const uint32_t src = smem_u32(abt_stage) + ((trip % ABT_STAGES) * ABT_THREADS + tid) * 80;
+      qq = lds128(src), kk = lds128(src + 16), vv = lds128(src + 32), dd = lds128(src + 48), oo = lds128(src + 64);
+    } else {
+      const bool ld = ok && active;
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      qq = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok) + sub) : z4;
+      kk = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + H * hd) + sub) : z4;
+      vv = ld ? __ldg(reinterpret_cast<const uint4*>(qb + j * qtok + 2 * H * hd) + sub) : z4;
+      dd = ld ? __ldg(reinterpret_cast<const uint4*>(db + j * otok) + sub) : z4;
+      oo = ld ? __ldg(reinterpret_cast<const uint4*>(ob + j * otok) + sub) : z4;
+    }
+    float s1 = PIPE ? abt_dot8(kk, qt) : abt_dot8(kk, qs);     // q_t . k_j      token j as a key of row t
+    float dp1 = PIPE ? abt_dot8(vv, dt) : abt_dot8(vv, ds);    // dO_t . v_j
+    float s2q = PIPE ? abt_dot8(qq, kt) : abt_dot8(qq, ks);    // q_j . k_t      token j as a query of column t
+    float dp2 = PIPE ? abt_dot8(dd, vt) : abt_dot8(dd, vs);    // dO_j . v_t
+    float dl = abt_dot8b(dd, oo);    // delta_j = dO_j . O_j
+    s1 = abt_group_sum<LPR>(s1, grp * LPR);
+    dp1 = abt_group_sum<LPR>(dp1, grp * LPR);
+    s2q = abt_group_sum<LPR>(s2q, grp * LPR);
+    dp2 = abt_group_sum<LPR>(dp2, grp * LPR);
+    dl = abt_group_sum<LPR>(dl, grp * LPR);
     const float p1 = ok ? fast_exp2(fmaf(s1, s2, -lse_t2)) : 0.f;   // P(t, j)
     const float ds1 = p1 * (dp1 - delta_t);                          // dS(t, j)
     const float p2 = ok ? fast_exp2(fmaf(s2q, s2, -lse_j2)) : 0.f;  // P(j, t)
@@ -711,7 +795,7 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
         stats[(bh * 2 + 1) * Lp + j] = -dl;
       }
     }
-    if (sub == 0 && j < Lm) {
+    if (sub == 0 && ok && j < Lm) {
       wsb[j] = ds2;              // dS(i, t)  -> dQ_i += scale dS(i, t) k_t
       wsb[Lm + j] = p1;          // P(t, j)   -> dV_j += P(t, j) dO_t
       wsb[2 * Lm + j] = ds1;     // dS(t, j)  -> dK_j += scale dS(t, j) q_t
@@ -719,12 +803,18 @@ attention_bwd_tail_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bflo
   }
   // rows of the warp (lanes with the same dims), then warps through shared memory, both in a fixed order: deterministic
 #pragma unroll
-  for (int off = LPR; off < 32; off <<= 1) {
+  for (int e = 0; e < 8; ++e) {
+    if (LPR == 8) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], off);
-      ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], off);
-      av[e] += __shfl_xor_sync(0xffffffffu, av[e], off);
+      for (int off = 8; off < 32; off <<= 1) {
+        aq[e] += __shfl_xor_sync(0xffffffffu, aq[e], off);
+        ak[e] += __shfl_xor_sync(0xffffffffu, ak[e], off);
+        av[e] += __shfl_xor_sync(0xffffffffu, av[e], off);
+      }
+    } else {   // groups at lanes 0, 10, 20 (the accumulators of lanes 30, 31 are zero and are never read)
+      aq[e] += __shfl_down_sync(0xffffffffu, aq[e], 10) + __shfl_down_sync(0xffffffffu, aq[e], 20);
+      ak[e] += __shfl_down_sync(0xffffffffu, ak[e], 10) + __shfl_down_sync(0xffffffffu, ak[e], 20);
+      av[e] += __shfl_down_sync(0xffffffffu, av[e], 10) + __shfl_down_sync(0xffffffffu, av[e], 20);
     }
   }
   if (grp == 0) {
@@ -937,15 +1027,21 @@ static int attention_bwd_impl(const void* qkv, const void* out, const void* dout
   float* stats = v2 ? acc + static_cast<long long>(B) * L * H * hd : nullptr;
   const int Lp = (Lm + AB_T - 1) / AB_T * AB_T;
   if (tail) {
+    static PerDeviceOnce tail_once;
+    if (tail_once.need()) {
+      cudaError_t e = cudaFuncSetAttribute(attention_bwd_tail_kernel<10, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABT_STAGE_BYTES);
+      if (e != cudaSuccess) return set_error(OVK_ERR_CUDA, "cudaFuncSetAttribute(attention_bwd_tail): %s", cudaGetErrorString(e));
+      tail_once.done();
+    }
     auto q_ = reinterpret_cast<const __nv_bfloat16*>(qkv);
     auto o_ = reinterpret_cast<const __nv_bfloat16*>(out);
     auto d_ = reinterpret_cast<const __nv_bfloat16*>(dout);
     float* dl_ = fused ? delta : nullptr;   // the two-pass dQ kernel computes delta itself
     if (hd == 64)
-      attention_bwd_tail_kernel<8><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
+      attention_bwd_tail_kernel<8, false><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
                                                                     scale, dl_, stats, Lp);
     else
-      attention_bwd_tail_kernel<16><<<dim3(H, B), ABT_THREADS, 0, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
+      attention_bwd_tail_kernel<10, true><<<dim3(H, B), ABT_THREADS, ABT_STAGE_BYTES, s>>>(q_, o_, d_, lse, reinterpret_cast<__nv_bfloat16*>(dqkv), workspace, L, H, hd,
                                                                      scale, dl_, stats, Lp);
     if ((rc = check_launch("attention_bwd_tail_kernel"))) return rc;
   }
