@@ -151,6 +151,32 @@ def test_attention_bwd_full_size_invariants(ops, B, L, H, hd):
         assert_grad(d5[bi, :, i, hi].cpu(), qf.grad[:, i], f"full-size d{name} of image {bi} head {hi}", 3e-2)
 
 
+@pytest.mark.parametrize("B,L,H,hd", [(3, 257, 2, 64), (2, 577, 3, 64), (2, 257, 3, 80), (2, 200, 2, 72), (5, 77, 2, 64)])
+def test_attention_bwd_one_pass_stays_inside_its_buffers(ops, B, L, H, hd):
+    """ovk_attention_bwd_fused through the C ABI with canaries behind the workspace it declares (remainder-token vectors,
+    fp32 dQ accumulator, per-query statistics), behind delta and behind dqkv: nothing past the declared sizes is written."""
+    from openvision_b200 import _lib
+    lib = _lib.load()
+    qkv = rnd(B * L, 3 * H * hd, seed=L).bfloat16().cuda()
+    dout = rnd(B * L, H * hd, seed=L + 1).bfloat16().cuda()
+    out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+    n = lib.ovk_attention_bwd_fused_workspace_floats(B, L, H, hd, 0)
+    assert n > 0
+    pad = 4096
+    ws = torch.full((n + pad,), 777.0, dtype=torch.float32, device="cuda")
+    delta = torch.full((B * H * L + pad,), 777.0, dtype=torch.float32, device="cuda")
+    dq = torch.full((B * L * 3 * H * hd + pad,), 3.0, dtype=torch.bfloat16, device="cuda")
+    for flags in (4, 0, 2):   # 8 compute warps (what the Python mirror passes), 16, the first one-pass kernel
+        _lib.call("ovk_attention_bwd_fused", qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dq.data_ptr(),
+                  delta.data_ptr(), ws.data_ptr(), B, L, H, hd, 1.0 / math.sqrt(hd), flags, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert bool((ws[n:] == 777.0).all()), f"flags {flags}: write past the workspace"
+        assert bool((delta[B * H * L:] == 777.0).all()), f"flags {flags}: write past delta"
+        assert bool((dq[B * L * 3 * H * hd:] == 3.0).all()), f"flags {flags}: write past dqkv"
+        ref = ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd)
+        assert_grad(dq[:B * L * 3 * H * hd].view(B * L, 3 * H * hd), ref, f"flags {flags}: C-ABI call vs the Python mirror", 2e-2)
+
+
 def test_h14_style_tower_forward_backward_vs_oracle():
     """head width 80 (H/14, BASELINE configs[4]) end to end at toy size: embeddings and image / parameter gradients
     against autograd of the CPU oracle (no golden fixture for this config: the oracle is pinned on the others)."""
