@@ -19,7 +19,12 @@ rows = list(csv.reader(io.StringIO(src)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi]
 idx = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) >= len(hdr)]
+data = []
+for r in rows[hi + 1:]:   # the first kernel of the report only (a second one repeats the header)
+    if r and r[0] == "Address":
+        break
+    if len(r) >= len(hdr):
+        data.append(r)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {s: 0 for s in stalls}
 for r in data:
