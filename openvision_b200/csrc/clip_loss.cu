@@ -22,10 +22,14 @@ constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 constexpr float NEG_INF = -INFINITY;
 
+// Warp maximum with ONE redux instruction on an order-preserving integer key (negatives: all bits flipped, the rest: sign bit
+// flipped) instead of five dependent shuffle + max steps: the reference offset of every 32 x 32 sub-block waits for it, and the
+// epilogue of the forward kernel is latency-bound (profiles: wait / short-scoreboard stalls, tensor pipe 70-77 %).
 __device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  const uint32_t b = __float_as_uint(v);
+  uint32_t k = b ^ (static_cast<uint32_t>(static_cast<int32_t>(b) >> 31) | 0x80000000u);
+  k = __reduce_max_sync(0xffffffffu, k);
+  return __uint_as_float(k ^ (((k >> 31) - 1u) | 0x80000000u));
 }
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
