@@ -177,6 +177,20 @@ def test_attention_bwd_one_pass_stays_inside_its_buffers(ops, B, L, H, hd):
         assert_grad(dq[:B * L * 3 * H * hd].view(B * L, 3 * H * hd), ref, f"flags {flags}: C-ABI call vs the Python mirror", 2e-2)
 
 
+@pytest.mark.parametrize("B,L,H,hd", [(160, 577, 12, 64), (300, 257, 16, 64), (100, 257, 16, 80)])
+def test_attention_bwd_one_pass_is_deterministic(ops, B, L, H, hd):
+    """Every reduction of the one-pass backward has a fixed order (dQ partial sums: one warp per accumulator block, key tiles
+    in order, each TMA reduce-add issued after the previous one COMPLETED; the remainder-token kernel: fixed-order block
+    reductions): repeated calls are bitwise identical.  A race in the tile kernel's pipeline would show up here as well
+    (several work items per CTA, items crossing (image, head) boundaries); tools/attn_bwd_stress.py is the longer version."""
+    qkv = (rnd(B * L, 3 * H * hd, seed=B) * 0.5).bfloat16().cuda()
+    dout = rnd(B * L, H * hd, seed=B + 1).bfloat16().cuda()
+    out, lse = ops.attention(qkv, B, L, H, hd, save_lse=True)
+    first = ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd)
+    for _ in range(6):
+        assert torch.equal(ops.attention_bwd(qkv, out, dout, lse, B, L, H, hd), first)
+
+
 def test_h14_style_tower_forward_backward_vs_oracle():
     """head width 80 (H/14, BASELINE configs[4]) end to end at toy size: embeddings and image / parameter gradients
     against autograd of the CPU oracle (no golden fixture for this config: the oracle is pinned on the others)."""
